@@ -1,0 +1,126 @@
+"""Oracle: DeepLabV3+ (ResNet-50/101, output_stride 16) forward + input gradient
+(TEST INFRASTRUCTURE, see oracle/__init__.py).
+
+Functional fp32 restatement driven by a reference-format state_dict:
+  seg_model/network/backbone/resnet.py  Bottleneck.forward :98-118, ResNet._make_layer :164-194,
+                                        stem :142-153
+  seg_model/network/_deeplab.py         DeepLabHeadV3Plus.forward :47-51, ASPP.forward :157-162,
+                                        ASPPPooling.forward :128-131
+  seg_model/network/utils.py            _SimpleSegmentationModel.forward :13-18
+  seg_model/network/modeling.py         _segm_resnet :32-58 (os=16: dilate layer4, ASPP rates 6/12/18)
+  seg_model/inference.py                infer :118-152 (CE ignore_index=255, gradient wrt the input)
+"""
+import torch
+import torch.nn.functional as F
+
+LAYERS = {"resnet50": [3, 4, 6, 3], "resnet101": [3, 4, 23, 3]}
+
+
+def _bn(sd, p, x):
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        False, 0.0, 1e-5)
+
+
+def _bottleneck(sd, p, x, stride, dilation, has_down):
+    out = F.relu(_bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv1.weight"])))
+    out = F.conv2d(out, sd[p + ".conv2.weight"], stride=stride, padding=dilation, dilation=dilation)
+    out = F.relu(_bn(sd, p + ".bn2", out))
+    out = _bn(sd, p + ".bn3", F.conv2d(out, sd[p + ".conv3.weight"]))
+    idt = x
+    if has_down:
+        idt = _bn(sd, p + ".downsample.1", F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride))
+    return F.relu(out + idt)
+
+
+def block_plan(backbone="resnet50"):
+    """[(prefix, inplanes, planes, stride, dilation, has_down)] for os=16 (replace_stride_with_dilation=[F,F,T])."""
+    plan, inplanes, dilation = [], 64, 1
+    for li, (planes, nblocks, stride, dilate) in enumerate(
+            zip([64, 128, 256, 512], LAYERS[backbone], [1, 2, 2, 2], [False, False, False, True])):
+        prev = dilation
+        if dilate:
+            dilation *= stride
+            stride = 1
+        for b in range(nblocks):
+            first = b == 0
+            has_down = first and (stride != 1 or inplanes != planes * 4)
+            plan.append((f"backbone.layer{li + 1}.{b}", inplanes, planes, stride if first else 1,
+                         prev if first else dilation, has_down))
+            inplanes = planes * 4
+    return plan
+
+
+def deeplab_forward(sd, x, backbone="resnet50", taps=None):
+    """x [B,3,H,W] -> logits [B,nc,H,W]."""
+    H, W = x.shape[-2:]
+    h = F.relu(_bn(sd, "backbone.bn1", F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=3)))
+    h = F.max_pool2d(h, 3, 2, 1)
+    low = None
+    for (p, _, _, stride, dil, has_down) in block_plan(backbone):
+        h = _bottleneck(sd, p, h, stride, dil, has_down)
+        if p.startswith("backbone.layer1.") and p.endswith(str(LAYERS[backbone][0] - 1)):
+            low = h
+    if taps is not None:
+        taps["low"], taps["out"] = low, h
+    c = "classifier"
+    ll = F.relu(_bn(sd, c + ".project.1", F.conv2d(low, sd[c + ".project.0.weight"])))
+    res = [F.relu(_bn(sd, c + ".aspp.convs.0.1", F.conv2d(h, sd[c + ".aspp.convs.0.0.weight"])))]
+    for k, r in zip((1, 2, 3), (6, 12, 18)):
+        res.append(F.relu(_bn(sd, f"{c}.aspp.convs.{k}.1",
+                              F.conv2d(h, sd[f"{c}.aspp.convs.{k}.0.weight"], padding=r, dilation=r))))
+    g = F.adaptive_avg_pool2d(h, 1)
+    g = F.relu(_bn(sd, c + ".aspp.convs.4.2", F.conv2d(g, sd[c + ".aspp.convs.4.1.weight"])))
+    res.append(F.interpolate(g, size=h.shape[-2:], mode="bilinear", align_corners=False))
+    a = F.relu(_bn(sd, c + ".aspp.project.1", F.conv2d(torch.cat(res, 1), sd[c + ".aspp.project.0.weight"])))
+    a = F.interpolate(a, size=ll.shape[-2:], mode="bilinear", align_corners=False)
+    y = F.relu(_bn(sd, c + ".classifier.1", F.conv2d(torch.cat([ll, a], 1), sd[c + ".classifier.0.weight"], padding=1)))
+    y = F.conv2d(y, sd[c + ".classifier.3.weight"], sd[c + ".classifier.3.bias"])
+    if taps is not None:
+        taps["aspp"], taps["logits_lowres"] = a, y
+    return F.interpolate(y, size=(H, W), mode="bilinear", align_corners=False)
+
+
+def infer(sd, x, labels, backbone="resnet50"):
+    """seg_model/inference.py:118-152 for B=1 (looped per image for B>1).
+    Returns (pred int64 [B,H,W], input_grad [B,3,H,W], loss [B])."""
+    preds, grads, losses = [], [], []
+    for b in range(x.shape[0]):
+        xb = x[b:b + 1].detach().clone().requires_grad_(True)
+        out = deeplab_forward(sd, xb, backbone)
+        preds.append(out.argmax(1))
+        loss = F.cross_entropy(out, labels[b:b + 1], ignore_index=255)
+        g, = torch.autograd.grad(loss, xb)
+        grads.append(g); losses.append(loss.detach())
+    return torch.cat(preds), torch.cat(grads), torch.stack(losses)
+
+
+def deeplab_param_spec(backbone="resnet50", num_classes=19):
+    f32, i64 = torch.float32, torch.int64
+    spec = {}
+
+    def conv(p, o, i, k):
+        spec[p + ".weight"] = ((o, i, k, k), f32)
+
+    def bn(p, c):
+        spec[p + ".weight"] = ((c,), f32); spec[p + ".bias"] = ((c,), f32)
+        spec[p + ".running_mean"] = ((c,), f32); spec[p + ".running_var"] = ((c,), f32)
+        spec[p + ".num_batches_tracked"] = ((), i64)
+
+    conv("backbone.conv1", 64, 3, 7); bn("backbone.bn1", 64)
+    for (p, inpl, planes, stride, dil, has_down) in block_plan(backbone):
+        conv(p + ".conv1", planes, inpl, 1); bn(p + ".bn1", planes)
+        conv(p + ".conv2", planes, planes, 3); bn(p + ".bn2", planes)
+        conv(p + ".conv3", planes * 4, planes, 1); bn(p + ".bn3", planes * 4)
+        if has_down:
+            conv(p + ".downsample.0", planes * 4, inpl, 1); bn(p + ".downsample.1", planes * 4)
+    c = "classifier"
+    conv(c + ".project.0", 48, 256, 1); bn(c + ".project.1", 48)
+    conv(c + ".aspp.convs.0.0", 256, 2048, 1); bn(c + ".aspp.convs.0.1", 256)
+    for k in (1, 2, 3):
+        conv(f"{c}.aspp.convs.{k}.0", 256, 2048, 3); bn(f"{c}.aspp.convs.{k}.1", 256)
+    conv(c + ".aspp.convs.4.1", 256, 2048, 1); bn(c + ".aspp.convs.4.2", 256)
+    conv(c + ".aspp.project.0", 256, 1280, 1); bn(c + ".aspp.project.1", 256)
+    conv(c + ".classifier.0", 256, 304, 3); bn(c + ".classifier.1", 256)
+    spec[c + ".classifier.3.weight"] = ((num_classes, 256, 1, 1), f32)
+    spec[c + ".classifier.3.bias"] = ((num_classes,), f32)
+    return spec

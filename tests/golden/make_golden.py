@@ -1,0 +1,227 @@
+"""Generate the golden fixtures in tests/golden/*.pt from the UNMODIFIED reference.
+
+Runs only where /root/reference exists (the build container):
+    python tests/golden/make_golden.py
+Every tensor below is produced by the reference's own modules/functions (imported through
+ref_shim); the oracle is NOT involved.  Weights come from oracle.weights.synth_state_dict, a pure
+function of (name, shape, seed), loaded into the reference modules with load_state_dict.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+import io  # noqa: E402
+import contextlib  # noqa: E402
+import torch  # noqa: E402
+from oracle.weights import synth_state_dict  # noqa: E402
+from oracle.unet import DEFAULT_MODEL_CONFIG  # noqa: E402
+
+from diffusion_model.models.unet_base import Unet, get_time_embedding  # noqa: E402
+from diffusion_model.config.models import ModelConfig  # noqa: E402
+from diffusion_model.scheduler.linear_noise_scheduler import LinearNoiseScheduler  # noqa: E402
+import seg_model.network as network  # noqa: E402
+import seg_model.inference as seg_infer  # noqa: E402
+from srgan_model.models import Generator  # noqa: E402
+import srgan_model.inference as srgan_infer  # noqa: E402
+from sgg.sgg import apply_gsg  # noqa: E402
+
+torch.set_num_threads(os.cpu_count())
+
+
+def save(name, obj):
+    path = os.path.join(HERE, name)
+    torch.save(obj, path)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+class InjectedRandn:
+    """Patch torch.randn so the scheduler's CPU draw (scheduler.py:110) returns a recorded tensor."""
+
+    def __init__(self, zs):
+        self.zs, self.i, self.orig = list(zs), 0, torch.randn
+
+    def __enter__(self):
+        def fake(*a, **k):
+            z = self.zs[self.i]; self.i += 1
+            return z.clone()
+        torch.randn = fake
+        return self
+
+    def __exit__(self, *a):
+        torch.randn = self.orig
+
+
+def g_scheduler():
+    out = {}
+    for T in (1000, 50):
+        s = LinearNoiseScheduler(T, 1e-4, 0.02)
+        out[f"tables_{T}"] = {k: getattr(s, k).clone() for k in (
+            "betas", "alphas", "alpha_cum_prod", "sqrt_alpha_cum_prod", "one_minus_cum_prod",
+            "sqrt_one_minus_alpha_cum_prod")}
+    s = LinearNoiseScheduler(1000, 1e-4, 0.02)
+    g = torch.Generator().manual_seed(11)
+    x0 = torch.rand(3, 3, 8, 16, generator=g) * 2 - 1
+    eps = torch.randn(3, 3, 8, 16, generator=g)
+    t = torch.tensor([0, 499, 999])
+    out["x0"], out["eps"], out["t"] = x0, eps, t
+    out["add_noise"] = s.add_noise(x0, eps, t)
+    out["add_noise2"] = s.add_noise2(x0, eps, t)
+    steps = {}
+    for ti in (0, 1, 10, 499, 999):
+        z = torch.randn(3, 3, 8, 16, generator=g)
+        with InjectedRandn([z]):
+            mean, sig, _ = s.sample_prev_timestep(x0, eps, torch.as_tensor(ti))
+        steps[ti] = dict(z=z, mean=mean, sigma_z=sig)
+    out["sample_prev_timestep"] = steps
+    tb = torch.tensor([0, 5, 999])
+    z = torch.randn(3, 3, 8, 16, generator=g)
+    with InjectedRandn([z]):
+        mean, sig, _ = s.sample_prev_timestep2(x0, eps, tb)
+    out["sample_prev_timestep2"] = dict(t=tb, z=z, mean=mean, sigma_z=sig)
+    out["time_embedding"] = get_time_embedding(torch.arange(0, 1000, 37), 128)
+    save("scheduler.pt", out)
+
+
+def unet_for(cfg, seed):
+    m = Unet(ModelConfig(**cfg)).eval()
+    sd = synth_state_dict(m.state_dict(), seed)
+    m.load_state_dict(sd)
+    return m
+
+
+def g_unet():
+    out = {}
+    g = torch.Generator().manual_seed(5)
+    for tag, ims, shape, t in (("im64_b2_64x64", 64, (2, 3, 64, 64), [7]),
+                               ("im128_b2_32x64", 128, (2, 3, 32, 64), [3, 500]),
+                               ("im128_b1_64x128", 128, (1, 3, 64, 128), [999])):
+        cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = ims
+        m = unet_for(cfg, 3455)
+        x = torch.randn(shape, generator=g)
+        with torch.no_grad():
+            y = m(x, torch.tensor(t))
+        out[tag] = dict(cfg=cfg, seed=3455, x=x, t=torch.tensor(t), y=y)
+        print(tag, float(y.std()))
+    save("unet_forward.pt", out)
+
+
+def g_sample():
+    """sample_ddpm.sample loop (sample_ddpm.py:35-44) B=2, 32x32, T=12, im_size=64, recorded noise."""
+    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = 64
+    m = unet_for(cfg, 3455)
+    T = 12
+    s = LinearNoiseScheduler(T, 1e-4, 0.02)
+    g = torch.Generator().manual_seed(21)
+    xT = torch.randn(2, 3, 32, 32, generator=g)
+    zs = [torch.randn(2, 3, 32, 32, generator=g) for _ in range(T)]
+    traj = []
+    xt = xT
+    with torch.no_grad():
+        for i in reversed(range(T)):
+            eps = m(xt, torch.as_tensor(i).unsqueeze(0))
+            with InjectedRandn([zs[i]]):
+                mean, sigma, _ = s.sample_prev_timestep(xt, eps, torch.as_tensor(i))
+            xt = mean + sigma if i != 0 else mean
+            traj.append(xt.clone())
+    save("sample_traj.pt", dict(cfg=cfg, seed=3455, T=T, xT=xT, zs=torch.stack(zs), traj=torch.stack(traj)))
+
+
+def seg_for(backbone, seed):
+    m = network.modeling.__dict__["deeplabv3plus_" + backbone](num_classes=19, output_stride=16,
+                                                               pretrained_backbone=False).eval()
+    sd = synth_state_dict(m.state_dict(), seed)
+    m.load_state_dict(sd)
+    return m
+
+
+def block_labels(g, B, H, W, blk=8):
+    lab = torch.randint(0, 19, (B, H // blk, W // blk), generator=g)
+    ign = torch.rand(B, H // blk, W // blk, generator=g) < 0.05
+    lab[ign] = 255
+    return lab.repeat_interleave(blk, 1).repeat_interleave(blk, 2)
+
+
+def g_seg():
+    out = {}
+    g = torch.Generator().manual_seed(31)
+    for backbone, (H, W) in (("resnet50", (64, 128)), ("resnet50", (128, 256)), ("resnet101", (64, 128))):
+        m = seg_for(backbone, 42)
+        x = torch.rand(1, 3, H, W, generator=g)
+        gt = block_labels(g, 1, H, W)
+        feats = {}
+        hook = m.classifier.classifier.register_forward_hook(lambda mod, i, o: feats.__setitem__("low", o.detach()))
+        with contextlib.redirect_stdout(io.StringIO()):
+            pred, grad, _ = seg_infer.infer(m, x.clone(), gt)
+        hook.remove()
+        out[f"{backbone}_{H}x{W}"] = dict(seed=42, x=x, gt=gt, logits_lowres=feats["low"],
+                                           pred=torch.from_numpy(pred).to(torch.uint8), grad=grad.detach().clone())
+        print(backbone, H, W, float(grad.abs().max()))
+    save("seg_infer.pt", out)
+
+
+def g_srgan():
+    G = Generator(upscale_factor=4).eval()
+    sd = synth_state_dict(G.state_dict(), 0)
+    G.load_state_dict(sd)
+    g = torch.Generator().manual_seed(41)
+    x = torch.rand(2, 3, 16, 32, generator=g) * 2 - 1
+    y = srgan_infer.inference(G, x)
+    save("srgan.pt", dict(seed=0, x=x, y=y))
+    return G
+
+
+def g_gsg_and_driver(G):
+    """apply_gsg (sgg.py:9-24) on one image and the repaired sample_with_sgg driver for 3 steps."""
+    out = {}
+    g = torch.Generator().manual_seed(51)
+    seg = seg_for("resnet50", 42)
+    h, w = 16, 32
+    mu = torch.randn(1, 3, h, w, generator=g)
+    sig = 0.1 * torch.randn(1, 3, h, w, generator=g)
+    sr = torch.rand(1, 3, 4 * h, 4 * w, generator=g)
+    gt = block_labels(g, 1, 4 * h, 4 * w)
+    with contextlib.redirect_stdout(io.StringIO()):
+        xt = apply_gsg(seg, mu, sig, sr.clone(), gt, 60.0)
+    out["gsg"] = dict(mu=mu, sigma=sig, sr_xt=sr, gt=gt, lam=60.0, xt=xt)       # xt is float64 (D7)
+    # repaired driver
+    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = 64
+    m = unet_for(cfg, 3455)
+    N = 3
+    s = LinearNoiseScheduler(1000, 1e-4, 0.02)
+    x0 = torch.rand(1, 3, h, w, generator=g) * 2 - 1
+    noise = torch.randn(1, 3, h, w, generator=g)
+    t_fwd = torch.tensor([N - 1])
+    zs = [torch.randn(1, 3, h, w, generator=g) for _ in range(N)]
+    traj = []
+    with torch.no_grad():
+        xt = s.add_noise2(x0, noise, t_fwd)
+        for i in reversed(range(N)):
+            eps = m(xt, torch.as_tensor(i).unsqueeze(0))
+            with InjectedRandn([zs[i]]):
+                mu_, sigma_, _ = s.sample_prev_timestep(xt, eps, torch.as_tensor(i))
+            if i == 0:
+                xt = mu_
+            else:
+                sr_xt = srgan_infer.inference(G, xt)
+                with torch.enable_grad(), contextlib.redirect_stdout(io.StringIO()):
+                    xt = apply_gsg(seg, mu_, sigma_, sr_xt, gt, 60.0).float()
+            traj.append(xt.clone())
+        sr_x0 = srgan_infer.inference(G, xt)
+    out["driver"] = dict(cfg=cfg, unet_seed=3455, seg_seed=42, srgan_seed=0, N=N, x0=x0, noise=noise, t_fwd=t_fwd,
+                         zs=torch.stack(zs), gt=gt, traj=torch.stack(traj), sr_x0=sr_x0)
+    save("sgg.pt", out)
+
+
+if __name__ == "__main__":
+    g_scheduler()
+    g_unet()
+    g_sample()
+    g_seg()
+    G = g_srgan()
+    g_gsg_and_driver(G)

@@ -1,0 +1,93 @@
+"""Pin the CPU oracle against golden vectors produced by the reference's own modules
+(tests/golden/make_golden.py).  Runs on CPU; no CUDA involved."""
+import torch
+
+from oracle import deeplab, sgg, srgan, unet
+from oracle.scheduler import OracleScheduler
+from oracle.weights import synth_state_dict
+
+
+def test_scheduler_tables_exact(golden):
+    g = golden("scheduler.pt")
+    for T in (1000, 50):
+        s = OracleScheduler(T, 1e-4, 0.02)
+        for k, v in g[f"tables_{T}"].items():
+            assert torch.equal(getattr(s, k), v), k
+
+
+def test_scheduler_steps(golden):
+    g = golden("scheduler.pt")
+    s = OracleScheduler(1000, 1e-4, 0.02)
+    assert torch.equal(s.add_noise(g["x0"], g["eps"], g["t"]), g["add_noise"])
+    assert torch.equal(s.add_noise2(g["x0"], g["eps"], g["t"]), g["add_noise2"])
+    for ti, d in g["sample_prev_timestep"].items():
+        mean, sz, _ = s.sample_prev_timestep(g["x0"], g["eps"], ti, z=d["z"])
+        assert torch.equal(mean, d["mean"])
+        if ti == 0:
+            assert sz is None and d["sigma_z"] is None
+        else:
+            assert torch.equal(sz, d["sigma_z"])
+    d = g["sample_prev_timestep2"]
+    mean, sz, _ = s.sample_prev_timestep2(g["x0"], g["eps"], d["t"], z=d["z"])
+    assert torch.equal(mean, d["mean"]) and torch.equal(sz, d["sigma_z"])
+    assert torch.equal(unet.get_time_embedding(torch.arange(0, 1000, 37), 128), g["time_embedding"])
+
+
+def test_unet_forward(golden):
+    g = golden("unet_forward.pt")
+    for tag, d in g.items():
+        sd = synth_state_dict(unet.unet_param_spec(d["cfg"]), d["seed"])
+        with torch.no_grad():
+            y = unet.unet_forward(sd, d["cfg"], d["x"], d["t"])
+        assert (y - d["y"]).abs().max() < 2e-5, tag
+
+
+def test_sample_trajectory(golden):
+    d = golden("sample_traj.pt")
+    sd = synth_state_dict(unet.unet_param_spec(d["cfg"]), d["seed"])
+    s = OracleScheduler(d["T"], 1e-4, 0.02)
+    xt = d["xT"]
+    with torch.no_grad():
+        for k, i in enumerate(reversed(range(d["T"]))):
+            eps = unet.unet_forward(sd, d["cfg"], xt, torch.tensor([i]))
+            mean, sz, _ = s.sample_prev_timestep(xt, eps, i, z=d["zs"][i])
+            xt = mean + sz if i != 0 else mean
+            assert (xt - d["traj"][k]).abs().max() < 1e-3, (k, float((xt - d["traj"][k]).abs().max()))
+
+
+def test_seg_infer(golden):
+    g = golden("seg_infer.pt")
+    for tag, d in g.items():
+        bb = tag.split("_")[0]
+        sd = synth_state_dict(deeplab.deeplab_param_spec(bb), d["seed"])
+        taps = {}
+        with torch.no_grad():
+            deeplab.deeplab_forward(sd, d["x"], bb, taps)
+        assert (taps["logits_lowres"] - d["logits_lowres"]).abs().max() < 1e-4, tag
+        pred, grad, _ = deeplab.infer(sd, d["x"], d["gt"], bb)
+        assert (pred[0].to(torch.uint8) == d["pred"]).float().mean() > 0.9999, tag
+        assert (grad - d["grad"]).abs().max() <= 1e-5 * d["grad"].abs().max() + 1e-9, tag
+
+
+def test_srgan(golden):
+    d = golden("srgan.pt")
+    sd = synth_state_dict(srgan.srgan_param_spec(), d["seed"])
+    with torch.no_grad():
+        y = srgan.generator_forward(sd, d["x"])
+    assert (y - d["y"]).abs().max() < 1e-5
+
+
+def test_gsg_and_repaired_driver(golden):
+    g = golden("sgg.pt")
+    d = g["gsg"]
+    seg_sd = synth_state_dict(deeplab.deeplab_param_spec("resnet50"), 42)
+    xt, _, _ = sgg.apply_gsg(seg_sd, d["mu"], d["sigma"], d["sr_xt"], d["gt"], d["lam"])
+    assert (xt.double() - d["xt"]).abs().max() < 1e-5
+    d = g["driver"]
+    usd = synth_state_dict(unet.unet_param_spec(d["cfg"]), d["unet_seed"])
+    gsd = synth_state_dict(srgan.srgan_param_spec(), d["srgan_seed"])
+    rec = []
+    out = sgg.sample_with_sgg(usd, d["cfg"], OracleScheduler(1000, 1e-4, 0.02), seg_sd, gsd, d["x0"], d["gt"],
+                              d["noise"], d["t_fwd"], list(d["zs"]), lam=60.0, n_steps=d["N"], record=rec)
+    assert (torch.stack(rec) - d["traj"]).abs().max() < 1e-3
+    assert (out - d["sr_x0"]).abs().max() < 1e-3
