@@ -1,0 +1,110 @@
+/* wc_b200.h - C ABI of the B200-native WeatherConverter hot path (libwc_b200.so).
+ *
+ * The reference (xXCoffeeColaXc/WeatherConverter) has no FFI: every arithmetic op on its hot path is a PyTorch
+ * call.  These entry points are what a maintainer would bind (ctypes) to replace those
+ * calls.  Conventions:
+ *   - every function returns 0 on success, non-zero on failure; wc_last_error() returns the message
+ *     (thread-local).  Nothing falls back to the CPU.
+ *   - pointers are raw DEVICE pointers unless the name ends in _host; `stream` is a cudaStream_t passed as
+ *     void* (NULL = default stream).  All work is stream-ordered; nothing synchronises the device.
+ *   - "nchw_f32" tensors use the reference's layout (fp32, NCHW, contiguous); "nhwc_bf16" tensors are the
+ *     internal activation layout: element (b,y,x,c) at ptr[((b*H+y)*W+x)*ld + c].
+ * Each entry cites the reference code it replaces (paths relative to the reference root).
+ */
+#ifndef WC_B200_H_
+#define WC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t wc_bf16; /* raw bfloat16 bits */
+
+const char* wc_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int wc_abi_version(void);
+/* Number of kernel launches issued by this library in the calling process so far (all entry points). */
+long long wc_launch_count(void);
+
+/* ---- DDPM scheduler (diffusion_model/scheduler/linear_noise_scheduler.py) ------------------------------ */
+/* :79-116 sample_prev_timestep + sample_ddpm.py:44.  mean = (xt - beta*eps/s)/sqrt_alpha ; out = mean + sigma*z.
+ * z == NULL -> t == 0 branch (out = mean).  mean_out / sigz_out / out may each be NULL.  Bit-exact vs fp32 torch. */
+int wc_ddpm_step(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
+                 size_t n_per_sample, int batch, float beta, float sqrt_one_minus_acp, float sqrt_alpha, float sigma,
+                 void* stream);
+/* :63-77 sample_prev_timestep2 (batched t [B] int64, sigma^2 = beta_t), tables are the scheduler's fp32 [T] arrays. */
+int wc_ddpm_step_batched(const float* xt, const float* eps, const float* z, float* out, float* mean_out,
+                         float* sigz_out, size_t n_per_sample, int batch, const float* betas, const float* alphas,
+                         const float* sqrt_one_minus_acp, const int64_t* t, void* stream);
+/* :30-35 add_noise2 / :37-61 add_noise. */
+int wc_add_noise(const float* x0, const float* noise, float* out, size_t n_per_sample, int batch,
+                 const float* sqrt_acp, const float* sqrt_one_minus_acp, const int64_t* t, void* stream);
+
+/* ---- guidance update (sgg/sgg.py:18-22, seg_model/inference.py:36-53) ------------------------------------ */
+/* grad [B,3,pool*h,pool*w] f32 ; mu, sigz, out [B,3,h,w] f32 ; mag_out [B,h,w] f32 or NULL. */
+int wc_sgg_update(const float* grad, const float* mu, const float* sigz, float* out, float* mag_out, int batch, int h,
+                  int w, int pool, float lambda, void* stream);
+
+/* ---- op-level building blocks (unit-test surface; the model-level calls below use the same kernels) ------ */
+/* nn.GroupNorm(8, C) [+ nn.SiLU] on NHWC bf16 (unet_base.py:89-90).  workspace >= wc_groupnorm_workspace_bytes. */
+size_t wc_groupnorm_workspace_bytes(int batch);
+int wc_groupnorm_silu(const wc_bf16* x, wc_bf16* y, int batch, int hw, int channels, int ldx, int ldy,
+                      const float* gamma, const float* beta, float eps, int silu, void* workspace, void* stream);
+/* nn.Conv2d / nn.ConvTranspose2d on the tcgen05 implicit-GEMM path (unet_base.py:91-95,129,333; resnet.py:90).
+ * x nhwc_bf16 [B,H,W,Cin]; weight fp32 PyTorch layout ([Cout,Cin,K,K], or [Cin,Cout,K,K] when transposed != 0);
+ * bias fp32 [Cout] or NULL; rowbias fp32 [B,Cout] or NULL (t-embedding add, unet_base.py:148); residual
+ * nhwc_bf16 on the output grid or NULL; x2/weight2 (may be NULL): fused 1x1 convolution of a second input
+ * (unet_base.py:150).  stride in {1,2}; stride 1 needs 2*pad == dil*(K-1).  Cout must be a multiple of 16. */
+int wc_conv2d(const wc_bf16* x, int batch, int H, int W, int Cin, int ldx, const float* weight, const float* bias,
+              int Cout, int K, int stride, int pad, int dil, int transposed, const float* rowbias,
+              const wc_bf16* residual, int ldr, const wc_bf16* x2, int Cin2, int ldx2, const float* weight2, int relu,
+              wc_bf16* y, int ldy, void* stream);
+/* 3-channel boundary convolutions on CUDA cores: conv_in (unet_base.py:399) NCHW f32 -> NHWC bf16, optional
+ * folded-BN scale/shift + ReLU (resnet.py:142-145); conv_out (unet_base.py:449) NHWC bf16 -> NCHW f32. */
+int wc_conv_in(const float* x, const float* weight, const float* bias, const float* scale, const float* shift,
+               wc_bf16* y, int batch, int H, int W, int Cout, int K, int stride, int pad, int ldy, int relu,
+               void* stream);
+int wc_conv_out(const wc_bf16* x, const float* weight, const float* bias, float* y, int batch, int H, int W, int Cin,
+                int K, int ldx, int tanh_out, void* stream);
+/* layout converters between the reference boundary layout and the internal one */
+int wc_nchw_f32_to_nhwc_bf16(const float* x, wc_bf16* y, int batch, int C, int hw, int ldy, void* stream);
+int wc_nhwc_bf16_to_nchw_f32(const wc_bf16* x, float* y, int batch, int C, int hw, int ldx, void* stream);
+/* nn.MultiheadAttention core (unet_base.py:159): softmax(q k^T / sqrt(hd)) v per (batch, head), flash-style on
+ * tcgen05.  q,k: [B,heads,ntok,hd] bf16; vt: [B,heads,hd,ntok] bf16; out: [B,ntok,heads*hd] bf16 (ldo). */
+int wc_attention(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, int batch, int heads, int ntok,
+                 int hd, int ldo, void* stream);
+
+/* ---- model-level: UNet (diffusion_model/models/unet_base.py:372-488) ------------------------------------- */
+typedef struct wc_unet wc_unet;
+typedef struct {
+  int im_channels, im_size, time_emb_dim, num_down_layers, num_mid_layers, num_up_layers, num_heads;
+  int n_down_channels;
+  int down_channels[8];
+  int n_mid_channels;
+  int mid_channels[8];
+  int down_sample[8];
+  int n_attn_resolutions;
+  int attn_resolutions[8];
+} wc_unet_config;
+/* names/ptrs: the reference state_dict (382 fp32 device tensors for config.yaml), read once and re-packed. */
+int wc_unet_create(wc_unet** out, const wc_unet_config* cfg, int n_params, const char* const* names,
+                   const float* const* ptrs, const int64_t* numels, void* stream);
+void wc_unet_destroy(wc_unet* net);
+/* Bytes of activation workspace needed by wc_unet_forward for a [batch,3,H,W] input. */
+size_t wc_unet_workspace_bytes(const wc_unet* net, int batch, int H, int W);
+/* Unet.forward(x, t) (unet_base.py:451-488): x, out nchw_f32 [B,3,H,W]; t int64 device [n_t], n_t in {1, B}.
+ * The first call for a (batch,H,W,workspace) binds tensor maps; later calls with the same binding only launch. */
+int wc_unet_forward(wc_unet* net, const float* x, const int64_t* t, int n_t, float* out, int batch, int H, int W,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* Algorithmic FLOPs (2*MAC, conv + linear + attention matmuls) of the last bound forward, per call. */
+double wc_unet_flops(const wc_unet* net);
+/* Kernel launches per forward of the last bound shape. */
+int wc_unet_launches(const wc_unet* net);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WC_B200_H_ */

@@ -1,0 +1,192 @@
+#include "conv.cuh"
+
+#include <algorithm>
+
+namespace wc {
+
+int pack_tap(__nv_bfloat16* dst, int ldk, int koff, const float* src, int Nn, int Cc, int Cpad, int KH, int KW, int ky,
+             int kx, int transpose, const float* scale, cudaStream_t st);
+
+DeviceArena::~DeviceArena() {
+  for (void* p : ptrs_) cudaFree(p);
+}
+void* DeviceArena::alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    set_error("cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+    return nullptr;
+  }
+  ptrs_.push_back(p);
+  total_ += bytes;
+  return p;
+}
+
+namespace {
+
+struct TapDef {
+  int map, dy, dx;
+  const WeightSrc* w;
+  int ky, kx;
+  int C;  // true input channels of this tap
+};
+
+int out_channels_of(const WeightSrc& w) { return w.transpose ? w.d1 : w.d0; }
+int in_channels_of(const WeightSrc& w) { return w.transpose ? w.d0 : w.d1; }
+
+// Pack weights for a tap list and fill everything of the plan except the A tensor maps.
+int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& taps, int B, int H, int W, int tb,
+                int th, int tw, int N, const Epilogue& ep, const OutSpec& out, int sy, int sx, int py, int px,
+                cudaStream_t st) {
+  WC_REQUIRE(N % 16 == 0, "igemm needs N % 16 == 0 (pad the output channels)");
+  WC_REQUIRE(static_cast<int>(taps.size()) <= kMaxTaps && !taps.empty(), "tap count out of range");
+  IgemmArgs& a = plan->args;
+  a = IgemmArgs{};
+  a.B = B; a.H = H; a.W = W; a.tb = tb; a.th = th; a.tw = tw;
+  a.N = N;
+  int total_kb = 0;
+  a.ntaps = static_cast<int>(taps.size());
+  for (size_t i = 0; i < taps.size(); ++i) {
+    const int nkb = (taps[i].C + kIgemmBK - 1) / kIgemmBK;
+    a.taps[i].map = static_cast<int8_t>(taps[i].map);
+    a.taps[i].dy = static_cast<int8_t>(taps[i].dy);
+    a.taps[i].dx = static_cast<int8_t>(taps[i].dx);
+    a.taps[i].nkb = nkb;
+    total_kb += nkb;
+  }
+  a.total_kb = total_kb;
+  const int ktotal = total_kb * kIgemmBK;
+  const long m_tiles = static_cast<long>((W + tw - 1) / tw) * ((H + th - 1) / th) * ((B + tb - 1) / tb);
+  a.BN = igemm_pick_bn(N, m_tiles);
+  if (out.mode == kOutQKV) {
+    WC_REQUIRE(out.hd % 16 == 0, "head_dim must be a multiple of 16");
+  }
+  // ---- weights
+  auto* wp = static_cast<__nv_bfloat16*>(arena->alloc(static_cast<size_t>(N) * ktotal * sizeof(__nv_bfloat16)));
+  if (!wp) return 1;
+  int koff = 0;
+  double macs_per_pixel = 0;
+  for (const TapDef& t : taps) {
+    const WeightSrc& w = *t.w;
+    const int n_src = out_channels_of(w);
+    WC_REQUIRE(n_src <= N, "weight has more output channels than N");
+    const int cpad = (t.C + kIgemmBK - 1) / kIgemmBK * kIgemmBK;
+    const int ky = w.flip ? w.KH - 1 - t.ky : t.ky, kx = w.flip ? w.KW - 1 - t.kx : t.kx;
+    if (int e = pack_tap(wp, ktotal, koff, w.w, n_src, t.C, cpad, w.KH, w.KW, ky, kx, w.transpose, w.scale, st)) return e;
+    koff += cpad;
+    macs_per_pixel += static_cast<double>(t.C) * n_src;
+  }
+  if (int e = igemm_make_bmap(&plan->maps.b, wp, N, ktotal, a.BN)) return e;
+  // zero rows [n_src, N) if any (arena memory is uninitialised)
+  {
+    const int n_src = out_channels_of(*taps[0].w);
+    if (n_src < N)
+      WC_CHECK_CUDA(cudaMemsetAsync(wp + static_cast<size_t>(n_src) * ktotal, 0,
+                                    static_cast<size_t>(N - n_src) * ktotal * sizeof(__nv_bfloat16), st));
+  }
+  // ---- epilogue
+  a.bias = ep.bias;
+  a.rowbias = ep.rowbias; a.ldrb = ep.ldrb;
+  if (ep.res) {
+    WC_REQUIRE(ep.res->B == B && ep.res->H == H * sy && ep.res->W == W * sx, "residual grid mismatch");
+    a.res = ep.res->ptr; a.ldr = ep.res->ld;
+  }
+  if (ep.mask) {
+    WC_REQUIRE(ep.mask->B == B && ep.mask->H == H * sy && ep.mask->W == W * sx, "mask grid mismatch");
+    a.mask = ep.mask->ptr; a.ldm = ep.mask->ld;
+  }
+  a.relu = ep.relu;
+  a.out_mode = out.mode;
+  a.sy = sy; a.sx = sx; a.py = py; a.px = px;
+  a.Ho = H * sy; a.Wo = W * sx;
+  if (out.mode == kOutNHWC) {
+    WC_REQUIRE(out.out.ptr && out.out.B == B && out.out.H == a.Ho && out.out.W == a.Wo, "output grid mismatch");
+    WC_REQUIRE(out.out.ld % 8 == 0, "output pixel stride must be a multiple of 8");
+    a.out = out.out.ptr; a.ldc = out.out.ld;
+  } else if (out.mode == kOutNCHWf32) {
+    a.out_f32 = out.out_f32; a.n_store = out.n_store;
+  } else {
+    a.q = out.q; a.k = out.k; a.vt = out.vt; a.heads = out.heads; a.hd = out.hd; a.C = out.heads * out.hd;
+    WC_REQUIRE(N == 3 * a.C, "QKV epilogue needs N == 3*C");
+    WC_REQUIRE((H * W) % 8 == 0, "token count must be a multiple of 8");
+  }
+  const long tiles = m_tiles * ((N + a.BN - 1) / a.BN);
+  plan->grid = static_cast<int>(std::min<long>(tiles, num_sms()));
+  plan->flops = 2.0 * macs_per_pixel * static_cast<double>(B) * H * W;
+  return 0;
+}
+
+}  // namespace
+
+int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w, const ConvGeom& g, int N,
+               const Act* x2, const WeightSrc* w2, const Epilogue& ep, const OutSpec& out, cudaStream_t st) {
+  WC_REQUIRE(x.C == in_channels_of(w), "input channels do not match the weight");
+  WC_REQUIRE(x.C % 8 == 0 && x.ld % 8 == 0, "input channels / stride must be multiples of 8");
+  op->plans.clear();
+  op->plans.emplace_back();
+  IgemmPlan& plan = op->plans.back();
+  std::vector<TapDef> taps;
+  int B = x.B, H, W, tb, th, tw;
+  if (g.stride == 1) {
+    WC_REQUIRE(2 * g.pad == g.dil * (g.K - 1), "stride-1 convolutions must be 'same' sized");
+    H = x.H; W = x.W;
+    igemm_pick_tile(B, H, W, &tb, &th, &tw);
+    if (int e = igemm_make_amap(&plan.maps.a[0], x, tb, th, tw)) return e;
+    for (int ky = 0; ky < g.K; ++ky)
+      for (int kx = 0; kx < g.K; ++kx)
+        taps.push_back({0, ky * g.dil - g.pad, kx * g.dil - g.pad, &w, ky, kx, x.C});
+    int nmaps = 1;
+    if (x2) {
+      WC_REQUIRE(w2 && x2->B == B && x2->H == H && x2->W == W && x2->C == in_channels_of(*w2), "fused 1x1 input mismatch");
+      if (int e = igemm_make_amap(&plan.maps.a[1], *x2, tb, th, tw)) return e;
+      taps.push_back({1, 0, 0, w2, 0, 0, x2->C});
+      nmaps = 2;
+    }
+    for (int i = nmaps; i < kMaxMaps; ++i) plan.maps.a[i] = plan.maps.a[0];
+  } else {
+    WC_REQUIRE(g.stride == 2 && g.dil == 1 && !x2, "only stride 1 or 2 (undilated, unfused) supported");
+    WC_REQUIRE(x.H % 2 == 0 && x.W % 2 == 0, "stride-2 convolution needs even input dims");
+    H = x.H / 2; W = x.W / 2;
+    igemm_pick_tile(B, H, W, &tb, &th, &tw);
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        if (int e = igemm_make_amap(&plan.maps.a[py * 2 + px], x, tb, th, tw, py, 2, px, 2, H, W)) return e;
+    plan.maps.a[4] = plan.maps.a[0];
+    for (int ky = 0; ky < g.K; ++ky)
+      for (int kx = 0; kx < g.K; ++kx) {
+        const int oy = ky - g.pad, ox = kx - g.pad;
+        const int py = ((oy % 2) + 2) % 2, px = ((ox % 2) + 2) % 2;
+        taps.push_back({py * 2 + px, (oy - py) / 2, (ox - px) / 2, &w, ky, kx, x.C});
+      }
+  }
+  if (int e = finish_plan(&plan, arena, taps, B, H, W, tb, th, tw, N, ep, out, 1, 1, 0, 0, st)) return e;
+  op->flops = plan.flops;
+  return 0;
+}
+
+int build_conv_transposed_s2(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w, int K, int pad, int N,
+                             const Epilogue& ep, const OutSpec& out, cudaStream_t st) {
+  WC_REQUIRE(w.transpose == 1, "transposed conv expects a [Cin][Cout][K][K] weight view");
+  WC_REQUIRE(x.C == in_channels_of(w), "input channels do not match the weight");
+  op->plans.clear();
+  op->flops = 0;
+  int tb, th, tw;
+  igemm_pick_tile(x.B, x.H, x.W, &tb, &th, &tw);
+  for (int qy = 0; qy < 2; ++qy)
+    for (int qx = 0; qx < 2; ++qx) {
+      std::vector<TapDef> taps;
+      for (int ky = (qy + pad) % 2; ky < K; ky += 2)
+        for (int kx = (qx + pad) % 2; kx < K; kx += 2)
+          taps.push_back({0, (qy + pad - ky) / 2, (qx + pad - kx) / 2, &w, ky, kx, x.C});
+      if (taps.empty()) continue;  // e.g. 1x1 stride-2 dgrad: only phase (0,0) receives gradient
+      op->plans.emplace_back();
+      IgemmPlan& plan = op->plans.back();
+      if (int e = igemm_make_amap(&plan.maps.a[0], x, tb, th, tw)) return e;
+      for (int i = 1; i < kMaxMaps; ++i) plan.maps.a[i] = plan.maps.a[0];
+      if (int e = finish_plan(&plan, arena, taps, x.B, x.H, x.W, tb, th, tw, N, ep, out, 2, 2, qy, qx, st)) return e;
+      op->flops += plan.flops;
+    }
+  return 0;
+}
+
+}  // namespace wc

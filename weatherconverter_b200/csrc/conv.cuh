@@ -1,0 +1,76 @@
+// Convolution layers expressed as igemm plans: tap lists for stride-1 (dilated) convs, stride-2 convs (phase
+// views), transposed / data-gradient convs (one plan per output phase), with weights packed to bf16 K-major.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "igemm.cuh"
+
+namespace wc {
+
+// Library-owned device allocations (packed weights, folded biases); freed with the owning object.
+class DeviceArena {
+ public:
+  ~DeviceArena();
+  void* alloc(size_t bytes);  // returns nullptr and sets the error on failure
+  size_t bytes() const { return total_; }
+
+ private:
+  std::vector<void*> ptrs_;
+  size_t total_ = 0;
+};
+
+struct WeightSrc {
+  const float* w = nullptr;  // fp32 device tensor, PyTorch layout
+  int d0 = 0, d1 = 0;        // dims 0 and 1 of the source tensor
+  int KH = 1, KW = 1;
+  int transpose = 0;            // 0: out-channel = dim0 (Conv2d fwd); 1: out-channel = dim1 (ConvTranspose2d / dgrad)
+  int flip = 0;                 // use tap (KH-1-ky, KW-1-kx): stride-1 data gradient
+  const float* scale = nullptr;  // optional per-dim0 scale (folded BatchNorm)
+};
+
+struct ConvGeom {
+  int K = 3, stride = 1, pad = 1, dil = 1;
+};
+
+struct Epilogue {
+  const float* bias = nullptr;
+  const float* rowbias = nullptr;
+  int ldrb = 0;
+  const Act* res = nullptr;
+  const Act* mask = nullptr;
+  int relu = 0;
+};
+
+struct OutSpec {
+  int mode = kOutNHWC;
+  Act out;  // kOutNHWC destination (full-resolution grid for transposed convs)
+  float* out_f32 = nullptr;
+  int n_store = 0;
+  __nv_bfloat16 *q = nullptr, *k = nullptr, *vt = nullptr;
+  int heads = 0, hd = 0;
+};
+
+// One logical layer = one or more igemm launches (4 for stride-2 transposed / dgrad convs).
+struct ConvOp {
+  std::vector<IgemmPlan> plans;
+  double flops = 0;
+  int run(cudaStream_t st) const {
+    for (const auto& p : plans)
+      if (int e = igemm_launch(p, st)) return e;
+    return 0;
+  }
+};
+
+// Forward convolution y = conv(x, W) (+ fused 1x1 conv of x2 with W2), "same" padding for stride 1,
+// Ho = H/2 for stride 2.  N = number of output channels (multiple of 16 after padding by the caller).
+int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w, const ConvGeom& g, int N,
+               const Act* x2, const WeightSrc* w2, const Epilogue& ep, const OutSpec& out, cudaStream_t st);
+
+// Transposed convolution with stride 2 (ConvTranspose2d(k, 2, pad), output exactly 2x) or, equivalently, the
+// data gradient of a stride-2 convolution: out[2j+q] = sum_{k = (q+pad) mod 2 ...} in[j + (q+pad-k)/2] * W[k].
+// Weight source must have transpose = 1 semantics (out-channel = dim1).
+int build_conv_transposed_s2(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w, int K, int pad, int N,
+                             const Epilogue& ep, const OutSpec& out, cudaStream_t st);
+
+}  // namespace wc

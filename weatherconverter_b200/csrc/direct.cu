@@ -1,0 +1,286 @@
+// Small CUDA-core kernels around the tensor-core path: boundary layout conversion fused with the 3-channel
+// convolutions (conv_in 3->64 reads the reference's NCHW fp32 image; conv_out 64->3 writes NCHW fp32), the
+// time-embedding MLP, weight packing, and NCHW<->NHWC converters.
+// Reference ops: unet_base.py:7-30 (get_time_embedding), :395-397 (t_proj), :96-98 (t_emb_layers), :399 (conv_in),
+// :449 (conv_out); resnet.py:142-145 (conv1+bn1+relu).
+#include "wc_host.h"
+#include "wc_ptx.cuh"
+
+namespace wc {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// conv (Cin small, e.g. 3) from NCHW fp32 to NHWC bf16, KxK, stride s, pad p, optional per-channel affine
+// (folded BatchNorm) and ReLU.  Block = 32 pixels x (Cout/8) channel octets.
+template <int CIN>
+__global__ void conv_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cout][CIN][K][K]*/,
+                                      const float* __restrict__ bias, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int B, int H,
+                                      int W, int Ho, int Wo, int Cout, int K, int stride, int pad, int ldy, int relu) {
+  extern __shared__ float sw[];  // [CIN*K*K][Cout]
+  const int taps = CIN * K * K;
+  for (int i = threadIdx.x; i < taps * Cout; i += blockDim.x) {
+    const int n = i % Cout, t = i / Cout;
+    sw[i] = w[static_cast<size_t>(n) * taps + t];
+  }
+  __syncthreads();
+  const int octs = Cout / 8;
+  const int oct = threadIdx.x % octs, pl = threadIdx.x / octs;
+  const int ppb = blockDim.x / octs;
+  const size_t npix = static_cast<size_t>(B) * Ho * Wo;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * ppb + pl; pix < npix; pix += static_cast<size_t>(gridDim.x) * ppb) {
+    const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho), b = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[oct * 8 + j] : 0.f;
+    for (int c = 0; c < CIN; ++c) {
+      const float* xp = x + (static_cast<size_t>(b) * CIN + c) * H * W;
+      for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * stride - pad + ky;
+        if (iy < 0 || iy >= H) continue;
+        for (int kx = 0; kx < K; ++kx) {
+          const int ix = ox * stride - pad + kx;
+          if (ix < 0 || ix >= W) continue;
+          const float v = __ldg(xp + static_cast<size_t>(iy) * W + ix);
+          const float* wp = sw + ((c * K + ky) * K + kx) * Cout + oct * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+        }
+      }
+    }
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(acc[j], scale[oct * 8 + j], shift[oct * 8 + j]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    uint4 u;
+    u.x = pack_bf16(acc[0], acc[1]); u.y = pack_bf16(acc[2], acc[3]);
+    u.z = pack_bf16(acc[4], acc[5]); u.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(y + pix * ldy + oct * 8) = u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv KxK (stride 1, pad K/2) from NHWC bf16 (Cin % 8 == 0) to NCHW fp32 with COUT (<=4) outputs; one thread
+// per output pixel; optional tanh epilogue y = (tanh(v)+1)/2 (SRGAN, models.py:92).
+template <int COUT>
+__global__ void conv_small_cout_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[COUT][Cin][K][K]*/,
+                                       const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W,
+                                       int Cin, int K, int ldx, int tanh_out) {
+  extern __shared__ float sw[];  // [K*K][Cin][COUT]
+  const int kk = K * K;
+  for (int i = threadIdx.x; i < kk * Cin * COUT; i += blockDim.x) {
+    const int n = i % COUT, c = (i / COUT) % Cin, t = i / (COUT * Cin);
+    sw[i] = w[(static_cast<size_t>(n) * Cin + c) * kk + t];
+  }
+  __syncthreads();
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  const int pad = K / 2;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(pix % W), oy = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+    float acc[COUT];
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) acc[n] = bias ? bias[n] : 0.f;
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy - pad + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < K; ++kx) {
+        const int ix = ox - pad + kx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4* xp = reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + iy) * W + ix) * ldx);
+        const float* wp = sw + static_cast<size_t>(ky * K + kx) * Cin * COUT;
+        for (int c8 = 0; c8 < Cin / 8; ++c8) {
+          const uint4 u = __ldg(xp + c8);
+          float f[8];
+          float2 t;
+          t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+          t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+          t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+          t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int n = 0; n < COUT; ++n) acc[n] = fmaf(f[j], wp[(c8 * 8 + j) * COUT + n], acc[n]);
+        }
+      }
+    }
+    const size_t plane = static_cast<size_t>(H) * W;
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) {
+      float v = acc[n];
+      if (tanh_out) v = (tanhf(v) + 1.f) * 0.5f;
+      y[(static_cast<size_t>(b) * COUT + n) * plane + static_cast<size_t>(oy) * W + ox] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Time embedding: emb = [sin(t/f_j), cos(t/f_j)], f_j = 10000^(j/half); h = W2 silu(W1 emb + b1) + b2;
+// writes silu(h) (every consumer applies SiLU first, unet_base.py:97) and h itself.
+__global__ void temb_mlp_kernel(const long long* __restrict__ t, int dim, const float* __restrict__ w1,
+                                const float* __restrict__ b1, const float* __restrict__ w2,
+                                const float* __restrict__ b2, float* __restrict__ temb, float* __restrict__ temb_silu) {
+  extern __shared__ float sh[];  // emb[dim], h1[dim]
+  float* emb = sh;
+  float* h1 = sh + dim;
+  const int b = blockIdx.x, half = dim / 2;
+  const float tv = static_cast<float>(t[b]);
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    const float factor = powf(10000.0f, static_cast<float>(j) / static_cast<float>(half));
+    const float a = tv / factor;
+    emb[j] = sinf(a);
+    emb[j + half] = cosf(a);
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < dim; n += blockDim.x) {
+    float acc = b1[n];
+    for (int k = 0; k < dim; ++k) acc = fmaf(w1[static_cast<size_t>(n) * dim + k], emb[k], acc);
+    h1[n] = acc / (1.f + expf(-acc));
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < dim; n += blockDim.x) {
+    float acc = b2[n];
+    for (int k = 0; k < dim; ++k) acc = fmaf(w2[static_cast<size_t>(n) * dim + k], h1[k], acc);
+    temb[static_cast<size_t>(b) * dim + n] = acc;
+    temb_silu[static_cast<size_t>(b) * dim + n] = acc / (1.f + expf(-acc));
+  }
+}
+
+// out[b][n] = bias[n] + sum_k W[n][k] * in[b][k]; one warp per output, all t_emb_layers of the net in one launch.
+__global__ void linear_rows_kernel(const float* __restrict__ in, int dim, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ out, int N) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  if (warp >= N) return;
+  float acc = 0.f;
+  for (int k = lane; k < dim; k += 32) acc = fmaf(w[static_cast<size_t>(warp) * dim + k], in[static_cast<size_t>(b) * dim + k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[static_cast<size_t>(b) * N + warp] = acc + bias[warp];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight packing: dst[n][koff + c] (bf16, row pitch ldk) = scale[.] * src[...][ky][kx] for n < Nn, c < Cc,
+// zero for c in [Cc, Cpad).  transpose = 0: src is [Nn][Cc][KH][KW] (Conv2d); 1: src is [Cc][Nn][KH][KW]
+// (ConvTranspose2d weight, or a dgrad view of a Conv2d weight).  scale (optional) is indexed by the src dim-0.
+__global__ void pack_tap_kernel(__nv_bfloat16* __restrict__ dst, int ldk, int koff, const float* __restrict__ src,
+                                int Nn, int Cc, int Cpad, int KH, int KW, int ky, int kx, int transpose,
+                                const float* __restrict__ scale) {
+  const size_t total = static_cast<size_t>(Nn) * Cpad;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cpad), n = static_cast<int>(i / Cpad);
+    float v = 0.f;
+    if (c < Cc) {
+      const size_t d0 = transpose ? c : n, d1 = transpose ? n : c;
+      const size_t D1 = transpose ? Nn : Cc;
+      v = src[((d0 * D1 + d1) * KH + ky) * KW + kx];
+      if (scale) v *= scale[d0];
+    }
+    dst[static_cast<size_t>(n) * ldk + koff + c] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
+                                             int HW, int ldy) {
+  const size_t total = static_cast<size_t>(B) * HW * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t p = (i / C) % HW, b = i / (static_cast<size_t>(C) * HW);
+    y[(b * HW + p) * ldy + c] = __float2bfloat16_rn(x[(b * C + c) * HW + p]);
+  }
+}
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int C,
+                                             int HW, int ldx) {
+  const size_t total = static_cast<size_t>(B) * HW * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t p = i % HW;
+    const int c = static_cast<int>((i / HW) % C);
+    const size_t b = i / (static_cast<size_t>(C) * HW);
+    y[i] = __bfloat162float(x[(b * HW + p) * ldx + c]);
+  }
+}
+
+inline int grid_for(size_t n_items, int per_block = 256) {
+  const size_t blocks = (n_items + per_block - 1) / per_block;
+  const size_t cap = static_cast<size_t>(num_sms()) * 8;
+  return static_cast<int>(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+int conv_small_cin(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
+                   __nv_bfloat16* y, int B, int Cin, int H, int W, int Cout, int K, int stride, int pad, int ldy,
+                   int relu, cudaStream_t st) {
+  WC_REQUIRE(Cin == 3, "conv_small_cin supports Cin == 3");
+  WC_REQUIRE(Cout % 8 == 0 && Cout <= 256, "Cout must be a multiple of 8, <= 256");
+  const int Ho = (H + 2 * pad - K) / stride + 1, Wo = (W + 2 * pad - K) / stride + 1;
+  const int octs = Cout / 8, threads = (256 / octs) * octs;
+  const size_t smem = static_cast<size_t>(Cin) * K * K * Cout * sizeof(float);
+  if (smem > 48 * 1024)
+    WC_CHECK_CUDA(cudaFuncSetAttribute(conv_small_cin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+  const size_t npix = static_cast<size_t>(B) * Ho * Wo;
+  conv_small_cin_kernel<3><<<grid_for(npix, threads / octs), threads, smem, st>>>(
+      x, w, bias, scale, shift, y, B, H, W, Ho, Wo, Cout, K, stride, pad, ldy, relu);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv_small_cout(const __nv_bfloat16* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
+                    int Cout, int K, int ldx, int tanh_out, cudaStream_t st) {
+  WC_REQUIRE(Cout == 3, "conv_small_cout supports Cout == 3");
+  WC_REQUIRE(Cin % 8 == 0, "Cin must be a multiple of 8");
+  const size_t smem = static_cast<size_t>(K) * K * Cin * Cout * sizeof(float);
+  if (smem > 48 * 1024)
+    WC_CHECK_CUDA(cudaFuncSetAttribute(conv_small_cout_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  conv_small_cout_kernel<3><<<grid_for(npix, 128), 128, smem, st>>>(x, w, bias, y, B, H, W, Cin, K, ldx, tanh_out);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+int temb_mlp(const long long* t, int Bt, int dim, const float* w1, const float* b1, const float* w2, const float* b2,
+             float* temb, float* temb_silu, cudaStream_t st) {
+  temb_mlp_kernel<<<Bt, 128, 2 * dim * sizeof(float), st>>>(t, dim, w1, b1, w2, b2, temb, temb_silu);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+int linear_rows(const float* in, int Bt, int dim, const float* w, const float* bias, float* out, int N,
+                cudaStream_t st) {
+  const int warps_per_block = 8;
+  linear_rows_kernel<<<dim3((N + warps_per_block - 1) / warps_per_block, Bt), warps_per_block * 32, 0, st>>>(
+      in, dim, w, bias, out, N);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+int pack_tap(__nv_bfloat16* dst, int ldk, int koff, const float* src, int Nn, int Cc, int Cpad, int KH, int KW, int ky,
+             int kx, int transpose, const float* scale, cudaStream_t st) {
+  pack_tap_kernel<<<grid_for(static_cast<size_t>(Nn) * Cpad), 256, 0, st>>>(dst, ldk, koff, src, Nn, Cc, Cpad, KH, KW,
+                                                                           ky, kx, transpose, scale);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+int nchw_f32_to_nhwc_bf16(const float* x, __nv_bfloat16* y, int B, int C, int HW, int ldy, cudaStream_t st) {
+  nchw_f32_to_nhwc_bf16_kernel<<<grid_for(static_cast<size_t>(B) * C * HW), 256, 0, st>>>(x, y, B, C, HW, ldy);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int nhwc_bf16_to_nchw_f32(const __nv_bfloat16* x, float* y, int B, int C, int HW, int ldx, cudaStream_t st) {
+  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(static_cast<size_t>(B) * C * HW), 256, 0, st>>>(x, y, B, C, HW, ldx);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace wc

@@ -1,0 +1,334 @@
+// See igemm.cuh for the design.  Reference ops replaced: every nn.Conv2d / nn.ConvTranspose2d / nn.Linear on
+// the hot path (unet_base.py:87-129,293-334,395-449; resnet.py:78-118; _deeplab.py:28-59,111-162).
+#include "igemm.cuh"
+#include "wc_ptx.cuh"
+
+namespace wc {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = kIgemmBM * kIgemmBK * 2;  // 16 KiB
+constexpr uint32_t kBBytesMax = 256 * kIgemmBK * 2;    // 32 KiB
+constexpr uint32_t kStageBytes = kABytes + kBBytesMax;
+constexpr uint32_t kSmemBytes = kIgemmStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kTmemCols = 512;
+
+template <int NC>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NC]) {
+  if constexpr (NC == 32) tmem_ld32(taddr, r);
+  else tmem_ld16(taddr, r);
+}
+
+template <int NC>
+__device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc, int n0, int b, int y, int x,
+                                              bool valid) {
+  const int oy = y * p.sy + p.py, ox = x * p.sx + p.px;
+  const size_t opix = (static_cast<size_t>(b) * p.Ho + oy) * p.Wo + ox;
+  for (int c0 = 0; c0 < p.BN; c0 += NC) {
+    const int nb = n0 + c0;
+    if (nb >= p.N) break;  // warp-uniform
+    uint32_t r[NC];
+    tmem_ld_n<NC>(tacc + c0, r);
+    tmem_wait_ld();
+    if (!valid) continue;
+    float v[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+      }
+    }
+    if (p.rowbias) {
+      const float* rb = p.rowbias + static_cast<size_t>(b) * p.ldrb + nb;
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        float4 bv = __ldg(reinterpret_cast<const float4*>(rb + j));
+        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+      }
+    }
+    if (p.res) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.res + opix * p.ldr + nb);
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) {
+        uint4 u = __ldg(rp + j);
+        float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+        v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
+        v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.mask) {
+      const uint4* mp = reinterpret_cast<const uint4*>(p.mask + opix * p.ldm + nb);
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) {
+        uint4 u = __ldg(mp + j);
+        float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+        if (!(f0.x > 0.f)) v[8 * j + 0] = 0.f;
+        if (!(f0.y > 0.f)) v[8 * j + 1] = 0.f;
+        if (!(f1.x > 0.f)) v[8 * j + 2] = 0.f;
+        if (!(f1.y > 0.f)) v[8 * j + 3] = 0.f;
+        if (!(f2.x > 0.f)) v[8 * j + 4] = 0.f;
+        if (!(f2.y > 0.f)) v[8 * j + 5] = 0.f;
+        if (!(f3.x > 0.f)) v[8 * j + 6] = 0.f;
+        if (!(f3.y > 0.f)) v[8 * j + 7] = 0.f;
+      }
+    }
+    if (p.out_mode == kOutNHWC) {
+      uint4* op = reinterpret_cast<uint4*>(p.out + opix * p.ldc + nb);
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) {
+        uint4 u;
+        u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        op[j] = u;
+      }
+    } else if (p.out_mode == kOutNCHWf32) {
+      const size_t plane = static_cast<size_t>(p.Ho) * p.Wo;
+      float* op = p.out_f32 + (static_cast<size_t>(b) * p.n_store) * plane + static_cast<size_t>(oy) * p.Wo + ox;
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (nb + j < p.n_store) op[static_cast<size_t>(nb + j) * plane] = v[j];
+    } else {  // kOutQKV, NC == 16, hd % 16 == 0: a chunk never straddles a head or the q/k/v boundary
+      const int which = nb / p.C, c = nb % p.C, head = c / p.hd, d = c % p.hd;
+      const int ntok = p.H * p.W;
+      const size_t tok = static_cast<size_t>(y) * p.W + x;
+      const size_t bh = static_cast<size_t>(b) * p.heads + head;
+      if (which < 2) {
+        __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + (bh * ntok + tok) * p.hd + d;
+        uint4* op = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int j = 0; j < NC / 8; ++j) {
+          uint4 u;
+          u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+          u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+          u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+          u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+          op[j] = u;
+        }
+      } else {
+        __nv_bfloat16* dst = p.vt + (bh * p.hd + d) * ntok + tok;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) dst[static_cast<size_t>(j) * ntok] = __float2bfloat16_rn(v[j]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kIgemmStages * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kIgemmStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kIgemmStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kIgemmStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kIgemmStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_x = (p.W + p.tw - 1) / p.tw, tiles_y = (p.H + p.th - 1) / p.th, tiles_b = (p.B + p.tb - 1) / p.tb;
+  const int m_tiles = tiles_x * tiles_y * tiles_b;
+  const int n_tiles = (p.N + p.BN - 1) / p.BN;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kIgemmStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 128);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto decode = [&](int tile, int& n0, int& b0, int& y0, int& x0) {
+    const int nt = tile % n_tiles, mt = tile / n_tiles;
+    n0 = nt * p.BN;
+    x0 = (mt % tiles_x) * p.tw;
+    y0 = ((mt / tiles_x) % tiles_y) * p.th;
+    b0 = (mt / (tiles_x * tiles_y)) * p.tb;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = kABytes + static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n0, b0, y0, x0;
+        decode(tile, n0, b0, y0, x0);
+        int kb_global = 0;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const IgemmTap tap = p.taps[t];
+          const CUtensorMap* amap = &maps.a[tap.map];
+          for (int kb = 0; kb < tap.nkb; ++kb, ++kb_global) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * kStageBytes;
+            mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+            tma_load_4d(sa, amap, full_bar(stage), kb * kIgemmBK, x0 + tap.dx, y0 + tap.dy, b0);
+            tma_load_2d(sa + kABytes, &maps.b, full_bar(stage), kb_global * kIgemmBK, n0);
+            if (++stage == kIgemmStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = umma_idesc_bf16(kIgemmBM, static_cast<uint32_t>(p.BN));
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        const uint32_t aphase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(a), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a) * 256u;
+        for (int ks = 0; ks < p.total_kb; ++ks) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint64_t adesc = umma_smem_desc(sa, 128, 1024);
+          const uint64_t bdesc = umma_smem_desc(sa + kABytes, 128, 1024);
+#pragma unroll
+          for (int k = 0; k < kIgemmBK / 16; ++k)
+            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ks | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == kIgemmStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(a));
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const int bb = row / (p.th * p.tw), rem = row % (p.th * p.tw), yy = rem / p.tw, xx = rem % p.tw;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aphase = (it >> 1) & 1u;
+      int n0, b0, y0, x0;
+      decode(tile, n0, b0, y0, x0);
+      const int b = b0 + bb, y = y0 + yy, x = x0 + xx;
+      const bool valid = (b < p.B) && (y < p.H) && (x < p.W);
+      mbar_wait(tfull_bar(a), aphase);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + static_cast<uint32_t>(a) * 256u + (static_cast<uint32_t>(quad * 32) << 16);
+      if (p.out_mode != kOutQKV && (p.BN % 32 == 0) && (p.N % 32 == 0))
+        epilogue_tile<32>(p, tacc, n0, b, y, x, valid);
+      else
+        epilogue_tile<16>(p, tacc, n0, b, y, x, valid);
+      tc_fence_before();
+      mbar_arrive(tempty_bar(a));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  igemm_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+static int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+void igemm_pick_tile(int B, int H, int W, int* tb, int* th, int* tw) {
+  int w = pow2_floor(W);
+  if (w < W && w * 2 <= 128) w *= 2;  // non power-of-two widths: cover with an over-hanging tile
+  if (w > 128) w = 128;
+  int rem = 128 / w;
+  int h = pow2_floor(H);
+  if (h < H && h * 2 <= rem) h *= 2;
+  if (h > rem) h = rem;
+  *tw = w; *th = h; *tb = 128 / (w * h);
+  (void)B;
+}
+
+int igemm_pick_bn(int N, long m_tiles) {
+  // Candidate N tiles (multiples of 16, <= 256, not wider than the padded N); pick the one minimising
+  // waves * per-tile cost, where the per-tile cost has a fixed part that penalises very narrow tiles.
+  const int npad = (N + 15) / 16 * 16;
+  int cands[9] = {256, 192, 128, 96, 64, 48, 32, 16, npad <= 256 ? npad : 16};
+  const int sms = num_sms();
+  int best = 16;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    if (bn > npad) continue;
+    const long n_tiles = (N + bn - 1) / bn;
+    const long waves = (m_tiles * n_tiles + sms - 1) / sms;
+    const double cost = static_cast<double>(waves) * (bn + 48.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+int igemm_make_amap(CUtensorMap* out, const Act& act, int tb, int th, int tw, int y0, int ys, int x0, int xs, int Hv,
+                    int Wv) {
+  if (Hv < 0) Hv = act.H;
+  if (Wv < 0) Wv = act.W;
+  const __nv_bfloat16* base = act.ptr + (static_cast<size_t>(y0) * act.W + x0) * act.ld;
+  uint64_t dims[4] = {static_cast<uint64_t>(act.C), static_cast<uint64_t>(Wv), static_cast<uint64_t>(Hv),
+                      static_cast<uint64_t>(act.B)};
+  uint64_t strides[4] = {1, static_cast<uint64_t>(act.ld) * xs, static_cast<uint64_t>(act.ld) * act.W * ys,
+                         static_cast<uint64_t>(act.ld) * act.W * act.H};
+  uint32_t box[4] = {static_cast<uint32_t>(kIgemmBK), static_cast<uint32_t>(tw), static_cast<uint32_t>(th),
+                     static_cast<uint32_t>(tb)};
+  return encode_tmap_bf16(out, base, 4, dims, strides, box, 128);
+}
+
+int igemm_make_bmap(CUtensorMap* out, const __nv_bfloat16* wpacked, int n_rows, int ktotal, int BN) {
+  uint64_t dims[2] = {static_cast<uint64_t>(ktotal), static_cast<uint64_t>(n_rows)};
+  uint64_t strides[2] = {1, static_cast<uint64_t>(ktotal)};
+  uint32_t box[2] = {static_cast<uint32_t>(kIgemmBK), static_cast<uint32_t>(BN)};
+  return encode_tmap_bf16(out, wpacked, 2, dims, strides, box, 128);
+}
+
+}  // namespace wc

@@ -1,0 +1,83 @@
+// Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (sm_100a).
+//
+//   out[pixel, n] = epilogue( sum_{tap} sum_{c} A_tap[pixel + (dy,dx), c] * Wp[n, koff(tap) + c] )
+//
+// * A operands are NHWC bf16 tensors described by up to kMaxMaps rank-4 TMA tensor maps (C, W, H, B).  One
+//   pipeline stage = one (tap, 64-channel block): a TMA box of 128 pixels x 64 channels (128-byte swizzle),
+//   zero-filled outside the image, lands in shared memory already in the canonical K-major UMMA layout.
+//   Stride-2 convolutions use one map per input phase (strided views); the fused 1x1 residual convolution of
+//   a ResNet sub-layer is simply one more tap reading a different tensor.
+// * B (weights) are pre-packed bf16 [Npad][Ktotal] K-major, loaded with a 2-D tensor map (box 64 x BN).
+// * tcgen05.mma 128 x BN x 16 (cta_group::1), fp32 accumulators double-buffered in TMEM (2 x 256 columns).
+// * Persistent CTAs, 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue
+//   (TMEM -> registers -> bias / t-emb / residual / ReLU -> bf16 stores), so the epilogue of tile i overlaps
+//   the main loop of tile i+1.
+#pragma once
+#include "wc_host.h"
+
+namespace wc {
+
+constexpr int kIgemmStages = 4;
+constexpr int kIgemmBM = 128;
+constexpr int kIgemmBK = 64;
+constexpr int kMaxTaps = 20;
+constexpr int kMaxMaps = 5;
+
+struct IgemmTap {
+  int8_t map;  // index into IgemmMaps::a
+  int8_t dy, dx;
+  int8_t pad_;
+  int32_t nkb;  // number of 64-channel K blocks for this tap
+};
+
+enum IgemmOutMode : int { kOutNHWC = 0, kOutQKV = 1, kOutNCHWf32 = 2 };
+
+struct IgemmArgs {
+  int B, H, W;     // logical pixel grid the M tiles walk (== spatial dims of every A map)
+  int tb, th, tw;  // tile shape, tb*th*tw == 128
+  int N, BN;       // true output channels (multiple of 16) and N tile
+  int ntaps, total_kb;
+  IgemmTap taps[kMaxTaps];
+  // epilogue
+  const float* bias;     // [N] or nullptr
+  const float* rowbias;  // [B][ldrb] per-sample additive term (t-embedding projection) or nullptr
+  int ldrb;
+  const __nv_bfloat16* res;  // residual, NHWC on the OUTPUT grid (B,Ho,Wo), or nullptr
+  int ldr;
+  const __nv_bfloat16* mask;  // ReLU-derivative mask on the output grid: result zeroed where mask <= 0, or nullptr
+  int ldm;
+  int relu;
+  int out_mode;
+  __nv_bfloat16* out;  // kOutNHWC: element (b, y*sy+py, x*sx+px, n) of a [B,Ho,Wo,ldc] buffer
+  int ldc, Ho, Wo, sy, sx, py, px;
+  float* out_f32;  // kOutNCHWf32: [B, N_store, Ho, Wo] fp32 planes
+  int n_store;
+  __nv_bfloat16 *q, *k, *vt;  // kOutQKV: Q,K [B,heads,ntok,hd]; V^T [B,heads,hd,ntok]
+  int heads, hd, C;
+};
+
+struct IgemmMaps {
+  CUtensorMap a[kMaxMaps];
+  CUtensorMap b;
+};
+
+struct IgemmPlan {
+  IgemmMaps maps;
+  IgemmArgs args;
+  int grid = 0;
+  double flops = 0;  // algorithmic FLOPs (2*MAC) of the convolution this plan implements
+};
+
+int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
+
+// Choose the M-tile shape for a (B,H,W) grid: widest power-of-two span of x, then y, then b.
+void igemm_pick_tile(int B, int H, int W, int* tb, int* th, int* tw);
+int igemm_pick_bn(int N, long m_tiles);
+
+// Rank-4 (C, W, H, B) bf16 tensor map over an NHWC view, with optional spatial sub-sampling (phase views for
+// stride-2 convolutions): element (b, y, x, c) of the view = act(b, y*ys + y0, x*xs + x0, c), view dims Hv x Wv.
+int igemm_make_amap(CUtensorMap* out, const Act& act, int tb, int th, int tw, int y0 = 0, int ys = 1, int x0 = 0,
+                    int xs = 1, int Hv = -1, int Wv = -1);
+int igemm_make_bmap(CUtensorMap* out, const __nv_bfloat16* wpacked, int n_rows, int ktotal, int BN);
+
+}  // namespace wc

@@ -1,0 +1,121 @@
+// C ABI (include/wc_b200.h): thin extern "C" wrappers over the kernels' host launchers.
+#include "../../include/wc_b200.h"
+
+#include "conv.cuh"
+
+namespace wc {
+int ddpm_step(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
+              size_t n_per_sample, int B, float beta, float s, float sqrt_alpha, float sigma, cudaStream_t st);
+int ddpm_step_batched(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
+                      size_t n_per_sample, int B, const float* betas, const float* alphas, const float* sqrt_1m_acp,
+                      const long long* t, cudaStream_t st);
+int add_noise(const float* x0, const float* noise, float* out, size_t n_per_sample, int B, const float* sqrt_acp,
+              const float* sqrt_1m_acp, const long long* t, cudaStream_t st);
+int sgg_update(const float* grad, const float* mu, const float* sigz, float* out, float* mag_out, int B, int h, int w,
+               int pool, float lam, cudaStream_t st);
+int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, int ld, int ldy, const float* gamma,
+                   const float* beta, float eps, int silu, void* workspace, cudaStream_t st);
+size_t groupnorm_workspace_bytes(int B);
+int conv_small_cin(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
+                   __nv_bfloat16* y, int B, int Cin, int H, int W, int Cout, int K, int stride, int pad, int ldy,
+                   int relu, cudaStream_t st);
+int conv_small_cout(const __nv_bfloat16* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
+                    int Cout, int K, int ldx, int tanh_out, cudaStream_t st);
+int nchw_f32_to_nhwc_bf16(const float* x, __nv_bfloat16* y, int B, int C, int HW, int ldy, cudaStream_t st);
+int nhwc_bf16_to_nchw_f32(const __nv_bfloat16* x, float* y, int B, int C, int HW, int ldx, cudaStream_t st);
+int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
+                      int heads, int ntok, int hd, int ldo, cudaStream_t st);
+}  // namespace wc
+
+using namespace wc;
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+static inline __nv_bfloat16* BF(wc_bf16* p) { return reinterpret_cast<__nv_bfloat16*>(p); }
+static inline const __nv_bfloat16* BF(const wc_bf16* p) { return reinterpret_cast<const __nv_bfloat16*>(p); }
+
+extern "C" {
+
+const char* wc_last_error(void) { return last_error_cstr(); }
+int wc_abi_version(void) { return 1; }
+long long wc_launch_count(void) { return launch_count(); }
+
+int wc_ddpm_step(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
+                 size_t n_per_sample, int batch, float beta, float sqrt_one_minus_acp, float sqrt_alpha, float sigma,
+                 void* stream) {
+  return ddpm_step(xt, eps, z, out, mean_out, sigz_out, n_per_sample, batch, beta, sqrt_one_minus_acp, sqrt_alpha, sigma,
+                   S(stream));
+}
+int wc_ddpm_step_batched(const float* xt, const float* eps, const float* z, float* out, float* mean_out,
+                         float* sigz_out, size_t n_per_sample, int batch, const float* betas, const float* alphas,
+                         const float* sqrt_one_minus_acp, const int64_t* t, void* stream) {
+  return ddpm_step_batched(xt, eps, z, out, mean_out, sigz_out, n_per_sample, batch, betas, alphas, sqrt_one_minus_acp,
+                           reinterpret_cast<const long long*>(t), S(stream));
+}
+int wc_add_noise(const float* x0, const float* noise, float* out, size_t n_per_sample, int batch,
+                 const float* sqrt_acp, const float* sqrt_one_minus_acp, const int64_t* t, void* stream) {
+  return add_noise(x0, noise, out, n_per_sample, batch, sqrt_acp, sqrt_one_minus_acp,
+                   reinterpret_cast<const long long*>(t), S(stream));
+}
+int wc_sgg_update(const float* grad, const float* mu, const float* sigz, float* out, float* mag_out, int batch, int h,
+                  int w, int pool, float lambda, void* stream) {
+  return sgg_update(grad, mu, sigz, out, mag_out, batch, h, w, pool, lambda, S(stream));
+}
+size_t wc_groupnorm_workspace_bytes(int batch) { return groupnorm_workspace_bytes(batch); }
+int wc_groupnorm_silu(const wc_bf16* x, wc_bf16* y, int batch, int hw, int channels, int ldx, int ldy,
+                      const float* gamma, const float* beta, float eps, int silu, void* workspace, void* stream) {
+  return groupnorm_silu(BF(x), BF(y), batch, hw, channels, ldx, ldy, gamma, beta, eps, silu, workspace, S(stream));
+}
+
+int wc_conv2d(const wc_bf16* x, int batch, int H, int W, int Cin, int ldx, const float* weight, const float* bias,
+              int Cout, int K, int stride, int pad, int dil, int transposed, const float* rowbias,
+              const wc_bf16* residual, int ldr, const wc_bf16* x2, int Cin2, int ldx2, const float* weight2, int relu,
+              wc_bf16* y, int ldy, void* stream) {
+  // One-shot convenience entry (unit tests, INTEGRATION.md example): packs weights, runs, frees.  The model-level
+  // entries keep their plans and packed weights alive instead.
+  cudaStream_t st = S(stream);
+  DeviceArena arena;
+  ConvOp op;
+  Act xin; xin.ptr = const_cast<__nv_bfloat16*>(BF(x)); xin.B = batch; xin.H = H; xin.W = W; xin.C = Cin; xin.ld = ldx;
+  const int Ho = transposed ? H * 2 : (stride == 2 ? H / 2 : H), Wo = transposed ? W * 2 : (stride == 2 ? W / 2 : W);
+  Act yout; yout.ptr = BF(y); yout.B = batch; yout.H = Ho; yout.W = Wo; yout.C = Cout; yout.ld = ldy;
+  Act res; res.ptr = const_cast<__nv_bfloat16*>(BF(residual)); res.B = batch; res.H = Ho; res.W = Wo; res.C = Cout; res.ld = ldr;
+  Act x2a; x2a.ptr = const_cast<__nv_bfloat16*>(BF(x2)); x2a.B = batch; x2a.H = H; x2a.W = W; x2a.C = Cin2; x2a.ld = ldx2;
+  Epilogue ep; ep.bias = bias; ep.rowbias = rowbias; ep.ldrb = Cout; ep.res = residual ? &res : nullptr; ep.relu = relu;
+  OutSpec os; os.mode = kOutNHWC; os.out = yout;
+  int e;
+  if (transposed) {
+    WC_REQUIRE(stride == 2, "transposed convolution supports stride 2");
+    WeightSrc w; w.w = weight; w.d0 = Cin; w.d1 = Cout; w.KH = w.KW = K; w.transpose = 1;
+    e = build_conv_transposed_s2(&op, &arena, xin, w, K, pad, Cout, ep, os, st);
+  } else {
+    WeightSrc w; w.w = weight; w.d0 = Cout; w.d1 = Cin; w.KH = w.KW = K;
+    WeightSrc w2; w2.w = weight2; w2.d0 = Cout; w2.d1 = Cin2;
+    ConvGeom g; g.K = K; g.stride = stride; g.pad = pad; g.dil = dil;
+    e = build_conv(&op, &arena, xin, w, g, Cout, x2 ? &x2a : nullptr, x2 ? &w2 : nullptr, ep, os, st);
+  }
+  if (e) return e;
+  if ((e = op.run(st))) return e;
+  WC_CHECK_CUDA(cudaStreamSynchronize(st));  // arena (packed weights) is freed on return
+  return 0;
+}
+
+int wc_conv_in(const float* x, const float* weight, const float* bias, const float* scale, const float* shift,
+               wc_bf16* y, int batch, int H, int W, int Cout, int K, int stride, int pad, int ldy, int relu,
+               void* stream) {
+  return conv_small_cin(x, weight, bias, scale, shift, BF(y), batch, 3, H, W, Cout, K, stride, pad, ldy, relu, S(stream));
+}
+int wc_conv_out(const wc_bf16* x, const float* weight, const float* bias, float* y, int batch, int H, int W, int Cin,
+                int K, int ldx, int tanh_out, void* stream) {
+  return conv_small_cout(BF(x), weight, bias, y, batch, H, W, Cin, 3, K, ldx, tanh_out, S(stream));
+}
+int wc_nchw_f32_to_nhwc_bf16(const float* x, wc_bf16* y, int batch, int C, int hw, int ldy, void* stream) {
+  return nchw_f32_to_nhwc_bf16(x, BF(y), batch, C, hw, ldy, S(stream));
+}
+int wc_nhwc_bf16_to_nchw_f32(const wc_bf16* x, float* y, int batch, int C, int hw, int ldx, void* stream) {
+  return nhwc_bf16_to_nchw_f32(BF(x), y, batch, C, hw, ldx, S(stream));
+}
+int wc_attention(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, int batch, int heads, int ntok,
+                 int hd, int ldo, void* stream) {
+  return attention_forward(BF(q), BF(k), BF(vt), BF(out), batch, heads, ntok, hd, ldo, S(stream));
+}
+
+}  // extern "C"
