@@ -29,6 +29,13 @@ int wc_abi_version(void);
 /* Number of kernel launches issued by this library in the calling process so far (all entry points). */
 long long wc_launch_count(void);
 
+/* Per-launch CUDA-event timing (bench.py roofline leg).  Between begin and end every kernel launch of the library is
+ * bracketed by events on its stream; end synchronises and returns, per class (0 igemm/tcgen05 conv+linear,
+ * 1 flash attention, 2 GroupNorm, 3 boundary convs, 4 scheduler, 5 other; arrays of 8), the summed milliseconds,
+ * launch counts and algorithmic work (FLOPs for classes 0-1, bytes for 2-4). */
+void wc_profile_begin(void);
+int wc_profile_end(double* ms_by_class, long long* count_by_class, double* work_by_class);
+
 /* ---- DDPM scheduler (diffusion_model/scheduler/linear_noise_scheduler.py) ------------------------------ */
 /* :79-116 sample_prev_timestep + sample_ddpm.py:44.  mean = (xt - beta*eps/s)/sqrt_alpha ; out = mean + sigma*z.
  * z == NULL -> t == 0 branch (out = mean).  mean_out / sigz_out / out may each be NULL.  Bit-exact vs fp32 torch. */

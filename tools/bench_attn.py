@@ -1,0 +1,27 @@
+"""Micro-benchmark of the flash-attention kernel (CUDA events, warm, one shape per line)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from weatherconverter_b200 import ops
+
+shapes = [(16, 4, 8192, 64), (16, 4, 8192, 16), (16, 4, 2048, 128), (16, 4, 2048, 32), (16, 4, 512, 192)]
+if len(sys.argv) > 1:
+    shapes = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+dev = torch.device("cuda")
+for (B, h, N, hd) in shapes:
+    q = torch.randn(B, h, N, hd, device=dev).bfloat16()
+    k = torch.randn(B, h, N, hd, device=dev).bfloat16()
+    vt = torch.randn(B, h, hd, N, device=dev).bfloat16()
+    for _ in range(2):
+        ops.attention(q, k, vt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    it = 5
+    e0.record()
+    for _ in range(it):
+        ops.attention(q, k, vt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / it
+    fl = 4.0 * B * h * N * N * hd
+    print(f"B{B} h{h} N{N} hd{hd}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s  exps/s {B*h*N*N/ms/1e9:.2f} T", flush=True)

@@ -15,9 +15,17 @@
 #include "wc_host.h"
 #include "wc_ptx.cuh"
 
+#include <type_traits>
+
 namespace wc {
 
 namespace {
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct AttnArgs {
   int ntok, heads, ldo;
@@ -179,26 +187,38 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
     const uint32_t o_tmem = s_tmem + BKV;
     const uint32_t p_row = p_smem + q * Cfg::kPTile + row * 128;
     const float sl2 = p.scale_log2;
-    float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_full(q), j & 1u);
-      tc_fence_after();
+    float m = -INFINITY;
+    float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+    // One KV tile of the online softmax.  TAIL (compile-time) masks keys >= ntok; only the last tile can need it,
+    // so the hot path carries no per-element predicates.  TMEM chunk loads are software-pipelined: the load of
+    // chunk c+1 is in flight while chunk c is processed.
+    auto tile = [&](int j, auto tail_tag) {
+      constexpr bool TAIL = decltype(tail_tag)::value;
       const int kv0 = j * BKV;
-      const bool tail = kv0 + BKV > p.ntok;
-      // pass 1: tile max
-      float tmax = -INFINITY;
+      constexpr int NCH = BKV / 32;
+      uint32_t ra[32], rb[32];
+      // ---- pass 1: tile max
+      float t0 = -INFINITY, t1 = -INFINITY;
+      tmem_ld32(s_tmem, ra);
 #pragma unroll
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(s_tmem + c0, r);
+      for (int c = 0; c < NCH; ++c) {
         tmem_wait_ld();
+        uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+        if (c + 1 < NCH) tmem_ld32(s_tmem + 32 * (c + 1), (c & 1) ? ra : rb);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(r[i]);
-          if (tail && kv0 + c0 + i >= p.ntok) v = -INFINITY;
-          tmax = fmaxf(tmax, v);
+        for (int i = 0; i < 32; i += 2) {
+          float a = __uint_as_float(cur[i]), b2 = __uint_as_float(cur[i + 1]);
+          if (TAIL) {
+            if (kv0 + 32 * c + i >= p.ntok) a = -INFINITY;
+            if (kv0 + 32 * c + i + 1 >= p.ntok) b2 = -INFINITY;
+          }
+          t0 = fmaxf(t0, a);
+          t1 = fmaxf(t1, b2);
         }
       }
+      const float tmax = fmaxf(t0, t1);
+      // start re-reading S for pass 2 while we (possibly) wait for the previous PV and rescale O
+      tmem_ld32(s_tmem, ra);
       if (j > 0) mbar_wait(pv_done(q), (j - 1) & 1u);  // O_{j-1} complete, P buffer free
       tc_fence_after();
       if (j == 0) {
@@ -207,9 +227,11 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
         const bool grow = (tmax - m) * sl2 > 8.0f;
         if (__any_sync(0xffffffffu, grow)) {
           const float m_new = fmaxf(m, tmax);
-          const float alpha = exp2f((m - m_new) * sl2);
-          l *= alpha;
+          const float alpha = ex2_approx((m - m_new) * sl2);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) lsum[i] *= alpha;
           m = m_new;
+          tmem_wait_ld();  // ra holds chunk 0 of pass 2; keep the TMEM pipe ordered before O traffic
 #pragma unroll
           for (int c0 = 0; c0 < HD; c0 += 16) {
             uint32_t r[16];
@@ -222,25 +244,27 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
           tmem_wait_st();
         }
       }
-      // pass 2: exponentiate, accumulate the row sum, write P (bf16) in the swizzled K-major layout
+      // ---- pass 2: p = 2^(s*sl2 - m*sl2), row sum, bf16 P in the swizzled K-major layout
       const float mneg = -m * sl2;
 #pragma unroll
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(s_tmem + c0, r);
+      for (int c = 0; c < NCH; ++c) {
         tmem_wait_ld();
+        uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+        if (c + 1 < NCH) tmem_ld32(s_tmem + 32 * (c + 1), (c & 1) ? ra : rb);
         float pv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float v = exp2f(fmaf(__uint_as_float(r[i]), sl2, mneg));
-          if (tail && kv0 + c0 + i >= p.ntok) v = 0.f;
+          float v = ex2_approx(fmaf(__uint_as_float(cur[i]), sl2, mneg));
+          if (TAIL) {
+            if (kv0 + 32 * c + i >= p.ntok) v = 0.f;
+          }
           pv[i] = v;
-          l += v;
+          lsum[i & 3] += v;
         }
-        const uint32_t blk = p_row + (c0 >> 6) * (128 * 128);
+        const uint32_t blk = p_row + ((32 * c) >> 6) * (128 * 128);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const int chunk = ((c0 & 63) >> 3) + ch;
+          const int chunk = (((32 * c) & 63) >> 3) + ch;
           const uint32_t addr = blk + (static_cast<uint32_t>(chunk ^ (row & 7)) << 4);
           const uint32_t w0 = pack_bf16(pv[8 * ch + 0], pv[8 * ch + 1]), w1 = pack_bf16(pv[8 * ch + 2], pv[8 * ch + 3]);
           const uint32_t w2 = pack_bf16(pv[8 * ch + 4], pv[8 * ch + 5]), w3 = pack_bf16(pv[8 * ch + 6], pv[8 * ch + 7]);
@@ -250,7 +274,14 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full(q));
+    };
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full(q), j & 1u);
+      tc_fence_after();
+      if (j * BKV + BKV > p.ntok) tile(j, std::true_type{});
+      else tile(j, std::false_type{});
     }
+    const float l = (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
     // ---- finalize: O / l -> bf16 -> out[b, tok, head*hd + d]
     mbar_wait(pv_done(q), (nkv - 1) & 1u);
     tc_fence_after();
@@ -317,6 +348,7 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     attr_set = true;
   }
   dim3 grid((ntok + 128 * NQ - 1) / (128 * NQ), BH);
+  ProfScope prof(kProfAttention, st, 4.0 * BH * static_cast<double>(ntok) * ntok * HD);
   attention_kernel<HD, BKV, NQ><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
   WC_LAUNCH_CHECK();
   return 0;

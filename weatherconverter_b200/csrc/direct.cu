@@ -228,6 +228,7 @@ int conv_small_cin(const float* x, const float* w, const float* bias, const floa
     WC_CHECK_CUDA(cudaFuncSetAttribute(conv_small_cin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
   const size_t npix = static_cast<size_t>(B) * Ho * Wo;
+  ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * (12.0 * H * W + 2.0 * Ho * Wo * Cout));
   conv_small_cin_kernel<3><<<grid_for(npix, threads / octs), threads, smem, st>>>(
       x, w, bias, scale, shift, y, B, H, W, Ho, Wo, Cout, K, stride, pad, ldy, relu);
   WC_LAUNCH_CHECK();
@@ -243,6 +244,7 @@ int conv_small_cout(const __nv_bfloat16* x, const float* w, const float* bias, f
     WC_CHECK_CUDA(cudaFuncSetAttribute(conv_small_cout_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
   const size_t npix = static_cast<size_t>(B) * H * W;
+  ProfScope prof(kProfBoundaryConv, st, static_cast<double>(npix) * (2.0 * Cin + 4.0 * Cout));
   conv_small_cout_kernel<3><<<grid_for(npix, 128), 128, smem, st>>>(x, w, bias, y, B, H, W, Cin, K, ldx, tanh_out);
   WC_LAUNCH_CHECK();
   return 0;

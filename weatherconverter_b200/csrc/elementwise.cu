@@ -122,6 +122,7 @@ int ddpm_step(const float* xt, const float* eps, const float* z, float* out, flo
   WC_REQUIRE(n_per_sample % 4 == 0, "elements per sample must be a multiple of 4");
   StepCoef c{beta, s, sqrt_alpha, sigma};
   const size_t n4 = n_per_sample / 4;
+  ProfScope prof(kProfScheduler, st, 4.0 * n_per_sample * B * (2 + (z ? 1 : 0) + (out ? 1 : 0) + (mean_out ? 1 : 0) + (sigz_out ? 1 : 0)));
   ddpm_step_kernel<false><<<grid_for(n4 * B), 256, 0, st>>>(
       reinterpret_cast<const float4*>(xt), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(z),
       reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(mean_out), reinterpret_cast<float4*>(sigz_out), n4, B,

@@ -269,6 +269,7 @@ int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
     WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
+  ProfScope prof(kProfIgemm, stream, plan.flops);
   igemm_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
   WC_LAUNCH_CHECK();
   return 0;

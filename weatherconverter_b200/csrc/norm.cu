@@ -121,6 +121,7 @@ int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int 
   if (nsplit > 64) nsplit = 64;
   if (nsplit < 1) nsplit = 1;
   float2* partial = reinterpret_cast<float2*>(workspace);
+  ProfScope prof(kProfGroupNorm, st, 6.0 * B * static_cast<double>(HW) * C);  // algorithmic bytes: 2 reads + 1 write, bf16
   gn_stats_kernel<<<dim3(nsplit, B), threads, threads * sizeof(float2), st>>>(x, HW, C, ld, nsplit, partial);
   WC_LAUNCH_CHECK();
   int asplit = (8 * num_sms() + B - 1) / B;

@@ -23,6 +23,8 @@ int conv_small_cout(const __nv_bfloat16* x, const float* w, const float* bias, f
                     int Cout, int K, int ldx, int tanh_out, cudaStream_t st);
 int nchw_f32_to_nhwc_bf16(const float* x, __nv_bfloat16* y, int B, int C, int HW, int ldy, cudaStream_t st);
 int nhwc_bf16_to_nchw_f32(const __nv_bfloat16* x, float* y, int B, int C, int HW, int ldx, cudaStream_t st);
+void prof_start();
+int prof_stop(double* ms, long long* count, double* work);
 int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                       int heads, int ntok, int hd, int ldo, cudaStream_t st);
 }  // namespace wc
@@ -37,6 +39,10 @@ extern "C" {
 const char* wc_last_error(void) { return last_error_cstr(); }
 int wc_abi_version(void) { return 1; }
 long long wc_launch_count(void) { return launch_count(); }
+void wc_profile_begin(void) { prof_start(); }
+int wc_profile_end(double* ms_by_class, long long* count_by_class, double* work_by_class) {
+  return prof_stop(ms_by_class, count_by_class, work_by_class);
+}
 
 int wc_ddpm_step(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
                  size_t n_per_sample, int batch, float beta, float sqrt_one_minus_acp, float sqrt_alpha, float sigma,

@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace wc {
 
@@ -20,6 +21,39 @@ const char* last_error_cstr() { return g_last_error.c_str(); }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
+struct ProfRec { int cls; cudaEvent_t a, b; double work; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+bool profiling_enabled() { return g_prof_on; }
+void prof_begin_launch(int cls, cudaStream_t st, double work) {
+  ProfRec r{cls, nullptr, nullptr, work};
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void prof_end_launch(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
+void prof_start() {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+}
+int prof_stop(double* ms, long long* count, double* work) {
+  g_prof_on = false;
+  for (int i = 0; i < kProfNumClasses; ++i) { ms[i] = 0; count[i] = 0; work[i] = 0; }
+  for (auto& r : g_prof) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return fail("profiling: event sync failed");
+    float t = 0;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms[r.cls] += t; count[r.cls] += 1; work[r.cls] += r.work;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return 0;
+}
 
 int num_sms() {
   static int sms = 0;

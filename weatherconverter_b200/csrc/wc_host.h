@@ -33,6 +33,23 @@ long long launch_count();
     WC_CHECK_CUDA(cudaGetLastError());  \
   } while (0)
 
+// Optional per-launch timing with CUDA events on the launching stream (bench.py roofline leg).
+enum ProfClass : int { kProfIgemm = 0, kProfAttention = 1, kProfGroupNorm = 2, kProfBoundaryConv = 3, kProfScheduler = 4,
+                       kProfOther = 5, kProfNumClasses = 8 };
+bool profiling_enabled();
+void prof_begin_launch(int cls, cudaStream_t st, double work);
+void prof_end_launch(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(int cls, cudaStream_t s, double work) : st(s), on(profiling_enabled()) {
+    if (on) prof_begin_launch(cls, st, work);
+  }
+  ~ProfScope() {
+    if (on) prof_end_launch(st);
+  }
+};
+
 int num_sms();
 const char* last_error_cstr();
 
