@@ -76,6 +76,27 @@ int wc_conv_in(const float* x, const float* weight, const float* bias, const flo
                void* stream);
 int wc_conv_out(const wc_bf16* x, const float* weight, const float* bias, float* y, int batch, int H, int W, int Cin,
                 int K, int ldx, int tanh_out, void* stream);
+/* Data gradient of nn.Conv2d (what loss.backward() computes for the conv inputs, seg_model/inference.py:141):
+ * dz nhwc_bf16 [B,Ho,Wo,Cout], weight fp32 [Cout,Cin,K,K]; dx nhwc_bf16 [B,Ho*stride,Wo*stride,Cin]
+ * (+ residual, then zeroed where mask <= 0: the fused ReLU derivative). */
+int wc_conv2d_dgrad(const wc_bf16* dz, int batch, int Ho, int Wo, int Cout, const float* weight, int Cin, int K, int stride,
+                    int dil, const wc_bf16* residual, const wc_bf16* mask, wc_bf16* dx, void* stream);
+/* nn.MaxPool2d(3,2,1) forward (argmax taps saved in idx, one byte per output element) and backward fused with the
+ * ReLU derivative of the pooled activation x (resnet.py:144-145). */
+int wc_maxpool3x3s2(const wc_bf16* x, wc_bf16* y, uint8_t* idx, int batch, int H, int W, int C, void* stream);
+int wc_maxpool3x3s2_bwd(const wc_bf16* dy, const uint8_t* idx, const wc_bf16* x, wc_bf16* dx, int batch, int H, int W, int C,
+                        void* stream);
+/* F.interpolate(mode='bilinear', align_corners=False) on nhwc_bf16 and its adjoint (optional ReLU mask). */
+int wc_bilinear(const wc_bf16* x, wc_bf16* y, int batch, int Hi, int Wi, int Ho, int Wo, int C, void* stream);
+int wc_bilinear_bwd(const wc_bf16* dy, const wc_bf16* mask, wc_bf16* dx, int batch, int Hi, int Wi, int Ho, int Wo, int C,
+                    void* stream);
+/* Loss head (network/utils.py:17 + inference.py:135-141): low-res logits nchw_f32 [B,19,h,w] -> full-res argmax,
+ * per-image CE(ignore 255) and d loss / d logits, full-res (f32 [B,H,W,19]) and pulled back to low-res
+ * (nhwc_bf16 [B,h,w,32], optional).  n_valid_ws: int[B] scratch. */
+int wc_seg_loss_head(const float* logits_lo, const int64_t* labels, int* n_valid_ws, int64_t* pred, float* dlogit_hi,
+                     float* loss, float* logits_hi, wc_bf16* dlogit_lo, int batch, int h, int w, int H, int W, void* stream);
+/* Data gradient of the 7x7/2 stem convolution (64 output channels) to the nchw_f32 image (resnet.py:142). */
+int wc_conv1_dgrad(const wc_bf16* dz, const float* weight, const float* scale, float* dx, int batch, int H, int W, void* stream);
 /* layout converters between the reference boundary layout and the internal one */
 int wc_nchw_f32_to_nhwc_bf16(const float* x, wc_bf16* y, int batch, int C, int hw, int ldy, void* stream);
 int wc_nhwc_bf16_to_nchw_f32(const wc_bf16* x, float* y, int batch, int C, int hw, int ldx, void* stream);
@@ -110,6 +131,22 @@ int wc_unet_forward(wc_unet* net, const float* x, const int64_t* t, int n_t, flo
 double wc_unet_flops(const wc_unet* net);
 /* Kernel launches per forward of the last bound shape. */
 int wc_unet_launches(const wc_unet* net);
+
+/* ---- model-level: DeepLabV3+ ResNet-50/101 os16 forward + CE + input gradient ------------------------------
+ * (seg_model/network/*, seg_model/inference.py:118-152).  blocks_per_layer = {3,4,6,3} (R50) or {3,4,23,3} (R101).
+ * names/ptrs: the reference state_dict (fp32 device tensors; num_batches_tracked entries may be omitted). */
+typedef struct wc_seg wc_seg;
+int wc_seg_create(wc_seg** out, const int* blocks_per_layer, int num_classes, int n_params, const char* const* names,
+                  const float* const* ptrs, void* stream);
+void wc_seg_destroy(wc_seg* net);
+size_t wc_seg_workspace_bytes(const wc_seg* net, int batch, int H, int W, int with_grad);
+/* infer(): x nchw_f32 [B,3,H,W]; labels int64 [B,H,W] (255 = ignore); outputs (each may be NULL): pred int64 [B,H,W]
+ * (argmax), input_grad nchw_f32 [B,3,H,W] (d loss_b / d x_b, loss_b = CE mean over image b's valid pixels; NULL
+ * skips the backward pass), loss f32 [B], logits nchw_f32 [B,19,H,W]. */
+int wc_seg_infer(wc_seg* net, const float* x, const int64_t* labels, int64_t* pred, float* input_grad, float* loss,
+                 float* logits, int batch, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+double wc_seg_flops(const wc_seg* net, int backward);
+int wc_seg_launches(const wc_seg* net);
 
 #ifdef __cplusplus
 }

@@ -15,21 +15,58 @@ import torch.nn.functional as F
 
 LAYERS = {"resnet50": [3, 4, 6, 3], "resnet101": [3, 4, 23, 3]}
 
+# Optional storage-precision emulation (tests only): when set to "bf16", every activation that the CUDA path stores
+# in bf16 is rounded to bf16 here too (straight-through in autograd) and conv weights are rounded to bf16.  This
+# separates "bf16 storage changes ReLU on/off patterns" from genuine implementation differences.
+EMULATE = None
+
+
+class _RoundBoth(torch.autograd.Function):
+    """bf16 rounding of an activation in the forward pass AND of its gradient in the backward pass (the CUDA path
+    stores both in bf16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+def _q(x):
+    return _RoundBoth.apply(x) if EMULATE == "bf16" else x
+
+
+def _qw(w):
+    return w.to(torch.bfloat16).float() if EMULATE == "bf16" else w
+
 
 def _bn(sd, p, x):
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
                         False, 0.0, 1e-5)
 
 
+def _cb(sd, wkey, bnkey, x, **kw):
+    """conv + eval BatchNorm.  Reference order (conv, then batch_norm) unless EMULATE: then BN is folded into the
+    weights BEFORE the bf16 rounding, exactly like the CUDA path packs them (csrc/seg.cu: conv_bn)."""
+    w = sd[wkey + ".weight"]
+    if EMULATE == "bf16":
+        scale = sd[bnkey + ".weight"] / torch.sqrt(sd[bnkey + ".running_var"] + 1e-5)
+        shift = sd[bnkey + ".bias"] - sd[bnkey + ".running_mean"] * scale
+        wf = (w * scale[:, None, None, None]).to(torch.bfloat16).float()
+        return F.conv2d(x, wf, **kw) + shift[None, :, None, None]
+    return _bn(sd, bnkey, F.conv2d(x, w, **kw))
+
+
 def _bottleneck(sd, p, x, stride, dilation, has_down):
-    out = F.relu(_bn(sd, p + ".bn1", F.conv2d(x, sd[p + ".conv1.weight"])))
-    out = F.conv2d(out, sd[p + ".conv2.weight"], stride=stride, padding=dilation, dilation=dilation)
-    out = F.relu(_bn(sd, p + ".bn2", out))
-    out = _bn(sd, p + ".bn3", F.conv2d(out, sd[p + ".conv3.weight"]))
+    out = _q(F.relu(_cb(sd, p + ".conv1", p + ".bn1", x)))
+    out = _q(F.relu(_cb(sd, p + ".conv2", p + ".bn2", out, stride=stride, padding=dilation, dilation=dilation)))
+    out = _cb(sd, p + ".conv3", p + ".bn3", out)
     idt = x
     if has_down:
-        idt = _bn(sd, p + ".downsample.1", F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride))
-    return F.relu(out + idt)
+        idt = _q(_cb(sd, p + ".downsample.0", p + ".downsample.1", x, stride=stride))
+    return _q(F.relu(out + idt))
 
 
 def block_plan(backbone="resnet50"):
@@ -53,7 +90,7 @@ def block_plan(backbone="resnet50"):
 def deeplab_forward(sd, x, backbone="resnet50", taps=None):
     """x [B,3,H,W] -> logits [B,nc,H,W]."""
     H, W = x.shape[-2:]
-    h = F.relu(_bn(sd, "backbone.bn1", F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=3)))
+    h = _q(F.relu(_bn(sd, "backbone.bn1", F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=3))))  # fp32 weights in both
     h = F.max_pool2d(h, 3, 2, 1)
     low = None
     for (p, _, _, stride, dil, has_down) in block_plan(backbone):
@@ -63,18 +100,17 @@ def deeplab_forward(sd, x, backbone="resnet50", taps=None):
     if taps is not None:
         taps["low"], taps["out"] = low, h
     c = "classifier"
-    ll = F.relu(_bn(sd, c + ".project.1", F.conv2d(low, sd[c + ".project.0.weight"])))
-    res = [F.relu(_bn(sd, c + ".aspp.convs.0.1", F.conv2d(h, sd[c + ".aspp.convs.0.0.weight"])))]
+    ll = _q(F.relu(_cb(sd, c + ".project.0", c + ".project.1", low)))
+    res = [_q(F.relu(_cb(sd, c + ".aspp.convs.0.0", c + ".aspp.convs.0.1", h)))]
     for k, r in zip((1, 2, 3), (6, 12, 18)):
-        res.append(F.relu(_bn(sd, f"{c}.aspp.convs.{k}.1",
-                              F.conv2d(h, sd[f"{c}.aspp.convs.{k}.0.weight"], padding=r, dilation=r))))
-    g = F.adaptive_avg_pool2d(h, 1)
-    g = F.relu(_bn(sd, c + ".aspp.convs.4.2", F.conv2d(g, sd[c + ".aspp.convs.4.1.weight"])))
+        res.append(_q(F.relu(_cb(sd, f"{c}.aspp.convs.{k}.0", f"{c}.aspp.convs.{k}.1", h, padding=r, dilation=r))))
+    g = _q(F.adaptive_avg_pool2d(h, 1))
+    g = _q(F.relu(_cb(sd, c + ".aspp.convs.4.1", c + ".aspp.convs.4.2", g)))
     res.append(F.interpolate(g, size=h.shape[-2:], mode="bilinear", align_corners=False))
-    a = F.relu(_bn(sd, c + ".aspp.project.1", F.conv2d(torch.cat(res, 1), sd[c + ".aspp.project.0.weight"])))
-    a = F.interpolate(a, size=ll.shape[-2:], mode="bilinear", align_corners=False)
-    y = F.relu(_bn(sd, c + ".classifier.1", F.conv2d(torch.cat([ll, a], 1), sd[c + ".classifier.0.weight"], padding=1)))
-    y = F.conv2d(y, sd[c + ".classifier.3.weight"], sd[c + ".classifier.3.bias"])
+    a = _q(F.relu(_cb(sd, c + ".aspp.project.0", c + ".aspp.project.1", torch.cat(res, 1))))
+    a = _q(F.interpolate(a, size=ll.shape[-2:], mode="bilinear", align_corners=False))
+    y = _q(F.relu(_cb(sd, c + ".classifier.0", c + ".classifier.1", torch.cat([ll, a], 1), padding=1)))
+    y = F.conv2d(y, _qw(sd[c + ".classifier.3.weight"]), sd[c + ".classifier.3.bias"])
     if taps is not None:
         taps["aspp"], taps["logits_lowres"] = a, y
     return F.interpolate(y, size=(H, W), mode="bilinear", align_corners=False)

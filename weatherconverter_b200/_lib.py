@@ -44,6 +44,13 @@ _SIGS = {
     "wc_groupnorm_silu": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_float, C.c_int, c_ptr, c_ptr]),
     "wc_conv2d": (C.c_int, [c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr] + [C.c_int] * 6 + [c_ptr, c_ptr, C.c_int, c_ptr,
                             C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int, c_ptr]),
+    "wc_conv2d_dgrad": (C.c_int, [c_ptr] + [C.c_int] * 4 + [c_ptr] + [C.c_int] * 4 + [c_ptr] * 4),
+    "wc_maxpool3x3s2": (C.c_int, [c_ptr] * 3 + [C.c_int] * 4 + [c_ptr]),
+    "wc_maxpool3x3s2_bwd": (C.c_int, [c_ptr] * 4 + [C.c_int] * 4 + [c_ptr]),
+    "wc_bilinear": (C.c_int, [c_ptr] * 2 + [C.c_int] * 6 + [c_ptr]),
+    "wc_bilinear_bwd": (C.c_int, [c_ptr] * 3 + [C.c_int] * 6 + [c_ptr]),
+    "wc_seg_loss_head": (C.c_int, [c_ptr] * 8 + [C.c_int] * 5 + [c_ptr]),
+    "wc_conv1_dgrad": (C.c_int, [c_ptr] * 4 + [C.c_int] * 3 + [c_ptr]),
     "wc_conv_in": (C.c_int, [c_ptr] * 6 + [C.c_int] * 9 + [c_ptr]),
     "wc_conv_out": (C.c_int, [c_ptr] * 4 + [C.c_int] * 7 + [c_ptr]),
     "wc_nchw_f32_to_nhwc_bf16": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 4 + [c_ptr]),
@@ -57,6 +64,13 @@ _SIGS = {
                                   c_ptr]),
     "wc_unet_flops": (C.c_double, [c_ptr]),
     "wc_unet_launches": (C.c_int, [c_ptr]),
+    "wc_seg_create": (C.c_int, [C.POINTER(c_ptr), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_char_p),
+                                C.POINTER(c_ptr), c_ptr]),
+    "wc_seg_destroy": (None, [c_ptr]),
+    "wc_seg_workspace_bytes": (C.c_size_t, [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "wc_seg_infer": (C.c_int, [c_ptr] * 7 + [C.c_int] * 3 + [c_ptr, C.c_size_t, c_ptr]),
+    "wc_seg_flops": (C.c_double, [c_ptr, C.c_int]),
+    "wc_seg_launches": (C.c_int, [c_ptr]),
 }
 
 EXPORTS = tuple(_SIGS.keys())

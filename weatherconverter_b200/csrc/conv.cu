@@ -5,7 +5,7 @@
 namespace wc {
 
 int pack_tap(__nv_bfloat16* dst, int ldk, int koff, const float* src, int Nn, int Cc, int Cpad, int KH, int KW, int ky,
-             int kx, int transpose, const float* scale, cudaStream_t st);
+             int kx, int transpose, const float* scale, int row_mul, int row_off, cudaStream_t st);
 
 DeviceArena::~DeviceArena() {
   for (void* p : ptrs_) cudaFree(p);
@@ -31,7 +31,7 @@ struct TapDef {
   int C;  // true input channels of this tap
 };
 
-int out_channels_of(const WeightSrc& w) { return w.transpose ? w.d1 : w.d0; }
+int out_channels_of(const WeightSrc& w) { return w.n_out > 0 ? w.n_out : (w.transpose ? w.d1 : w.d0); }
 int in_channels_of(const WeightSrc& w) { return w.transpose ? w.d0 : w.d1; }
 
 // Pack weights for a tap list and fill everything of the plan except the A tensor maps.
@@ -72,7 +72,7 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
     WC_REQUIRE(n_src <= N, "weight has more output channels than N");
     const int cpad = (t.C + kIgemmBK - 1) / kIgemmBK * kIgemmBK;
     const int ky = w.flip ? w.KH - 1 - t.ky : t.ky, kx = w.flip ? w.KW - 1 - t.kx : t.kx;
-    if (int e = pack_tap(wp, ktotal, koff, w.w, n_src, t.C, cpad, w.KH, w.KW, ky, kx, w.transpose, w.scale, st)) return e;
+    if (int e = pack_tap(wp, ktotal, koff, w.w, n_src, t.C, cpad, w.KH, w.KW, ky, kx, w.transpose, w.scale, w.row_mul, w.row_off, st)) return e;
     koff += cpad;
     macs_per_pixel += static_cast<double>(t.C) * n_src;
   }
@@ -96,6 +96,7 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
     a.mask = ep.mask->ptr; a.ldm = ep.mask->ld;
   }
   a.relu = ep.relu;
+  a.prelu = ep.prelu;
   a.out_mode = out.mode;
   a.sy = sy; a.sx = sx; a.py = py; a.px = px;
   a.Ho = H * sy; a.Wo = W * sx;
@@ -121,7 +122,7 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
 int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w, const ConvGeom& g, int N,
                const Act* x2, const WeightSrc* w2, const Epilogue& ep, const OutSpec& out, cudaStream_t st) {
   WC_REQUIRE(x.C == in_channels_of(w), "input channels do not match the weight");
-  WC_REQUIRE(x.C % 8 == 0 && x.ld % 8 == 0, "input channels / stride must be multiples of 8");
+  WC_REQUIRE(x.ld % 8 == 0, "input pixel stride must be a multiple of 8 elements");
   op->plans.clear();
   op->plans.emplace_back();
   IgemmPlan& plan = op->plans.back();

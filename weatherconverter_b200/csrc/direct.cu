@@ -170,15 +170,15 @@ __global__ void linear_rows_kernel(const float* __restrict__ in, int dim, const 
 // (ConvTranspose2d weight, or a dgrad view of a Conv2d weight).  scale (optional) is indexed by the src dim-0.
 __global__ void pack_tap_kernel(__nv_bfloat16* __restrict__ dst, int ldk, int koff, const float* __restrict__ src,
                                 int Nn, int Cc, int Cpad, int KH, int KW, int ky, int kx, int transpose,
-                                const float* __restrict__ scale) {
+                                const float* __restrict__ scale, int row_mul, int row_off, int D0, int D1src) {
   const size_t total = static_cast<size_t>(Nn) * Cpad;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % Cpad), n = static_cast<int>(i / Cpad);
     float v = 0.f;
     if (c < Cc) {
-      const size_t d0 = transpose ? c : n, d1 = transpose ? n : c;
-      const size_t D1 = transpose ? Nn : Cc;
+      const size_t d0 = transpose ? c : static_cast<size_t>(n) * row_mul + row_off, d1 = transpose ? n : c;
+      const size_t D1 = D1src;
       v = src[((d0 * D1 + d1) * KH + ky) * KW + kx];
       if (scale) v *= scale[d0];
     }
@@ -267,9 +267,11 @@ int linear_rows(const float* in, int Bt, int dim, const float* w, const float* b
 }
 
 int pack_tap(__nv_bfloat16* dst, int ldk, int koff, const float* src, int Nn, int Cc, int Cpad, int KH, int KW, int ky,
-             int kx, int transpose, const float* scale, cudaStream_t st) {
+             int kx, int transpose, const float* scale, int row_mul, int row_off, cudaStream_t st) {
+  // source dim-1 extent: transposed sources are [Cc][Nn], plain sources [rows][Cc]
   pack_tap_kernel<<<grid_for(static_cast<size_t>(Nn) * Cpad), 256, 0, st>>>(dst, ldk, koff, src, Nn, Cc, Cpad, KH, KW,
-                                                                           ky, kx, transpose, scale);
+                                                                           ky, kx, transpose, scale, row_mul, row_off, 0,
+                                                                           transpose ? Nn : Cc);
   WC_LAUNCH_CHECK();
   return 0;
 }

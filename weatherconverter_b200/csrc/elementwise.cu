@@ -94,8 +94,8 @@ sgg_update_kernel(const float* __restrict__ grad, const float* __restrict__ mu, 
       float s = 0.f;  // F.avg_pool2d accumulates in fp32 then scales
       for (int dy = 0; dy < pool; ++dy)
         for (int dx = 0; dx < pool; ++dx) s = __fadd_rn(s, gp[static_cast<size_t>(dy) * Ws + dx]);
-      const double g = static_cast<double>(__fdiv_rn(s, area)) * stdv[c];
-      acc += g * g;
+      const double g = __dmul_rn(static_cast<double>(__fdiv_rn(s, area)), stdv[c]);
+      acc = __dadd_rn(acc, __dmul_rn(g, g));  // no FMA contraction: numpy squares, then sums
     }
     const double mag = sqrt(acc);
     if (mag_out) mag_out[i] = static_cast<float>(mag);
@@ -104,7 +104,7 @@ sgg_update_kernel(const float* __restrict__ grad, const float* __restrict__ mu, 
       const double sz = static_cast<double>(sigz[o]);
       // reference: (mu + ((lam*sigma) * mag)) + sigma, evaluated in float64 after promotion (D7)
       const double lam_s = static_cast<double>(__fmul_rn(lam, sigz[o]));
-      out[o] = static_cast<float>((static_cast<double>(mu[o]) + lam_s * mag) + sz);
+      out[o] = static_cast<float>(__dadd_rn(__dadd_rn(static_cast<double>(mu[o]), __dmul_rn(lam_s, mag)), sz));
     }
   }
 }

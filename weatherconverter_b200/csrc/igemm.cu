@@ -64,6 +64,14 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
 #pragma unroll
       for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.f);
     }
+    if (p.prelu) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        float4 sv = __ldg(reinterpret_cast<const float4*>(p.prelu + nb + j));
+        v[j] = v[j] > 0.f ? v[j] : v[j] * sv.x; v[j + 1] = v[j + 1] > 0.f ? v[j + 1] : v[j + 1] * sv.y;
+        v[j + 2] = v[j + 2] > 0.f ? v[j + 2] : v[j + 2] * sv.z; v[j + 3] = v[j + 3] > 0.f ? v[j + 3] : v[j + 3] * sv.w;
+      }
+    }
     if (p.mask) {
       const uint4* mp = reinterpret_cast<const uint4*>(p.mask + opix * p.ldm + nb);
 #pragma unroll

@@ -47,6 +47,7 @@ struct IgemmArgs {
   const __nv_bfloat16* mask;  // ReLU-derivative mask on the output grid: result zeroed where mask <= 0, or nullptr
   int ldm;
   int relu;
+  const float* prelu;  // per-channel PReLU slopes [N] applied after bias/residual, or nullptr
   int out_mode;
   __nv_bfloat16* out;  // kOutNHWC: element (b, y*sy+py, x*sx+px, n) of a [B,Ho,Wo,ldc] buffer
   int ldc, Ho, Wo, sy, sx, py, px;

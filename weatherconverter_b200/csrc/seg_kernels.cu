@@ -1,0 +1,550 @@
+// Bandwidth-bound kernels of the DeepLabV3+ forward / input-gradient path and of the SRGAN generator
+// (NHWC bf16 activations).  Reference ops:
+//   resnet.py:145 MaxPool2d(3,2,1) (+ its backward), _deeplab.py:125-131 AdaptiveAvgPool2d(1) + bilinear broadcast,
+//   _deeplab.py:50 / network/utils.py:17 F.interpolate(bilinear, align_corners=False) (+ adjoints),
+//   seg_model/inference.py:124-141 argmax + CrossEntropyLoss(ignore_index=255) + backward,
+//   srgan_model/models.py:5-21 depthwise convolutions.
+#include "wc_host.h"
+#include "wc_ptx.cuh"
+
+namespace wc {
+
+namespace {
+
+inline int grid_for(size_t n_items, int per_block = 256) {
+  const size_t blocks = (n_items + per_block - 1) / per_block;
+  const size_t cap = static_cast<size_t>(num_sms()) * 16;
+  return static_cast<int>(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+// scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (eval-mode BatchNorm folded into the conv)
+__global__ void bn_fold_kernel(const float* g, const float* b, const float* mean, const float* var, float eps,
+                               float* scale, float* shift, int n, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  if (i < n) {
+    const float s = g[i] / sqrtf(var[i] + eps);
+    scale[i] = s;
+    shift[i] = b[i] - mean[i] * s;
+  } else {
+    scale[i] = 0.f;
+    shift[i] = 0.f;
+  }
+}
+
+// ---- MaxPool 3x3 s2 p1, NHWC bf16, 8 channels per thread; stores the argmax tap (0..8) per element.
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   uint8_t* __restrict__ idx, int B, int H, int W, int C, int Ho, int Wo) {
+  const int c8n = C / 8;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * c8n;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % c8n);
+    size_t p = i / c8n;
+    const int ox = static_cast<int>(p % Wo), oy = static_cast<int>((p / Wo) % Ho), b = static_cast<int>(p / (static_cast<size_t>(Wo) * Ho));
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + iy) * W + ix) * C + c8 * 8));
+        float f[8];
+        float2 t;
+        t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+        t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+        t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+        t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > best[j]) { best[j] = f[j]; bi[j] = ky * 3 + kx; }  // first maximum wins (PyTorch order)
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(best[0], best[1]); o.y = pack_bf16(best[2], best[3]);
+    o.z = pack_bf16(best[4], best[5]); o.w = pack_bf16(best[6], best[7]);
+    *reinterpret_cast<uint4*>(y + p * C + c8 * 8) = o;
+    uint2 ii;
+    ii.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    ii.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + p * C + c8 * 8) = ii;
+  }
+}
+
+// dX[b,iy,ix,c] = sum over the (<= 4) pooling windows containing (iy,ix) whose argmax is this pixel; then the
+// ReLU mask of the pre-pool activation (x > 0) is applied (conv1+bn1+relu precede the pool, resnet.py:142-145).
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                   const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx, int B, int H,
+                                   int W, int C, int Ho, int Wo) {
+  const size_t total = static_cast<size_t>(B) * H * W * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    size_t p = i / C;
+    const int ix = static_cast<int>(p % W), iy = static_cast<int>((p / W) % H), b = static_cast<int>(p / (static_cast<size_t>(W) * H));
+    float acc = 0.f;
+    if (__bfloat162float(x[i]) > 0.f) {
+      for (int oy = (iy) / 2; oy <= (iy + 1) / 2; ++oy) {   // windows with 2*oy-1 <= iy <= 2*oy+1
+        if (oy < 0 || oy >= Ho) continue;
+        const int ky = iy - (2 * oy - 1);
+        if (ky < 0 || ky > 2) continue;
+        for (int ox = (ix) / 2; ox <= (ix + 1) / 2; ++ox) {
+          if (ox < 0 || ox >= Wo) continue;
+          const int kx = ix - (2 * ox - 1);
+          if (kx < 0 || kx > 2) continue;
+          const size_t q = ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * C + c;
+          if (idx[q] == ky * 3 + kx) acc += __bfloat162float(dy[q]);
+        }
+      }
+    }
+    dx[i] = __float2bfloat16_rn(acc);
+  }
+}
+
+// ---- global average pool: x [B,HW,C] (ld) -> y [B,C]; one block per (b, 64-channel slab)
+__global__ void gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int HW, int C, int ld) {
+  __shared__ float red[4][64];
+  const int b = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
+  float acc = 0.f;
+  if (c < C)
+    for (int p = part; p < HW; p += 4) acc += __bfloat162float(x[(static_cast<size_t>(b) * HW + p) * ld + c]);
+  red[part][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (part == 0 && c < C)
+    y[static_cast<size_t>(b) * C + c] = __float2bfloat16_rn((red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]) / HW);
+}
+// y[b,p,c] (ldy) = v[b,c]  (bilinear up-sampling of a 1x1 map = broadcast, _deeplab.py:131)
+__global__ void broadcast_kernel(const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ y, int B, int HW, int C, int ldy) {
+  const int c8n = C / 8;
+  const size_t total = static_cast<size_t>(B) * HW * c8n;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % c8n);
+    const size_t p = i / c8n, b = p / HW;
+    *reinterpret_cast<uint4*>(y + p * ldy + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(v + b * C + c8 * 8));
+  }
+}
+// adjoint of broadcast: v[b,c] = sum_p y[b,p,c], optionally masked by (m[b,c] > 0) (ReLU of the pooled branch)
+__global__ void sum_hw_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ m,
+                              __nv_bfloat16* __restrict__ v, int HW, int C, int ldy) {
+  __shared__ float red[4][64];
+  const int b = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
+  float acc = 0.f;
+  if (c < C)
+    for (int p = part; p < HW; p += 4) acc += __bfloat162float(y[(static_cast<size_t>(b) * HW + p) * ldy + c]);
+  red[part][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (part == 0 && c < C) {
+    float s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    if (m && !(__bfloat162float(m[static_cast<size_t>(b) * C + c]) > 0.f)) s = 0.f;
+    v[static_cast<size_t>(b) * C + c] = __float2bfloat16_rn(s);
+  }
+}
+// adjoint of the global average pool, accumulated into dx: dx[b,p,c] += g[b,c] / HW
+__global__ void gap_bwd_add_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dx, int B, int HW, int C, int ld) {
+  const size_t total = static_cast<size_t>(B) * HW * C;
+  const float inv = 1.f / HW;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const size_t p = i / C, b = p / HW;
+    __nv_bfloat16* d = dx + p * ld + c;
+    *d = __float2bfloat16_rn(__bfloat162float(*d) + __bfloat162float(g[b * C + c]) * inv);
+  }
+}
+
+// ---- bilinear resize, align_corners=False (PyTorch area_pixel_compute_source_index semantics)
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float src = (dst + 0.5f) * scale - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = static_cast<int>(src);
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - i0;
+}
+
+// NHWC bf16 -> NHWC bf16 (channel slice views allowed), 8 channels per thread
+__global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int Hi,
+                                    int Wi, int Ho, int Wo, int C, int ldx, int ldy) {
+  const int c8n = C / 8;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo * c8n;
+  const float sy = static_cast<float>(Hi) / Ho, sx = static_cast<float>(Wi) / Wo;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % c8n);
+    size_t p = i / c8n;
+    const int ox = static_cast<int>(p % Wo), oy = static_cast<int>((p / Wo) % Ho), b = static_cast<int>(p / (static_cast<size_t>(Wo) * Ho));
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(oy, sy, Hi, y0, y1, ly);
+    bilinear_src(ox, sx, Wi, x0, x1, lx);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const __nv_bfloat16* xb = x + static_cast<size_t>(b) * Hi * Wi * ldx + c8 * 8;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(xb + (static_cast<size_t>(y0) * Wi + x0) * ldx));
+    const uint4 bq = __ldg(reinterpret_cast<const uint4*>(xb + (static_cast<size_t>(y0) * Wi + x1) * ldx));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(xb + (static_cast<size_t>(y1) * Wi + x0) * ldx));
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(xb + (static_cast<size_t>(y1) * Wi + x1) * ldx));
+    const uint32_t* pa = &a.x; const uint32_t* pb = &bq.x; const uint32_t* pc = &c.x; const uint32_t* pd = &d.x;
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = unpack_bf16(pa[j]), fb = unpack_bf16(pb[j]), fc = unpack_bf16(pc[j]), fd = unpack_bf16(pd[j]);
+      o[j] = pack_bf16(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x, w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+    }
+    *reinterpret_cast<uint4*>(y + p * ldy + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Adjoint (gather form): dx[b,iy,ix,c] = sum over output pixels whose 2x2 stencil touches (iy,ix).  For an integer
+// up-sampling factor f every input pixel is touched by outputs within [f*i - f, f*i + 2f) per axis.
+// Optional ReLU mask (m > 0).  Source may be a channel slice (ldy); fp32 accumulation.
+__global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ m,
+                                    __nv_bfloat16* __restrict__ dx, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                                    int ldy, int ldm, int ldx) {
+  const size_t total = static_cast<size_t>(B) * Hi * Wi * C;
+  const float sy = static_cast<float>(Hi) / Ho, sx = static_cast<float>(Wi) / Wo;
+  const int fy = (Ho + Hi - 1) / Hi, fx = (Wo + Wi - 1) / Wi;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    size_t p = i / C;
+    const int ix = static_cast<int>(p % Wi), iy = static_cast<int>((p / Wi) % Hi), b = static_cast<int>(p / (static_cast<size_t>(Wi) * Hi));
+    float acc = 0.f;
+    const bool live = !m || (__bfloat162float(m[p * ldm + c]) > 0.f);
+    if (live) {
+      const int oy_lo = max(0, fy * iy - fy - 1), oy_hi = min(Ho - 1, fy * iy + 2 * fy);
+      const int ox_lo = max(0, fx * ix - fx - 1), ox_hi = min(Wo - 1, fx * ix + 2 * fx);
+      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        int y0, y1; float ly;
+        bilinear_src(oy, sy, Hi, y0, y1, ly);
+        float wy = 0.f;
+        if (y0 == iy) wy += 1.f - ly;
+        if (y1 == iy) wy += ly;
+        if (wy == 0.f) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          int x0, x1; float lx;
+          bilinear_src(ox, sx, Wi, x0, x1, lx);
+          float wx = 0.f;
+          if (x0 == ix) wx += 1.f - lx;
+          if (x1 == ix) wx += lx;
+          if (wx == 0.f) continue;
+          acc += wy * wx * __bfloat162float(dy[((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * ldy + c]);
+        }
+      }
+    }
+    dx[p * ldx + c] = __float2bfloat16_rn(acc);
+  }
+}
+
+// ---- segmentation loss head (seg_model/inference.py:124-141 + network/utils.py:17)
+// n_valid[b] = #pixels with label != ignore
+__global__ void count_valid_kernel(const long long* __restrict__ labels, int HW, int ignore, int* __restrict__ n_valid) {
+  const int b = blockIdx.y;
+  int cnt = 0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x)
+    cnt += labels[static_cast<size_t>(b) * HW + p] != ignore;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_valid + b, cnt);
+}
+
+// One thread per full-resolution pixel: bilinear logits (from low-res NCHW fp32 planes), argmax -> pred,
+// softmax-CE: dlogit = (softmax - onehot) / n_valid[b] (0 where ignored) written as fp32 [B,H,W,NCP] (NCP >= NC);
+// per-image loss accumulated with one atomic per warp.
+template <int NC>
+__global__ void seg_loss_grad_kernel(const float* __restrict__ logits_lo, const long long* __restrict__ labels,
+                                     const int* __restrict__ n_valid, long long* __restrict__ pred,
+                                     float* __restrict__ dlogit_hi, float* __restrict__ loss, float* __restrict__ logits_hi,
+                                     int B, int h, int w, int H, int W, int ignore) {
+  const size_t total = static_cast<size_t>(B) * H * W;
+  const float sy = static_cast<float>(h) / H, sx = static_cast<float>(w) / W;
+  // warp-uniform trip count (the loss reduction below uses full-warp shuffles)
+  const size_t lane = threadIdx.x & 31;
+  for (size_t wb = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) - lane; wb < total;
+       wb += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t i = wb + lane;
+    float lsum = 0.f;
+    int b = 0;
+    if (i < total) {
+      const int ox = static_cast<int>(i % W), oy = static_cast<int>((i / W) % H);
+      b = static_cast<int>(i / (static_cast<size_t>(W) * H));
+      int y0, y1, x0, x1;
+      float ly, lx;
+      bilinear_src(oy, sy, h, y0, y1, ly);
+      bilinear_src(ox, sx, w, x0, x1, lx);
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      const size_t plane = static_cast<size_t>(h) * w;
+      const float* lb = logits_lo + static_cast<size_t>(b) * NC * plane;
+      float v[NC];
+      float mx = -INFINITY;
+      int am = 0;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const float* pl = lb + c * plane;
+        v[c] = w00 * pl[y0 * w + x0] + w01 * pl[y0 * w + x1] + w10 * pl[y1 * w + x0] + w11 * pl[y1 * w + x1];
+        if (v[c] > mx) { mx = v[c]; am = c; }
+      }
+      if (pred) pred[i] = am;
+      if (logits_hi) {
+        const size_t pl_hi = static_cast<size_t>(H) * W;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) logits_hi[(static_cast<size_t>(b) * NC + c) * pl_hi + static_cast<size_t>(oy) * W + ox] = v[c];
+      }
+      const long long lab = labels[i];
+      float* d = dlogit_hi + i * NC;
+      if (lab == ignore) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) d[c] = 0.f;
+      } else {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { v[c] = __expf(v[c] - mx); s += v[c]; }
+        const float inv = 1.f / s, invn = 1.f / static_cast<float>(n_valid[b]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) d[c] = (v[c] * inv - (c == lab ? 1.f : 0.f)) * invn;
+        lsum = -__logf(v[lab < NC && lab >= 0 ? lab : 0] * inv) * invn;
+      }
+    }
+    // warp-level loss reduction (warps never straddle images when H*W % 32 == 0; otherwise per-lane atomics)
+    if (loss) {
+      const int b0 = __shfl_sync(0xffffffffu, b, 0);
+      if (__all_sync(0xffffffffu, b == b0)) {
+        float t = lsum;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((threadIdx.x & 31) == 0 && t != 0.f) atomicAdd(loss + b0, t);
+      } else if (lsum != 0.f) {
+        atomicAdd(loss + b, lsum);
+      }
+    }
+  }
+}
+
+// Adjoint of the final bilinear up-sampling for the NC logit channels: dlo[b,y,x,c] (NHWC bf16, ld = ldo, channels
+// >= NC zero-filled up to CP) = sum_hi w * dhi[b,Y,X,c].
+template <int NC>
+__global__ void logits_bilinear_bwd_kernel(const float* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo, int B, int h,
+                                           int w, int H, int W, int CP, int ldo) {
+  const size_t total = static_cast<size_t>(B) * h * w;
+  const float sy = static_cast<float>(h) / H, sx = static_cast<float>(w) / W;
+  const int fy = (H + h - 1) / h, fx = (W + w - 1) / w;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ix = static_cast<int>(i % w), iy = static_cast<int>((i / w) % h), b = static_cast<int>(i / (static_cast<size_t>(w) * h));
+    float acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+    const int oy_lo = max(0, fy * iy - fy - 1), oy_hi = min(H - 1, fy * iy + 2 * fy);
+    const int ox_lo = max(0, fx * ix - fx - 1), ox_hi = min(W - 1, fx * ix + 2 * fx);
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      int y0, y1; float ly;
+      bilinear_src(oy, sy, h, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        int x0, x1; float lx;
+        bilinear_src(ox, sx, w, x0, x1, lx);
+        float wx = 0.f;
+        if (x0 == ix) wx += 1.f - lx;
+        if (x1 == ix) wx += lx;
+        if (wx == 0.f) continue;
+        const float ww = wy * wx;
+        const float* d = dhi + ((static_cast<size_t>(b) * H + oy) * W + ox) * NC;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] += ww * d[c];
+      }
+    }
+    __nv_bfloat16* o = dlo + i * ldo;
+    for (int c = 0; c < CP; ++c) o[c] = __float2bfloat16_rn(c < NC ? acc[c] : 0.f);
+  }
+}
+
+// ---- data gradient of conv1 (7x7, stride 2, pad 3, 3 input channels) to the NCHW fp32 image:
+// dX[b,c,y,x] = sum_{ky,kx: parity ok} sum_o dZ[b,(y+3-ky)/2,(x+3-kx)/2,o] * W[o,c,ky,kx] * scale[o]
+__global__ void conv1_dgrad_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ w /*[64][3][7][7]*/,
+                                   const float* __restrict__ scale, float* __restrict__ dx, int B, int H, int W, int Ho,
+                                   int Wo, int Cout) {
+  extern __shared__ float sw[];  // [49][Cout][3]
+  for (int i = threadIdx.x; i < 49 * Cout * 3; i += blockDim.x) {
+    const int c = i % 3, o = (i / 3) % Cout, t = i / (3 * Cout);
+    sw[i] = w[(static_cast<size_t>(o) * 3 + c) * 49 + t] * (scale ? scale[o] : 1.f);
+  }
+  __syncthreads();
+  const size_t total = static_cast<size_t>(B) * H * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W), y = static_cast<int>((i / W) % H), b = static_cast<int>(i / (static_cast<size_t>(W) * H));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int ky = (y + 3) & 1; ky < 7; ky += 2) {
+      const int oy = (y + 3 - ky) / 2;
+      if (y + 3 - ky < 0 || oy >= Ho) continue;
+      for (int kx = (x + 3) & 1; kx < 7; kx += 2) {
+        const int ox = (x + 3 - kx) / 2;
+        if (x + 3 - kx < 0 || ox >= Wo) continue;
+        const uint4* zp = reinterpret_cast<const uint4*>(dz + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * Cout);
+        const float* wp = sw + static_cast<size_t>(ky * 7 + kx) * Cout * 3;
+        for (int o8 = 0; o8 < Cout / 8; ++o8) {
+          const uint4 u = __ldg(zp + o8);
+          float f[8];
+          float2 t;
+          t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+          t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+          t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+          t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float* ww = wp + (o8 * 8 + j) * 3;
+            a0 = fmaf(f[j], ww[0], a0); a1 = fmaf(f[j], ww[1], a1); a2 = fmaf(f[j], ww[2], a2);
+          }
+        }
+      }
+    }
+    const size_t plane = static_cast<size_t>(H) * W, o = static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(y) * W + x;
+    dx[o] = a0; dx[o + plane] = a1; dx[o + 2 * plane] = a2;
+  }
+}
+
+// d[p,c] = 0 where m[p,c] <= 0 (ReLU derivative applied to a gradient slice in place)
+__global__ void relu_mask_kernel(__nv_bfloat16* __restrict__ d, const __nv_bfloat16* __restrict__ m, size_t npix, int C,
+                                 int ldd, int ldm) {
+  const size_t total = npix * C;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t p = i / C;
+    const int c = static_cast<int>(i % C);
+    if (!(__bfloat162float(m[p * ldm + c]) > 0.f)) d[p * ldd + c] = __float2bfloat16_rn(0.f);
+  }
+}
+
+// ---- composed separable-conv weights (srgan_model/models.py:5-21): W[o,c,ky,kx] = pw[o,c] * dw[c,0,ky,kx];
+// bias[o] = pw_bias[o] + sum_c pw[o,c] * dw_bias[c]
+__global__ void compose_sep_kernel(const float* __restrict__ dw, const float* __restrict__ pw, const float* __restrict__ dwb,
+                                   const float* __restrict__ pwb, float* __restrict__ w, float* __restrict__ bias, int Co,
+                                   int Ci, int KK) {
+  const size_t total = static_cast<size_t>(Co) * Ci * KK;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i % KK), c = static_cast<int>((i / KK) % Ci), o = static_cast<int>(i / (static_cast<size_t>(KK) * Ci));
+    w[i] = pw[static_cast<size_t>(o) * Ci + c] * dw[static_cast<size_t>(c) * KK + t];
+  }
+  if (bias) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < Co; o += gridDim.x * blockDim.x) {
+      float s = pwb ? pwb[o] : 0.f;
+      if (dwb)
+        for (int c = 0; c < Ci; ++c) s += pw[static_cast<size_t>(o) * Ci + c] * dwb[c];
+      bias[o] = s;
+    }
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ host launchers
+int bn_fold(const float* g, const float* b, const float* mean, const float* var, float eps, float* scale, float* shift,
+            int n, int n_pad, cudaStream_t st) {
+  bn_fold_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(g, b, mean, var, eps, scale, shift, n, n_pad);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  ProfScope prof(kProfOther, st, 0);
+  maxpool_fwd_kernel<<<grid_for(static_cast<size_t>(B) * Ho * Wo * C / 8), 256, 0, st>>>(x, y, idx, B, H, W, C, Ho, Wo);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* x, __nv_bfloat16* dx, int B, int H,
+                int W, int C, cudaStream_t st) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  ProfScope prof(kProfOther, st, 0);
+  maxpool_bwd_kernel<<<grid_for(static_cast<size_t>(B) * H * W * C), 256, 0, st>>>(dy, idx, x, dx, B, H, W, C, Ho, Wo);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int gap_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, int ld, cudaStream_t st) {
+  ProfScope prof(kProfOther, st, 0);
+  gap_fwd_kernel<<<dim3((C + 63) / 64, B), 256, 0, st>>>(x, y, HW, C, ld);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int broadcast_hw(const __nv_bfloat16* v, __nv_bfloat16* y, int B, int HW, int C, int ldy, cudaStream_t st) {
+  ProfScope prof(kProfOther, st, 0);
+  broadcast_kernel<<<grid_for(static_cast<size_t>(B) * HW * C / 8), 256, 0, st>>>(v, y, B, HW, C, ldy);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int sum_hw(const __nv_bfloat16* y, const __nv_bfloat16* mask, __nv_bfloat16* v, int B, int HW, int C, int ldy, cudaStream_t st) {
+  ProfScope prof(kProfOther, st, 0);
+  sum_hw_kernel<<<dim3((C + 63) / 64, B), 256, 0, st>>>(y, mask, v, HW, C, ldy);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int gap_bwd_add(const __nv_bfloat16* g, __nv_bfloat16* dx, int B, int HW, int C, int ld, cudaStream_t st) {
+  ProfScope prof(kProfOther, st, 0);
+  gap_bwd_add_kernel<<<grid_for(static_cast<size_t>(B) * HW * C), 256, 0, st>>>(g, dx, B, HW, C, ld);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int bilinear_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int Hi, int Wi, int Ho, int Wo, int C, int ldx, int ldy,
+                 cudaStream_t st) {
+  WC_REQUIRE(C % 8 == 0, "bilinear: C must be a multiple of 8");
+  ProfScope prof(kProfOther, st, 0);
+  bilinear_fwd_kernel<<<grid_for(static_cast<size_t>(B) * Ho * Wo * C / 8), 256, 0, st>>>(x, y, B, Hi, Wi, Ho, Wo, C, ldx, ldy);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int bilinear_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* mask, __nv_bfloat16* dx, int B, int Hi, int Wi, int Ho,
+                 int Wo, int C, int ldy, int ldm, int ldx, cudaStream_t st) {
+  ProfScope prof(kProfOther, st, 0);
+  bilinear_bwd_kernel<<<grid_for(static_cast<size_t>(B) * Hi * Wi * C), 256, 0, st>>>(dy, mask, dx, B, Hi, Wi, Ho, Wo, C, ldy, ldm, ldx);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int seg_loss_grad(const float* logits_lo, const long long* labels, int* n_valid, long long* pred, float* dlogit_hi,
+                  float* loss, float* logits_hi, int B, int h, int w, int H, int W, int nc, int ignore, cudaStream_t st) {
+  WC_REQUIRE(nc == 19, "loss head is compiled for 19 classes (Cityscapes trainIds)");
+  ProfScope prof(kProfOther, st, 0);
+  WC_CHECK_CUDA(cudaMemsetAsync(n_valid, 0, B * sizeof(int), st));
+  if (loss) WC_CHECK_CUDA(cudaMemsetAsync(loss, 0, B * sizeof(float), st));
+  count_valid_kernel<<<dim3(std::min(64, (H * W + 255) / 256), B), 256, 0, st>>>(labels, H * W, ignore, n_valid);
+  WC_LAUNCH_CHECK();
+  seg_loss_grad_kernel<19><<<grid_for(static_cast<size_t>(B) * H * W, 128), 128, 0, st>>>(logits_lo, labels, n_valid, pred, dlogit_hi, loss, logits_hi, B, h, w, H, W, ignore);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int logits_bilinear_bwd(const float* dhi, __nv_bfloat16* dlo, int B, int h, int w, int H, int W, int nc, int cp, int ldo,
+                        cudaStream_t st) {
+  WC_REQUIRE(nc == 19, "loss head is compiled for 19 classes");
+  ProfScope prof(kProfOther, st, 0);
+  logits_bilinear_bwd_kernel<19><<<grid_for(static_cast<size_t>(B) * h * w, 128), 128, 0, st>>>(dhi, dlo, B, h, w, H, W, cp, ldo);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int conv1_dgrad(const __nv_bfloat16* dz, const float* w, const float* scale, float* dx, int B, int H, int W, int Cout,
+                cudaStream_t st) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t smem = static_cast<size_t>(49) * Cout * 3 * sizeof(float);
+  ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * (12.0 * H * W + 2.0 * Ho * Wo * Cout));
+  conv1_dgrad_kernel<<<grid_for(static_cast<size_t>(B) * H * W, 128), 128, smem, st>>>(dz, w, scale, dx, B, H, W, Ho, Wo, Cout);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int relu_mask_inplace(__nv_bfloat16* d, const __nv_bfloat16* m, size_t npix, int C, int ldd, int ldm, cudaStream_t st) {
+  ProfScope prof(kProfOther, st, 0);
+  relu_mask_kernel<<<grid_for(npix * C), 256, 0, st>>>(d, m, npix, C, ldd, ldm);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int compose_sep(const float* dw, const float* pw, const float* dwb, const float* pwb, float* w, float* bias, int Co, int Ci,
+                int KK, cudaStream_t st) {
+  compose_sep_kernel<<<grid_for(static_cast<size_t>(Co) * Ci * KK), 256, 0, st>>>(dw, pw, dwb, pwb, w, bias, Co, Ci, KK);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace wc

@@ -27,6 +27,19 @@ void prof_start();
 int prof_stop(double* ms, long long* count, double* work);
 int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                       int heads, int ntok, int hd, int ldo, cudaStream_t st);
+int maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st);
+int maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* x, __nv_bfloat16* dx, int B, int H,
+                int W, int C, cudaStream_t st);
+int bilinear_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int Hi, int Wi, int Ho, int Wo, int C, int ldx, int ldy,
+                 cudaStream_t st);
+int bilinear_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* mask, __nv_bfloat16* dx, int B, int Hi, int Wi, int Ho,
+                 int Wo, int C, int ldy, int ldm, int ldx, cudaStream_t st);
+int seg_loss_grad(const float* logits_lo, const long long* labels, int* n_valid, long long* pred, float* dlogit_hi,
+                  float* loss, float* logits_hi, int B, int h, int w, int H, int W, int nc, int ignore, cudaStream_t st);
+int logits_bilinear_bwd(const float* dhi, __nv_bfloat16* dlo, int B, int h, int w, int H, int W, int nc, int cp, int ldo,
+                        cudaStream_t st);
+int conv1_dgrad(const __nv_bfloat16* dz, const float* w, const float* scale, float* dx, int B, int H, int W, int Cout,
+                cudaStream_t st);
 }  // namespace wc
 
 using namespace wc;
@@ -104,6 +117,59 @@ int wc_conv2d(const wc_bf16* x, int batch, int H, int W, int Cin, int ldx, const
   return 0;
 }
 
+int wc_conv2d_dgrad(const wc_bf16* dz, int batch, int Ho, int Wo, int Cout, const float* weight, int Cin, int K, int stride,
+                    int dil, const wc_bf16* residual, const wc_bf16* mask, wc_bf16* dx, void* stream) {
+  // data gradient of y = conv2d(x, weight[Cout,Cin,K,K], stride, pad = dil*(K-1)/2 (stride 1) or K==3 (stride 2))
+  cudaStream_t st = S(stream);
+  DeviceArena arena;
+  ConvOp op;
+  const int H = Ho * stride, W = Wo * stride;
+  Act g; g.ptr = const_cast<__nv_bfloat16*>(BF(dz)); g.B = batch; g.H = Ho; g.W = Wo; g.C = Cout; g.ld = Cout;
+  Act out; out.ptr = BF(dx); out.B = batch; out.H = H; out.W = W; out.C = Cin; out.ld = Cin;
+  Act res = out; res.ptr = const_cast<__nv_bfloat16*>(BF(residual));
+  Act msk = out; msk.ptr = const_cast<__nv_bfloat16*>(BF(mask));
+  WeightSrc w; w.w = weight; w.d0 = Cout; w.d1 = Cin; w.KH = w.KW = K; w.transpose = 1;
+  Epilogue ep; ep.res = residual ? &res : nullptr; ep.mask = mask ? &msk : nullptr;
+  OutSpec os; os.mode = kOutNHWC; os.out = out;
+  int e;
+  if (stride == 1) {
+    w.flip = 1;
+    ConvGeom gg; gg.K = K; gg.stride = 1; gg.dil = dil; gg.pad = dil * (K - 1) / 2;
+    e = build_conv(&op, &arena, g, w, gg, Cin, nullptr, nullptr, ep, os, st);
+  } else {
+    if (!residual) WC_CHECK_CUDA(cudaMemsetAsync(out.ptr, 0, out.pixels() * Cin * 2, st));
+    e = build_conv_transposed_s2(&op, &arena, g, w, K, K == 3 ? 1 : 0, Cin, ep, os, st);
+  }
+  if (e) return e;
+  if ((e = op.run(st))) return e;
+  WC_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+int wc_maxpool3x3s2(const wc_bf16* x, wc_bf16* y, uint8_t* idx, int batch, int H, int W, int C, void* stream) {
+  return maxpool_fwd(BF(x), BF(y), idx, batch, H, W, C, S(stream));
+}
+int wc_maxpool3x3s2_bwd(const wc_bf16* dy, const uint8_t* idx, const wc_bf16* x, wc_bf16* dx, int batch, int H, int W, int C,
+                        void* stream) {
+  return maxpool_bwd(BF(dy), idx, BF(x), BF(dx), batch, H, W, C, S(stream));
+}
+int wc_bilinear(const wc_bf16* x, wc_bf16* y, int batch, int Hi, int Wi, int Ho, int Wo, int C, void* stream) {
+  return bilinear_fwd(BF(x), BF(y), batch, Hi, Wi, Ho, Wo, C, C, C, S(stream));
+}
+int wc_bilinear_bwd(const wc_bf16* dy, const wc_bf16* mask, wc_bf16* dx, int batch, int Hi, int Wi, int Ho, int Wo, int C,
+                    void* stream) {
+  return bilinear_bwd(BF(dy), BF(mask), BF(dx), batch, Hi, Wi, Ho, Wo, C, C, C, C, S(stream));
+}
+int wc_seg_loss_head(const float* logits_lo, const int64_t* labels, int* n_valid_ws, int64_t* pred, float* dlogit_hi,
+                     float* loss, float* logits_hi, wc_bf16* dlogit_lo, int batch, int h, int w, int H, int W, void* stream) {
+  if (int e = seg_loss_grad(logits_lo, reinterpret_cast<const long long*>(labels), n_valid_ws,
+                            reinterpret_cast<long long*>(pred), dlogit_hi, loss, logits_hi, batch, h, w, H, W, 19, 255, S(stream)))
+    return e;
+  if (dlogit_lo) return logits_bilinear_bwd(dlogit_hi, BF(dlogit_lo), batch, h, w, H, W, 19, 32, 32, S(stream));
+  return 0;
+}
+int wc_conv1_dgrad(const wc_bf16* dz, const float* weight, const float* scale, float* dx, int batch, int H, int W, void* stream) {
+  return conv1_dgrad(BF(dz), weight, scale, dx, batch, H, W, 64, S(stream));
+}
 int wc_conv_in(const float* x, const float* weight, const float* bias, const float* scale, const float* shift,
                wc_bf16* y, int batch, int H, int W, int Cout, int K, int stride, int pad, int ldy, int relu,
                void* stream) {
