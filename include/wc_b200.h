@@ -148,6 +148,18 @@ int wc_seg_infer(wc_seg* net, const float* x, const int64_t* labels, int64_t* pr
 double wc_seg_flops(const wc_seg* net, int backward);
 int wc_seg_launches(const wc_seg* net);
 
+/* ---- model-level: Swift-SRGAN generator (srgan_model/models.py:65-92, inference.py:35-39) ------------------- */
+typedef struct wc_srgan wc_srgan;
+int wc_srgan_create(wc_srgan** out, int num_blocks, int upscale, int n_params, const char* const* names,
+                    const float* const* ptrs, void* stream);
+void wc_srgan_destroy(wc_srgan* net);
+size_t wc_srgan_workspace_bytes(const wc_srgan* net, int batch, int h, int w);
+/* Generator.forward: x nchw_f32 [B,3,h,w] -> y nchw_f32 [B,3,upscale*h,upscale*w] in [0,1]. */
+int wc_srgan_forward(wc_srgan* net, const float* x, float* y, int batch, int h, int w, void* workspace,
+                     size_t workspace_bytes, void* stream);
+double wc_srgan_flops(const wc_srgan* net);
+int wc_srgan_launches(const wc_srgan* net);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,8 +117,8 @@ def test_sgg_update_kernel_matches_reference_arithmetic(golden):
     ref = torch.cat(ref)
     xt = torch.empty(B, 3, h, w, device=dev)
     mag_out = torch.empty(B, h, w, device=dev)
-    check(lib().wc_sgg_update(ptr(grad.to(dev)), ptr(mu.to(dev)), ptr(sig.to(dev)), ptr(xt), ptr(mag_out), B, h, w, 4, 60.0,
-                              stream_ptr()))
+    grad_d, mu_d, sig_d = grad.to(dev), mu.to(dev), sig.to(dev)   # keep the device tensors alive across the raw-pointer call
+    check(lib().wc_sgg_update(ptr(grad_d), ptr(mu_d), ptr(sig_d), ptr(xt), ptr(mag_out), B, h, w, 4, 60.0, stream_ptr()))
     assert torch.equal(xt.cpu(), ref)
 
 

@@ -70,7 +70,8 @@ def test_maxpool_fwd_bwd():
     check(lib().wc_maxpool3x3s2(ptr(xh), ptr(y), ptr(idx), B, H, W, Cc, stream_ptr()))
     assert torch.equal(ops.to_nchw_f32(y), y_ref.detach())
     dx = torch.empty_like(xh)
-    check(lib().wc_maxpool3x3s2_bwd(ptr(ops.to_nhwc_bf16(dy)), ptr(idx), ptr(xh), ptr(dx), B, H, W, Cc, stream_ptr()))
+    dyh = ops.to_nhwc_bf16(dy)
+    check(lib().wc_maxpool3x3s2_bwd(ptr(dyh), ptr(idx), ptr(xh), ptr(dx), B, H, W, Cc, stream_ptr()))
     assert _rel(ops.to_nchw_f32(dx), ref_dx) < 5e-3
 
 
@@ -87,10 +88,12 @@ def test_bilinear_fwd_bwd(Hi, Wi, Ho, Wo, C):
     dy = torch.randn(B, C, Ho, Wo, generator=g).to(dev)
     y_ref.backward(_bf(dy))
     y = torch.empty(B, Ho, Wo, C, device=dev, dtype=torch.bfloat16)
-    check(lib().wc_bilinear(ptr(ops.to_nhwc_bf16(x)), ptr(y), B, Hi, Wi, Ho, Wo, C, stream_ptr()))
+    xh = ops.to_nhwc_bf16(x)
+    check(lib().wc_bilinear(ptr(xh), ptr(y), B, Hi, Wi, Ho, Wo, C, stream_ptr()))
     assert _rel(ops.to_nchw_f32(y), y_ref.detach()) < 4e-3
     dx = torch.empty(B, Hi, Wi, C, device=dev, dtype=torch.bfloat16)
-    check(lib().wc_bilinear_bwd(ptr(ops.to_nhwc_bf16(dy)), None, ptr(dx), B, Hi, Wi, Ho, Wo, C, stream_ptr()))
+    dyh = ops.to_nhwc_bf16(dy)
+    check(lib().wc_bilinear_bwd(ptr(dyh), None, ptr(dx), B, Hi, Wi, Ho, Wo, C, stream_ptr()))
     assert _rel(ops.to_nchw_f32(dx), xb.grad) < 4e-3
 
 
@@ -113,7 +116,8 @@ def test_loss_head():
     nv = torch.empty(B, dtype=torch.int32, device=dev)
     dlo = torch.empty(B, h, w, 32, device=dev, dtype=torch.bfloat16)
     lhi = torch.empty(B, 19, H, W, device=dev)
-    check(lib().wc_seg_loss_head(ptr(lo.detach()), ptr(lab), ptr(nv), ptr(pred), ptr(dhi), ptr(loss), ptr(lhi), ptr(dlo),
+    lo_d = lo.detach()
+    check(lib().wc_seg_loss_head(ptr(lo_d), ptr(lab), ptr(nv), ptr(pred), ptr(dhi), ptr(loss), ptr(lhi), ptr(dlo),
                                  B, h, w, H, W, stream_ptr()))
     assert (lhi - hi.detach()).abs().max() < 1e-4
     assert (pred == hi.argmax(1)).float().mean() > 0.9999
@@ -134,5 +138,6 @@ def test_conv1_dgrad():
     dz = torch.randn(B, 64, H // 2, W // 2, generator=g).to(dev)
     ref = torch.nn.grad.conv2d_input((B, 3, H, W), w * sc[:, None, None, None], _bf(dz), stride=2, padding=3)
     dx = torch.empty(B, 3, H, W, device=dev)
-    check(lib().wc_conv1_dgrad(ptr(ops.to_nhwc_bf16(dz)), ptr(w), ptr(sc), ptr(dx), B, H, W, stream_ptr()))
+    dzh = ops.to_nhwc_bf16(dz)
+    check(lib().wc_conv1_dgrad(ptr(dzh), ptr(w), ptr(sc), ptr(dx), B, H, W, stream_ptr()))
     assert _rel(dx, ref) < 1e-4

@@ -160,7 +160,7 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
         taps.push_back({py * 2 + px, (oy - py) / 2, (ox - px) / 2, &w, ky, kx, x.C});
       }
   }
-  if (int e = finish_plan(&plan, arena, taps, B, H, W, tb, th, tw, N, ep, out, 1, 1, 0, 0, st)) return e;
+  if (int e = finish_plan(&plan, arena, taps, B, H, W, tb, th, tw, N, ep, out, out.up, out.up, out.py, out.px, st)) return e;
   op->flops = plan.flops;
   return 0;
 }

@@ -52,6 +52,7 @@ struct OutSpec {
   int n_store = 0;
   __nv_bfloat16 *q = nullptr, *k = nullptr, *vt = nullptr;
   int heads = 0, hd = 0;
+  int up = 1, py = 0, px = 0;  // build_conv only: write pixel (y,x) to (y*up+py, x*up+px) of an up-times larger grid
 };
 
 // One logical layer = one or more igemm launches (4 for stride-2 transposed / dgrad convs).

@@ -17,7 +17,8 @@ template <int CIN>
 __global__ void conv_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cout][CIN][K][K]*/,
                                       const float* __restrict__ bias, const float* __restrict__ scale,
                                       const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int B, int H,
-                                      int W, int Ho, int Wo, int Cout, int K, int stride, int pad, int ldy, int relu) {
+                                      int W, int Ho, int Wo, int Cout, int K, int stride, int pad, int ldy, int relu,
+                                      const float* __restrict__ prelu) {
   extern __shared__ float sw[];  // [CIN*K*K][Cout]
   const int taps = CIN * K * K;
   for (int i = threadIdx.x; i < taps * Cout; i += blockDim.x) {
@@ -56,6 +57,10 @@ __global__ void conv_small_cin_kernel(const float* __restrict__ x, const float* 
     if (relu) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    if (prelu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = acc[j] > 0.f ? acc[j] : acc[j] * prelu[oct * 8 + j];
     }
     uint4 u;
     u.x = pack_bf16(acc[0], acc[1]); u.y = pack_bf16(acc[2], acc[3]);
@@ -218,7 +223,7 @@ inline int grid_for(size_t n_items, int per_block = 256) {
 
 int conv_small_cin(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
                    __nv_bfloat16* y, int B, int Cin, int H, int W, int Cout, int K, int stride, int pad, int ldy,
-                   int relu, cudaStream_t st) {
+                   int relu, cudaStream_t st, const float* prelu) {
   WC_REQUIRE(Cin == 3, "conv_small_cin supports Cin == 3");
   WC_REQUIRE(Cout % 8 == 0 && Cout <= 256, "Cout must be a multiple of 8, <= 256");
   const int Ho = (H + 2 * pad - K) / stride + 1, Wo = (W + 2 * pad - K) / stride + 1;
@@ -230,7 +235,7 @@ int conv_small_cin(const float* x, const float* w, const float* bias, const floa
   const size_t npix = static_cast<size_t>(B) * Ho * Wo;
   ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * (12.0 * H * W + 2.0 * Ho * Wo * Cout));
   conv_small_cin_kernel<3><<<grid_for(npix, threads / octs), threads, smem, st>>>(
-      x, w, bias, scale, shift, y, B, H, W, Ho, Wo, Cout, K, stride, pad, ldy, relu);
+      x, w, bias, scale, shift, y, B, H, W, Ho, Wo, Cout, K, stride, pad, ldy, relu, prelu);
   WC_LAUNCH_CHECK();
   return 0;
 }

@@ -11,7 +11,7 @@
 namespace wc {
 int conv_small_cin(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
                    __nv_bfloat16* y, int B, int Cin, int H, int W, int Cout, int K, int stride, int pad, int ldy,
-                   int relu, cudaStream_t st);
+                   int relu, cudaStream_t st, const float* prelu = nullptr);
 int bn_fold(const float* g, const float* b, const float* mean, const float* var, float eps, float* scale, float* shift,
             int n, int n_pad, cudaStream_t st);
 int maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st);

@@ -548,3 +548,132 @@ int compose_sep(const float* dw, const float* pw, const float* dwb, const float*
 }
 
 }  // namespace wc
+
+// =====================================================================================================================
+// SRGAN final layer (srgan_model/models.py:85,92): depthwise 9x9 (64 ch, bias) -> pointwise 64->3 (bias) -> (tanh+1)/2,
+// NHWC bf16 in, NCHW fp32 out.  One CTA = an 8 x 64 output tile; the (8+8) x (64+8) x 64-channel halo tile is staged
+// in shared memory as 32 channel-pair planes (conflict-free row reads); each thread owns 4 adjacent pixels and half
+// of the channel pairs, sliding a 12-wide register window over every kernel row.
+namespace wc {
+namespace {
+
+constexpr int kFT_H = 8, kFT_W = 64, kFHalo = 4, kFPlaneW = kFT_W + 2 * kFHalo /*72*/, kFPlaneH = kFT_H + 2 * kFHalo /*16*/;
+constexpr int kFPlane = kFPlaneW * kFPlaneH + 1;  // +1 word: de-phase the planes across banks for the staging writes
+
+__global__ void __launch_bounds__(256, 1)
+srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dw /*[64][81]*/,
+                   const float* __restrict__ dwb, const float* __restrict__ pw /*[3][64]*/, const float* __restrict__ pwb,
+                   float* __restrict__ y, int B, int H, int W, int ldx) {
+  extern __shared__ uint32_t sm[];
+  uint32_t* tile = sm;                                            // [32][kFPlane] bf16x2
+  float* wsm = reinterpret_cast<float*>(sm + 32 * kFPlane);       // [32][81][2]
+  float* red = wsm + 32 * 81 * 2;                                 // [128 threads][12]
+  const int tiles_x = (W + kFT_W - 1) / kFT_W, tiles_y = (H + kFT_H - 1) / kFT_H;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 32 * 81 * 2; i += 256) {
+    const int j = i & 1, tap = (i >> 1) % 81, c2 = (i >> 1) / 81;
+    wsm[i] = dw[(c2 * 2 + j) * 81 + tap];
+  }
+  const int grp = tid >> 7, t = tid & 127, ty = t >> 4, tx = (t & 15) * 4;
+  for (int tl = blockIdx.x; tl < B * tiles_x * tiles_y; tl += gridDim.x) {
+    const int b = tl / (tiles_x * tiles_y), r = tl % (tiles_x * tiles_y), y0 = (r / tiles_x) * kFT_H, x0 = (r % tiles_x) * kFT_W;
+    __syncthreads();
+    // stage the halo tile: one 16-byte (8-channel) chunk per thread-iteration
+    for (int i = tid; i < kFPlaneH * kFPlaneW * 8; i += 256) {
+      const int c8 = i & 7, px = (i >> 3) % kFPlaneW, py = (i >> 3) / kFPlaneW;
+      const int gy = y0 + py - kFHalo, gx = x0 + px - kFHalo;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+        u = __ldg(reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(b) * H + gy) * W + gx) * ldx + c8 * 8));
+      uint32_t* dst = tile + (c8 * 4) * kFPlane + py * kFPlaneW + px;
+      dst[0] = u.x; dst[kFPlane] = u.y; dst[2 * kFPlane] = u.z; dst[3 * kFPlane] = u.w;
+    }
+    __syncthreads();
+    float o[3][4];
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) o[n][p] = 0.f;
+    for (int c2 = grp * 16; c2 < grp * 16 + 16; ++c2) {
+      float a0[4], a1[4];
+      const float b0 = dwb ? dwb[2 * c2] : 0.f, b1 = dwb ? dwb[2 * c2 + 1] : 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) { a0[p] = b0; a1[p] = b1; }
+      const uint32_t* pl = tile + c2 * kFPlane + ty * kFPlaneW + tx;
+      const float2* wp = reinterpret_cast<const float2*>(wsm) + c2 * 81;
+#pragma unroll
+      for (int ky = 0; ky < 9; ++ky) {
+        float v0[12], v1[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const float2 f = unpack_bf16(pl[ky * kFPlaneW + i]);
+          v0[i] = f.x; v1[i] = f.y;
+        }
+#pragma unroll
+        for (int kx = 0; kx < 9; ++kx) {
+          const float2 wv = wp[ky * 9 + kx];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            a0[p] = fmaf(v0[p + kx], wv.x, a0[p]);
+            a1[p] = fmaf(v1[p + kx], wv.y, a1[p]);
+          }
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < 3; ++n) {
+        const float w0 = pw[n * 64 + 2 * c2], w1 = pw[n * 64 + 2 * c2 + 1];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) o[n][p] = fmaf(a0[p], w0, fmaf(a1[p], w1, o[n][p]));
+      }
+    }
+    if (grp == 1) {
+#pragma unroll
+      for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) red[t * 12 + n * 4 + p] = o[n][p];
+    }
+    __syncthreads();
+    if (grp == 0) {
+      const int gy = y0 + ty;
+      const size_t plane = static_cast<size_t>(H) * W;
+#pragma unroll
+      for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int gx = x0 + tx + p;
+          if (gy < H && gx < W) {
+            const float v = o[n][p] + red[t * 12 + n * 4 + p] + (pwb ? pwb[n] : 0.f);
+            y[(static_cast<size_t>(b) * 3 + n) * plane + static_cast<size_t>(gy) * W + gx] = (tanhf(v) + 1.f) * 0.5f;
+          }
+        }
+    }
+  }
+}
+
+__global__ void gather_stride_kernel(const float* src, float* dst, int n, int mul, int off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i * mul + off];
+}
+
+}  // namespace
+
+int srgan_final(const __nv_bfloat16* x, const float* dw, const float* dwb, const float* pw, const float* pwb, float* y, int B,
+                int H, int W, int ldx, cudaStream_t st) {
+  const size_t smem = (32 * kFPlane) * 4 + 32 * 81 * 2 * 4 + 128 * 12 * 4;
+  static bool attr = false;
+  if (!attr) {
+    WC_CHECK_CUDA(cudaFuncSetAttribute(srgan_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = true;
+  }
+  const int tiles = B * ((W + kFT_W - 1) / kFT_W) * ((H + kFT_H - 1) / kFT_H);
+  ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * H * W * (128.0 + 12.0));
+  srgan_final_kernel<<<std::min(tiles, num_sms()), 256, smem, st>>>(x, dw, dwb, pw, pwb, y, B, H, W, ldx);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int gather_stride(const float* src, float* dst, int n, int mul, int off, cudaStream_t st) {
+  gather_stride_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n, mul, off);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace wc

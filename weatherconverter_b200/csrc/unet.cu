@@ -26,7 +26,7 @@ int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv
 double attention_flops(int B, int heads, int ntok, int hd);
 int conv_small_cin(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
                    __nv_bfloat16* y, int B, int Cin, int H, int W, int Cout, int K, int stride, int pad, int ldy,
-                   int relu, cudaStream_t st);
+                   int relu, cudaStream_t st, const float* prelu = nullptr);
 int conv_small_cout(const __nv_bfloat16* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
                     int Cout, int K, int ldx, int tanh_out, cudaStream_t st);
 int temb_mlp(const long long* t, int Bt, int dim, const float* w1, const float* b1, const float* w2, const float* b2,

@@ -18,7 +18,7 @@ int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int 
 size_t groupnorm_workspace_bytes(int B);
 int conv_small_cin(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
                    __nv_bfloat16* y, int B, int Cin, int H, int W, int Cout, int K, int stride, int pad, int ldy,
-                   int relu, cudaStream_t st);
+                   int relu, cudaStream_t st, const float* prelu = nullptr);
 int conv_small_cout(const __nv_bfloat16* x, const float* w, const float* bias, float* y, int B, int H, int W, int Cin,
                     int Cout, int K, int ldx, int tanh_out, cudaStream_t st);
 int nchw_f32_to_nhwc_bf16(const float* x, __nv_bfloat16* y, int B, int C, int HW, int ldy, cudaStream_t st);
