@@ -1,18 +1,21 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the WeatherConverter hot path on B200 (contract: see the task README).
+"""bench.py — headline benchmark of the WeatherConverter hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1]
 
-Workload (N = 1 and every N, weak scaling): BASELINE.json configs[1] — UNet DDPM sampling at 128x256, batch 16
-per GPU, 1000-step linear schedule, reference UNet (config.yaml, im_size 128, 110.6 M params), random-init
-weights, synthetic noise.  A "step" is ONE reverse-diffusion step over the batch: Unet.forward(x_t, t) followed by
-the fused posterior update x_{t-1} = mean + sigma_t z.  Per-step cost does not depend on t, so
-    images/s = (N * batch) / (T_schedule * seconds_per_step).
+Default workload (every N, weak scaling) = the configuration BASELINE.json's metric is quoted on:
+  c3  SGG-guided translation at 256x512 (BASELINE.json configs[2]/[3]), batch 32 per GPU, N = 500 reverse steps,
+      geometry A of SURVEY.md 8d (reference-faithful): latent 64x128 (UNet config.yaml with im_size 64) -> SRGAN x4 ->
+      DeepLabV3+-ResNet-50 (os16, 19 classes) forward + CE + input gradient at 256x512 -> avg-pool 4 -> guidance
+      update (lambda = 60), GSG on every step (the repaired driver of SURVEY.md 8c).
+  c2  UNet DDPM sampling at 128x256, batch 16 per GPU, 1000-step schedule (BASELINE.json configs[1]).
+A "step" is ONE reverse-diffusion step over the batch; per-step cost does not depend on t, so
+    images/s = (N_gpus * batch) / (schedule_steps * seconds_per_step).
 `value` times the steps with inputs resident in HBM; `e2e` times the same steps through the public Python API with
 the per-step noise coming from pinned HOST memory (the reference draws z on the CPU every step,
 linear_noise_scheduler.py:110) and x_{t-1} read back to the host, copies inside the timed region.
-`--impl reference` times the reference algorithm's CPU implementation (the oracle port; the reference itself is a
-Python package that is not shipped to the GPU box) on all host cores, on a bounded sample of the same workload.
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port — the reference is a Python
+source tree that cannot travel to the GPU box) on all host cores, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -29,9 +32,13 @@ METRIC = "guided translation images/sec (256x512, T steps) at 1/2/4/8 B200 vs ho
 UNIT = "images/s"
 
 WORKLOADS = {
-    # name: (im_size, batch/GPU, H, W, schedule steps, description)
-    "c2": (128, 16, 128, 256, 1000, "C2: UNet DDPM sampling 128x256, batch 16/GPU, 1000-step schedule (BASELINE.json configs[1])"),
-    "c1": (64, 4, 64, 64, 50, "C1: UNet DDPM sampling 64x64, batch 4, 50 steps (BASELINE.json configs[0])"),
+    "c3": dict(kind="sgg", im_size=64, batch=32, h=64, w=128, T=500,
+               desc="C3/C4: SGG-guided translation 256x512 (latent 64x128, SRGAN x4, DeepLabV3+-R50 gradient guidance every "
+                    "step, lambda 60), batch 32/GPU, 500 reverse steps (BASELINE.json configs[2]/[3], geometry A)"),
+    "c2": dict(kind="ddpm", im_size=128, batch=16, h=128, w=256, T=1000,
+               desc="C2: UNet DDPM sampling 128x256, batch 16/GPU, 1000-step schedule (BASELINE.json configs[1])"),
+    "c1": dict(kind="ddpm", im_size=64, batch=4, h=64, w=64, T=50,
+               desc="C1: UNet DDPM sampling 64x64, batch 4, 50 steps (BASELINE.json configs[0])"),
 }
 
 
@@ -82,7 +89,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.05)
 
     def finish(self):
         self._halt.set()
@@ -91,30 +98,100 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def build_model(im_size, dev):
+def block_labels(gen, B, H, W, blk=8):
+    """Cityscapes-shaped synthetic masks: 8x8 blocks of uniform class in 0..18, 5 % of the blocks = 255."""
     import torch
-    from weatherconverter_b200.diffusion_model.models.unet_base import Unet
-    from weatherconverter_b200.diffusion_model.config.models import ModelConfig
-    torch.manual_seed(3455)   # config.yaml:32
-    cfg = ModelConfig(im_size=im_size)
-    model = Unet(cfg).to(dev).eval()
-    return model, cfg
+    lab = torch.randint(0, 19, (B, H // blk, W // blk), generator=gen)
+    lab[torch.rand(B, H // blk, W // blk, generator=gen) < 0.05] = 255
+    return lab.repeat_interleave(blk, 1).repeat_interleave(blk, 2)
 
 
-def cpu_reference_rate(im_size, H, W, T, steps, warmup, batch=1):
-    """Oracle port (plain PyTorch fp32, all host threads) on a bounded sample: `batch` image(s), `steps` timed
-    reverse steps.  Returns (images/s extrapolated to the T-step schedule, seconds/step, cores)."""
+# ------------------------------------------------------------------------------------------------ GPU workloads
+class GpuWorkload:
+    def __init__(self, spec, dev, rank):
+        import torch
+        from weatherconverter_b200.diffusion_model.config.models import ModelConfig
+        from weatherconverter_b200.diffusion_model.models.unet_base import Unet
+        from weatherconverter_b200.diffusion_model.scheduler.linear_noise_scheduler import LinearNoiseScheduler
+        from weatherconverter_b200.sharding import initial_noise
+        self.spec, self.dev = spec, dev
+        B, h, w = spec["batch"], spec["h"], spec["w"]
+        torch.manual_seed(3455)   # diffusion config.yaml:32
+        self.unet = Unet(ModelConfig(im_size=spec["im_size"])).to(dev).eval()
+        self.sched = LinearNoiseScheduler(spec["T"] if spec["kind"] == "ddpm" else 1000, 1e-4, 0.02)
+        self.x0 = initial_noise((3, h, w), rank * B, (rank + 1) * B).to(dev)   # RNG keyed by the global image index
+        self.eps = torch.empty_like(self.x0)
+        self.T = spec["T"]
+        if spec["kind"] == "sgg":
+            from weatherconverter_b200.seg_model.network import modeling
+            from weatherconverter_b200.srgan_model.models import Generator
+            torch.manual_seed(42)   # seg config.yaml:3
+            self.seg = modeling.deeplabv3plus_resnet50(num_classes=19, output_stride=16, pretrained_backbone=False)
+            g = torch.Generator().manual_seed(7)
+            for n, b in self.seg.named_buffers():   # non-degenerate eval BatchNorm statistics (SURVEY 8c)
+                if n.endswith("running_mean"):
+                    b.copy_(0.1 * torch.randn(b.shape, generator=g))
+                elif n.endswith("running_var"):
+                    b.copy_(0.5 + torch.rand(b.shape, generator=g))
+            self.seg = self.seg.to(dev).eval()
+            torch.manual_seed(0)
+            self.srgan = Generator(upscale_factor=4)
+            for n, b in self.srgan.named_buffers():
+                if n.endswith("running_mean"):
+                    b.copy_(0.1 * torch.randn(b.shape, generator=g))
+                elif n.endswith("running_var"):
+                    b.copy_(0.5 + torch.rand(b.shape, generator=g))
+            self.srgan = self.srgan.to(dev).eval()
+            self.gt = block_labels(torch.Generator().manual_seed(1234 + rank), B, 4 * h, 4 * w).to(dev)
+        self.t_dev = {}
+
+    def t_tensor(self, i):
+        import torch
+        if i not in self.t_dev:
+            self.t_dev[i] = torch.tensor([i], device=self.dev)
+        return self.t_dev[i]
+
+    def step(self, xt, k, z):
+        """One reverse step at timestep i = T-1-(k mod (T-1)) (never 0: the timed steps all inject noise)."""
+        i = self.T - 1 - (k % (self.T - 1))
+        self.unet(xt, self.t_tensor(i), out=self.eps)
+        if self.spec["kind"] == "ddpm":
+            return self.sched.step(xt, self.eps, i, z=z)
+        from weatherconverter_b200.sgg.sgg import apply_gsg_batch
+        mu, sigma, _ = self.sched.sample_prev_timestep(xt, self.eps, i, z=z)
+        sr = self.srgan(xt)
+        return apply_gsg_batch(self.seg, mu, sigma, sr, self.gt, 60.0)
+
+    def flops_per_step(self):
+        f = self.unet.flops_per_forward()
+        parts = {"unet": f}
+        if self.spec["kind"] == "sgg":
+            sf, sb = self.seg.flops()
+            parts.update(srgan=self.srgan.flops(), seg_fwd=sf, seg_dgrad=sb)
+        return sum(parts.values()), parts
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def cpu_reference_rate(spec, steps, warmup):
+    """Oracle port (plain PyTorch fp32, all host threads) on a bounded sample: ONE image, `steps` timed reverse steps.
+    Returns (images/s extrapolated linearly to the schedule, seconds/step/image, cores)."""
     import torch
+    from oracle import deeplab, sgg, srgan
     from oracle.scheduler import OracleScheduler
     from oracle.unet import DEFAULT_MODEL_CONFIG, unet_forward, unet_param_spec
     from oracle.weights import synth_state_dict
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = im_size
+    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = spec["im_size"]
+    T, h, w = spec["T"], spec["h"], spec["w"]
     sd = synth_state_dict(unet_param_spec(cfg), 3455)
-    sched = OracleScheduler(T, 1e-4, 0.02)
+    sched = OracleScheduler(T if spec["kind"] == "ddpm" else 1000, 1e-4, 0.02)
     g = torch.Generator().manual_seed(1234)
-    xt = torch.randn(batch, 3, H, W, generator=g)
+    xt = torch.randn(1, 3, h, w, generator=g)
+    if spec["kind"] == "sgg":
+        seg_sd = synth_state_dict(deeplab.deeplab_param_spec("resnet50"), 42)
+        gan_sd = synth_state_dict(srgan.srgan_param_spec(), 0)
+        gt = block_labels(g, 1, 4 * h, 4 * w)
     times = []
     with torch.no_grad():
         for k in range(warmup + steps):
@@ -123,28 +200,35 @@ def cpu_reference_rate(im_size, H, W, T, steps, warmup, batch=1):
             eps = unet_forward(sd, cfg, xt, torch.tensor([i]))
             z = torch.randn(xt.shape, generator=g)
             mean, sz, _ = sched.sample_prev_timestep(xt, eps, i, z=z)
-            xt = mean + sz
+            if spec["kind"] == "sgg":
+                sr = srgan.generator_forward(gan_sd, xt)
+                with torch.enable_grad():
+                    xt, _, _ = sgg.apply_gsg(seg_sd, mean, sz, sr, gt, 60.0)
+            else:
+                xt = mean + sz
             dt = time.perf_counter() - t0
             if k >= warmup:
                 times.append(dt)
     sec = sum(times) / len(times)
-    return batch / (T * sec), sec, cores
+    return 1.0 / (T * sec), sec, cores
 
 
 def run_reference(args):
     """Reference arm: rank 0 only; CPU implementation of the same step on a bounded sample."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    im_size, B, H, W, T, desc = WORKLOADS[args.workload]
-    value, sec, cores = cpu_reference_rate(im_size, H, W, T, args.steps, args.warmup, batch=1)
-    sample = f"1 image of the batch, {args.steps} timed reverse steps after {args.warmup} warm-up, extrapolated linearly to T={T}"
+    spec = WORKLOADS[args.workload]
+    steps = min(args.steps, 5)
+    warm = min(args.warmup, 1)
+    value, sec, cores = cpu_reference_rate(spec, steps, warm)
+    sample = (f"oracle port (PyTorch fp32, {cores} threads): 1 image of the batch, {steps} timed reverse steps after {warm} "
+              f"warm-up, extrapolated linearly to {spec['T']} steps")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "batch_per_gpu": B, "height": H, "width": W, "schedule_steps": T,
-                   "sample": sample},
+        "config": {"workload": spec["desc"], "batch_per_gpu": spec["batch"], "latent": [spec["h"], spec["w"]],
+                   "schedule_steps": spec["T"], "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -158,17 +242,20 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--resident-only", action="store_true", help="skip the e2e and profiling legs (ncu launch lists)")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from weatherconverter_b200 import _lib, ops
-    from weatherconverter_b200.diffusion_model.scheduler.linear_noise_scheduler import LinearNoiseScheduler
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -182,21 +269,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W_ = max(args.warmup, 3)
     K = args.steps
-    im_size, B, H, Wd, T, desc = WORKLOADS[args.workload]
+    spec = dict(WORKLOADS[args.workload])
+    if args.batch:
+        spec["batch"] = args.batch
+    B, T = spec["batch"], spec["T"]
     peaks = read_peaks()
-
-    model, cfg = build_model(im_size, dev)
-    sched = LinearNoiseScheduler(T, 1e-4, 0.02)
-    # per-image RNG keyed by the GLOBAL image index -> results independent of the number of GPUs
-    xs = []
-    for b in range(B):
-        g = torch.Generator().manual_seed(1234 + rank * B + b)
-        xs.append(torch.randn(3, H, Wd, generator=g))
-    xt0 = torch.stack(xs).to(dev)
+    wl = GpuWorkload(spec, dev, rank)
+    x0 = wl.x0
     gz = torch.Generator(device=dev).manual_seed(99 + rank)
-    eps = torch.empty_like(xt0)
-    nsteps_total = W_ + K
-    t_devs = [torch.tensor([T - 1 - (k % T)], device=dev) for k in range(nsteps_total)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -205,11 +285,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident leg: z pre-generated in HBM ----------------
-    zs = [torch.randn(xt0.shape, device=dev, generator=gz) for _ in range(min(nsteps_total, 8))]
-    xt = xt0.clone()
+    zs = [torch.randn(x0.shape, device=dev, generator=gz) for _ in range(4)]
+    xt = x0.clone()
     for k in range(W_):
-        model(xt, t_devs[k], out=eps)
-        xt = sched.step(xt, eps, T - 1 - (k % T), z=zs[k % len(zs)])
+        xt = wl.step(xt, k, zs[k % 4])
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -217,8 +296,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(W_, W_ + K):
-        model(xt, t_devs[k], out=eps)
-        xt = sched.step(xt, eps, T - 1 - (k % T), z=zs[k % len(zs)])
+        xt = wl.step(xt, k, zs[k % 4])
     e1.record()
     barrier()
     clocks = sampler.finish()
@@ -227,58 +305,60 @@ def main():
     finite = bool(torch.isfinite(xt).all())
 
     # ---------------- end-to-end leg: z from pinned host memory, x_{t-1} read back each step ----------------
-    z_host = [torch.randn(xt0.shape).pin_memory() for _ in range(4)]
-    x_host = torch.empty(xt0.shape).pin_memory()
-    z_dev = torch.empty_like(xt0)
-    xt = xt0.clone()
-    for k in range(W_):
+    if args.resident_only:
+        args.no_profile = True
+    z_host = [torch.randn(x0.shape).pin_memory() for _ in range(4)]
+    x_host = torch.empty(x0.shape).pin_memory()
+    z_dev = torch.empty_like(x0)
+    xt = x0.clone()
+    for k in range(0 if args.resident_only else W_):
         z_dev.copy_(z_host[k % 4], non_blocking=True)
-        model(xt, t_devs[k], out=eps)
-        xt = sched.step(xt, eps, T - 1 - (k % T), z=z_dev)
+        xt = wl.step(xt, k, z_dev)
         x_host.copy_(xt, non_blocking=True)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for k in range(W_, W_ + K):
+    for k in range(W_, W_ + (1 if args.resident_only else K)):
         z_dev.copy_(z_host[k % 4], non_blocking=True)
-        model(xt, t_devs[k], out=eps)
-        xt = sched.step(xt, eps, T - 1 - (k % T), z=z_dev)
+        xt = wl.step(xt, k, z_dev)
         x_host.copy_(xt, non_blocking=True)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
-    bytes_io = xt0.numel() * 4
+    bytes_io = x0.numel() * 4
 
     # ---------------- per-kernel-class timing (CUDA events around every launch), roofline of the dominant kernel
-    import ctypes as C
-    lib = _lib.lib()
-    lib.wc_profile_begin()
-    xt = xt0.clone()
-    for k in range(K):
-        model(xt, t_devs[k], out=eps)
-        xt = sched.step(xt, eps, T - 1 - (k % T), z=zs[k % len(zs)])
-    ms_c, cnt_c, work_c = (C.c_double * 8)(), (C.c_longlong * 8)(), (C.c_double * 8)()
-    _lib.check(lib.wc_profile_end(ms_c, cnt_c, work_c))
-    names = ["igemm_tcgen05", "flash_attention_tcgen05", "groupnorm_silu", "boundary_conv", "ddpm_step", "other"]
-    classes = {}
-    for i, n in enumerate(names):
-        if cnt_c[i]:
-            classes[n] = {"ms_per_step": ms_c[i] / K, "launches_per_step": cnt_c[i] / K,
-                          "work_per_step": work_c[i] / K}
-    prof_total = sum(v["ms_per_step"] for v in classes.values())
-    dom = "igemm_tcgen05"
-    achieved = classes[dom]["work_per_step"] / (classes[dom]["ms_per_step"] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tf_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": None,
-                "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "share_of_step": classes[dom]["ms_per_step"] / prof_total,
-                "flops_per_launch": classes[dom]["work_per_step"] / classes[dom]["launches_per_step"],
-                "avg_launch_ms": classes[dom]["ms_per_step"] / classes[dom]["launches_per_step"]}
-    for n, v in classes.items():
-        if n in ("igemm_tcgen05", "flash_attention_tcgen05"):
-            v["tflops"] = v["work_per_step"] / (v["ms_per_step"] * 1e-3) / 1e12
-        else:
-            v["gbs"] = v["work_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9
+    classes, roofline = {}, None
+    flops_step, flop_parts = wl.flops_per_step()
+    if not args.no_profile:
+        lib = _lib.lib()
+        KP = min(K, 3)
+        lib.wc_profile_begin()
+        xt = x0.clone()
+        for k in range(KP):
+            xt = wl.step(xt, k, zs[k % 4])
+        ms_c, cnt_c, work_c = (C.c_double * 8)(), (C.c_longlong * 8)(), (C.c_double * 8)()
+        _lib.check(lib.wc_profile_end(ms_c, cnt_c, work_c))
+        names = ["igemm_tcgen05", "flash_attention_tcgen05", "groupnorm_silu", "boundary_conv", "scheduler", "other"]
+        for i, n in enumerate(names):
+            if cnt_c[i]:
+                classes[n] = {"ms_per_step": ms_c[i] / KP, "launches_per_step": cnt_c[i] / KP, "work_per_step": work_c[i] / KP}
+        prof_total = sum(v["ms_per_step"] for v in classes.values())
+        for n, v in classes.items():
+            if n in ("igemm_tcgen05", "flash_attention_tcgen05"):
+                v["tflops"] = v["work_per_step"] / (v["ms_per_step"] * 1e-3) / 1e12
+            elif v["work_per_step"] > 0:
+                v["gbs"] = v["work_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9
+            v["share_of_step"] = v["ms_per_step"] / prof_total
+        dom = "igemm_tcgen05"
+        achieved = classes[dom]["tflops"]
+        roofline = {"bound": "tensor", "kernel": "igemm_kernel (csrc/igemm.cu)", "achieved": achieved,
+                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                    "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "share_of_step": classes[dom]["share_of_step"],
+                    "flops_per_launch": classes[dom]["work_per_step"] / classes[dom]["launches_per_step"],
+                    "avg_launch_ms": classes[dom]["ms_per_step"] / classes[dom]["launches_per_step"],
+                    "launches_per_step": classes[dom]["launches_per_step"]}
 
     # ---------------- reduce over ranks (max time), assemble the line ----------------
     if world > 1:
@@ -288,33 +368,32 @@ def main():
     ms_step = ms_total / K
     value = world * B / (T * ms_step * 1e-3)
     e2e_value = world * B / (T * (ms_e2e / K) * 1e-3)
-    flops_step = model.flops_per_forward()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = cpu_reference_rate(im_size, H, Wd, T, args.cpu_steps, 1, batch=1)
+        v, sec, cores = cpu_reference_rate(WORKLOADS[args.workload], args.cpu_steps, 1)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sec_per_step_per_image": sec,
-                        "sample": f"oracle port (PyTorch fp32, {cores} threads): 1 image, {args.cpu_steps} timed reverse "
-                                  f"steps after 1 warm-up, extrapolated linearly to T={T}"}
+                        "sample": f"oracle port (PyTorch fp32, {cores} threads): 1 image, {args.cpu_steps} timed reverse steps "
+                                  f"after 1 warm-up, extrapolated linearly to {T} steps"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": desc, "batch_per_gpu": B, "height": H, "width": Wd, "schedule_steps": T,
-                       "step": "one reverse-diffusion step (Unet.forward + fused posterior update) over the batch",
-                       "l2": "per-step working set (activations ~GBs) exceeds the 126 MB L2; no explicit flush",
-                       "unet_params_m": sum(p.numel() for p in model.parameters()) / 1e6,
-                       "guidance": "not in this workload (SGG path = configs[2], see DESIGN.md)"},
+            "config": {"workload": spec["desc"], "batch_per_gpu": B, "latent": [spec["h"], spec["w"]], "schedule_steps": T,
+                       "step": "one reverse-diffusion step over the batch (UNet forward + posterior"
+                               + (" + SRGAN x4 + DeepLabV3+ forward/CE/input-gradient + guidance update)" if spec["kind"] == "sgg" else " update)"),
+                       "l2": "per-step working set (GBs of activations) exceeds the 126 MB L2; no explicit flush",
+                       "weights": "random init (UNet seed 3455, seg 42, SRGAN 0), BatchNorm statistics randomised"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": int(launches),
-            "launches_per_step": launches / K,
+            "gpu_launches": int(launches), "launches_per_step": launches / K,
             "clocks": clocks,
             "roofline": roofline,
             "kernel_classes": classes,
-            "step_tflops": flops_step / (ms_step * 1e-3) / 1e12,
             "step_gflop_per_image": flops_step / B / 1e9,
+            "step_gflop_parts_per_image": {k: v / B / 1e9 for k, v in flop_parts.items()},
+            "step_tflops": flops_step / (ms_step * 1e-3) / 1e12,
             "step_frac_of_tensor_peak": flops_step / (ms_step * 1e-3) / 1e12 / peaks["tf_sustained"],
             "cpu_baseline": cpu_baseline,
             "finite": finite,

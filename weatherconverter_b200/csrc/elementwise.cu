@@ -158,6 +158,7 @@ int add_noise(const float* x0, const float* noise, float* out, size_t n_per_samp
 
 int sgg_update(const float* grad, const float* mu, const float* sigz, float* out, float* mag_out, int B, int h, int w,
                int pool, float lam, cudaStream_t st) {
+  ProfScope prof(kProfScheduler, st, static_cast<double>(B) * h * w * (12.0 * pool * pool + 36.0));
   sgg_update_kernel<<<grid_for(static_cast<size_t>(B) * h * w), 256, 0, st>>>(grad, mu, sigz, out, mag_out, B, h, w,
                                                                               pool, lam);
   WC_LAUNCH_CHECK();

@@ -78,6 +78,9 @@ int build(wc_srgan* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
     OutSpec os; os.mode = kOutNHWC; os.out = out;
     auto op = std::make_shared<ConvOp>();
     if (int e = build_conv(op.get(), arena, x, w, g, co, nullptr, nullptr, ep, os, st)) { err = e; return; }
+    // algorithmic FLOPs = the reference's separable form (depthwise 3x3 + pointwise), not the composed dense conv
+    op->flops = 2.0 * x.pixels() * (9.0 * x.C + static_cast<double>(x.C) * co);
+    for (auto& pl : op->plans) pl.flops = op->flops / op->plans.size();
     net->flops += op->flops;
     net->ops.push_back([op](cudaStream_t s) { return op->run(s); });
   };
@@ -135,6 +138,8 @@ int build(wc_srgan* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
         OutSpec os; os.mode = kOutNHWC; os.out = up; os.up = 2; os.py = q / 2; os.px = q % 2;
         auto op = std::make_shared<ConvOp>();
         if (int e = build_conv(op.get(), arena, cur, ws_, g, NCH, nullptr, nullptr, ep, os, st)) return e;
+        op->flops = 2.0 * cur.pixels() * (9.0 * NCH / 4.0 + static_cast<double>(NCH) * NCH);   // this phase's share
+        for (auto& pl : op->plans) pl.flops = op->flops / op->plans.size();
         net->flops += op->flops;
         net->ops.push_back([op](cudaStream_t s) { return op->run(s); });
       }

@@ -44,9 +44,9 @@ class LinearNoiseScheduler:
         if t.numel() == 1 and B > 1:
             t = t.expand(B).contiguous()
         out = torch.empty_like(original)
-        check(lib().wc_add_noise(ptr(original), ptr(noise), ptr(out), original[0].numel(), B,
-                                 ptr(self.sqrt_alpha_cum_prod.to(original.device)),
-                                 ptr(self.sqrt_one_minus_alpha_cum_prod.to(original.device)), ptr(t), stream_ptr()))
+        ta, tb = self.sqrt_alpha_cum_prod.to(original.device), self.sqrt_one_minus_alpha_cum_prod.to(original.device)
+        check(lib().wc_add_noise(ptr(original), ptr(noise), ptr(out), original[0].numel(), B, ptr(ta), ptr(tb), ptr(t),
+                                 stream_ptr()))
         return out
 
     add_noise2 = add_noise  # reference :30-35 (same arithmetic, tables indexed on the module device)
@@ -101,7 +101,8 @@ class LinearNoiseScheduler:
         mean = torch.empty_like(xt)
         all_zero = bool(torch.all(t == 0))  # same host sync as the reference (:71)
         dev = xt.device
-        tabs = (ptr(self.betas.to(dev)), ptr(self.alphas.to(dev)), ptr(self.sqrt_one_minus_alpha_cum_prod.to(dev)))
+        keep = (self.betas.to(dev), self.alphas.to(dev), self.sqrt_one_minus_alpha_cum_prod.to(dev))
+        tabs = tuple(ptr(k) for k in keep)
         if all_zero:
             check(lib().wc_ddpm_step_batched(ptr(xt), ptr(noise_pred), None, None, ptr(mean), None, xt[0].numel(), B,
                                              *tabs, ptr(t), stream_ptr()))

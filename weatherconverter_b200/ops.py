@@ -70,7 +70,8 @@ def conv_in(x, weight, bias=None, scale=None, shift=None, stride=1, pad=None, re
         pad = K // 2
     Ho, Wo = (H + 2 * pad - K) // stride + 1, (W + 2 * pad - K) // stride + 1
     y = torch.empty(B, Ho, Wo, Cout, device=x.device, dtype=torch.bfloat16)
-    check(lib().wc_conv_in(ptr(x.contiguous()), ptr(weight.contiguous()), ptr(bias), ptr(scale), ptr(shift), ptr(y),
+    x, weight = x.contiguous(), weight.contiguous()    # named: must outlive the raw-pointer call
+    check(lib().wc_conv_in(ptr(x), ptr(weight), ptr(bias), ptr(scale), ptr(shift), ptr(y),
                            B, H, W, Cout, K, stride, pad, Cout, 1 if relu else 0, stream_ptr()))
     return y
 
@@ -81,7 +82,8 @@ def conv_out(x, weight, bias=None, tanh_out=False):
     B, H, W, Cin = x.shape
     K = weight.shape[-1]
     y = torch.empty(B, 3, H, W, device=x.device, dtype=torch.float32)
-    check(lib().wc_conv_out(ptr(x), ptr(weight.contiguous()), ptr(bias), ptr(y), B, H, W, Cin, K, x.stride(2),
+    weight = weight.contiguous()
+    check(lib().wc_conv_out(ptr(x), ptr(weight), ptr(bias), ptr(y), B, H, W, Cin, K, x.stride(2),
                             1 if tanh_out else 0, stream_ptr()))
     return y
 
@@ -91,7 +93,8 @@ def attention(q, k, vt):
     require_cuda(q, k, vt)
     B, h, N, hd = q.shape
     out = torch.empty(B, N, h * hd, device=q.device, dtype=torch.bfloat16)
-    check(lib().wc_attention(ptr(q.contiguous()), ptr(k.contiguous()), ptr(vt.contiguous()), ptr(out), B, h, N, hd,
+    q, k, vt = q.contiguous(), k.contiguous(), vt.contiguous()
+    check(lib().wc_attention(ptr(q), ptr(k), ptr(vt), ptr(out), B, h, N, hd,
                              h * hd, stream_ptr()))
     return out
 
@@ -105,7 +108,8 @@ def ddpm_step(xt, eps, z, beta, sqrt_one_minus_acp, sqrt_alpha, sigma, want_part
     out = torch.empty_like(xt)
     mean = torch.empty_like(xt) if want_parts else None
     sigz = torch.empty_like(xt) if (want_parts and z is not None) else None
-    check(lib().wc_ddpm_step(ptr(xt), ptr(eps), ptr(z.contiguous() if z is not None else None), ptr(out), ptr(mean),
+    z = z.contiguous() if z is not None else None
+    check(lib().wc_ddpm_step(ptr(xt), ptr(eps), ptr(z), ptr(out), ptr(mean),
                              ptr(sigz), n, B, float(beta), float(sqrt_one_minus_acp), float(sqrt_alpha), float(sigma),
                              stream_ptr()))
     return (out, mean, sigz) if want_parts else out
