@@ -145,6 +145,12 @@ size_t wc_seg_workspace_bytes(const wc_seg* net, int batch, int H, int W, int wi
  * skips the backward pass), loss f32 [B], logits nchw_f32 [B,19,H,W]. */
 int wc_seg_infer(wc_seg* net, const float* x, const int64_t* labels, int64_t* pred, float* input_grad, float* loss,
                  float* logits, int batch, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, but input_grad is [B,3,H/grad_pool,W/grad_pool] = F.avg_pool2d(d loss / d x, grad_pool) (sgg/sgg.py:18): the
+ * pooling is folded into the stem's data-gradient kernel (both are linear), so the full-resolution gradient is
+ * never materialised.  grad_pool in {1 (no pooling), 2, 4, 6, 8}. */
+int wc_seg_infer_pooled(wc_seg* net, const float* x, const int64_t* labels, int64_t* pred, float* input_grad, float* loss,
+                        float* logits, int batch, int H, int W, int grad_pool, void* workspace, size_t workspace_bytes,
+                        void* stream);
 double wc_seg_flops(const wc_seg* net, int backward);
 int wc_seg_launches(const wc_seg* net);
 

@@ -97,6 +97,22 @@ def test_seg_gradient_has_every_branch(golden):
         assert dist > 1.1 * full, cut
 
 
+def test_fused_pooled_gradient_equals_avg_pool_of_gradient(golden):
+    """wc_seg_infer_pooled(grad_pool=4) == F.avg_pool2d(full input gradient, 4) (sgg.py:18) up to fp32 re-association."""
+    import torch.nn.functional as F
+    dev = _dev()
+    d = golden("seg_infer.pt")["resnet50_128x256"]
+    m = _seg("resnet50", d["seed"], dev)
+    x, gt = d["x"].to(dev).repeat(2, 1, 1, 1), d["gt"].to(dev).repeat(2, 1, 1)
+    full = m.infer(x, gt)["grad"]
+    for P in (2, 4, 8):
+        pooled = m.infer(x, gt, grad_pool=P)["grad"]
+        ref = F.avg_pool2d(full, P, P)
+        rel = float((pooled - ref).norm() / ref.norm())
+        print(f"pool {P}: rms-rel {rel:.2e}")
+        assert pooled.shape == ref.shape and rel < 1e-4
+
+
 def test_sgg_update_kernel_matches_reference_arithmetic(golden):
     """wc_sgg_update == avg_pool2d(4) -> compute_gradient_magnitude (float64) -> mu + lambda*sigma*mag + sigma
     (sgg.py:18-22, inference.py:39-43), bit-exact after the final cast to fp32, for a batch of gradients."""

@@ -27,6 +27,28 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x for a PAIR of inputs on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3
+// minimax polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of P), exponent patched with one
+// integer multiply-add.  Used for a fixed share of every 32-column chunk so the MUFU and FMA pipes work in parallel
+// (the softmax of the N = 8192 layers is exp-throughput bound: N^2 exponentials per head).
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23: adding it rounds x to the nearest integer in the low mantissa bits
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 r = fadd2(x, make_float2(kMagic, kMagic));
+  const float2 n = fadd2(r, make_float2(-kMagic, -kMagic));
+  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
+  float2 p = ffma2(f, make_float2(0.05517163872718811f, 0.05517163872718811f), make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = ffma2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = ffma2(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  float2 o;
+  o.x = __uint_as_float(__float_as_uint(r.x) * 0x800000u + __float_as_uint(p.x));  // bits(p) + (n << 23)
+  o.y = __uint_as_float(__float_as_uint(r.y) * 0x800000u + __float_as_uint(p.y));
+  return o;
+}
+
+constexpr int kPolyPerChunk = 14;  // of every 32 exponentials, this many run on the FMA pipe (must be even)
+
 struct AttnArgs {
   int ntok, heads, ldo;
   float scale_log2;  // log2(e) / sqrt(hd)
@@ -188,7 +210,7 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
     const uint32_t p_row = p_smem + q * Cfg::kPTile + row * 128;
     const float sl2 = p.scale_log2;
     float m = -INFINITY;
-    float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 lsum[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     // One KV tile of the online softmax.  TAIL (compile-time) masks keys >= ntok; only the last tile can need it,
     // so the hot path carries no per-element predicates.  TMEM chunk loads are software-pipelined: the load of
     // chunk c+1 is in flight while chunk c is processed.
@@ -198,7 +220,9 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
       constexpr int NCH = BKV / 32;
       uint32_t ra[32], rb[32];
       // ---- pass 1: tile max
-      float t0 = -INFINITY, t1 = -INFINITY;
+      float tm[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tm[i] = -INFINITY;   // 8 independent max chains (no serial FMNMX dependency)
       tmem_ld32(s_tmem, ra);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -212,11 +236,10 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
             if (kv0 + 32 * c + i >= p.ntok) a = -INFINITY;
             if (kv0 + 32 * c + i + 1 >= p.ntok) b2 = -INFINITY;
           }
-          t0 = fmaxf(t0, a);
-          t1 = fmaxf(t1, b2);
+          tm[(i >> 1) & 7] = fmaxf(tm[(i >> 1) & 7], fmaxf(a, b2));
         }
       }
-      const float tmax = fmaxf(t0, t1);
+      const float tmax = fmaxf(fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3])), fmaxf(fmaxf(tm[4], tm[5]), fmaxf(tm[6], tm[7])));
       // start re-reading S for pass 2 while we (possibly) wait for the previous PV and rescale O
       tmem_ld32(s_tmem, ra);
       if (j > 0) mbar_wait(pv_done(q), (j - 1) & 1u);  // O_{j-1} complete, P buffer free
@@ -229,7 +252,7 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
           const float m_new = fmaxf(m, tmax);
           const float alpha = ex2_approx((m - m_new) * sl2);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) lsum[i] *= alpha;
+          for (int i = 0; i < 2; ++i) { lsum[i].x *= alpha; lsum[i].y *= alpha; }
           m = m_new;
           tmem_wait_ld();  // ra holds chunk 0 of pass 2; keep the TMEM pipe ordered before O traffic
 #pragma unroll
@@ -252,14 +275,23 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
         uint32_t(&cur)[32] = (c & 1) ? rb : ra;
         if (c + 1 < NCH) tmem_ld32(s_tmem + 32 * (c + 1), (c & 1) ? ra : rb);
         float pv[32];
+        const float2 sl2v = make_float2(sl2, sl2), mnegv = make_float2(mneg, mneg);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = ex2_approx(fmaf(__uint_as_float(cur[i]), sl2, mneg));
-          if (TAIL) {
-            if (kv0 + 32 * c + i >= p.ntok) v = 0.f;
+        for (int i = 0; i < 32; i += 2) {
+          const float2 xs = ffma2(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2v, mnegv);
+          float2 v;
+          if (i < kPolyPerChunk) {
+            v = exp2_poly2(xs);
+          } else {
+            v.x = ex2_approx(xs.x);
+            v.y = ex2_approx(xs.y);
           }
-          pv[i] = v;
-          lsum[i & 3] += v;
+          if (TAIL) {
+            if (kv0 + 32 * c + i >= p.ntok) v.x = 0.f;
+            if (kv0 + 32 * c + i + 1 >= p.ntok) v.y = 0.f;
+          }
+          pv[i] = v.x; pv[i + 1] = v.y;
+          lsum[(i >> 1) & 1] = fadd2(lsum[(i >> 1) & 1], v);
         }
         const uint32_t blk = p_row + ((32 * c) >> 6) * (128 * 128);
 #pragma unroll
@@ -281,7 +313,7 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
       if (j * BKV + BKV > p.ntok) tile(j, std::true_type{});
       else tile(j, std::false_type{});
     }
-    const float l = (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+    const float l = (lsum[0].x + lsum[0].y) + (lsum[1].x + lsum[1].y);
     // ---- finalize: O / l -> bf16 -> out[b, tok, head*hd + d]
     mbar_wait(pv_done(q), (nkv - 1) & 1u);
     tc_fence_after();

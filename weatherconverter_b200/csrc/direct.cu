@@ -70,6 +70,69 @@ __global__ void conv_small_cin_kernel(const float* __restrict__ x, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Same convolution specialised for Cout = 64: one thread per output pixel computes all 64 channels; weights live
+// in shared memory as [tap][64] and are read as broadcast 16-byte vectors; the MACs are packed FFMA2.
+template <int CIN>
+__global__ void __launch_bounds__(128)
+conv_stem64_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][CIN][K][K]*/,
+                   const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                   __nv_bfloat16* __restrict__ y, int B, int H, int W, int Ho, int Wo, int K, int stride, int pad, int ldy,
+                   int relu, const float* __restrict__ prelu) {
+  extern __shared__ float sw[];  // [CIN*K*K][64]
+  const int taps = CIN * K * K;
+  for (int i = threadIdx.x; i < taps * 64; i += blockDim.x) {
+    const int n = i & 63, t = i >> 6;
+    sw[i] = w[static_cast<size_t>(n) * taps + t];
+  }
+  __syncthreads();
+  const size_t npix = static_cast<size_t>(B) * Ho * Wo;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ox = static_cast<int>(pix % Wo), oy = static_cast<int>((pix / Wo) % Ho), b = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
+    float2 acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = bias ? make_float2(bias[2 * j], bias[2 * j + 1]) : make_float2(0.f, 0.f);
+    for (int c = 0; c < CIN; ++c) {
+      const float* xp = x + (static_cast<size_t>(b) * CIN + c) * H * W;
+      for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * stride - pad + ky;
+        const bool rowok = iy >= 0 && iy < H;
+        for (int kx = 0; kx < K; ++kx) {
+          const int ix = ox * stride - pad + kx;
+          float v = 0.f;
+          if (rowok && ix >= 0 && ix < W) v = __ldg(xp + static_cast<size_t>(iy) * W + ix);
+          const float2 vv = make_float2(v, v);
+          const float4* wp = reinterpret_cast<const float4*>(sw + ((c * K + ky) * K + kx) * 64);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 w4 = wp[j];
+            acc[2 * j] = ffma2(vv, make_float2(w4.x, w4.y), acc[2 * j]);
+            acc[2 * j + 1] = ffma2(vv, make_float2(w4.z, w4.w), acc[2 * j + 1]);
+          }
+        }
+      }
+    }
+    uint4* op = reinterpret_cast<uint4*>(y + pix * ldy);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { f[2 * j] = acc[4 * q + j].x; f[2 * j + 1] = acc[4 * q + j].y; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int n = 8 * q + j;
+        if (scale) f[j] = fmaf(f[j], scale[n], shift[n]);
+        if (relu) f[j] = fmaxf(f[j], 0.f);
+        if (prelu) f[j] = f[j] > 0.f ? f[j] : f[j] * prelu[n];
+      }
+      uint4 u;
+      u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+      op[q] = u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // conv KxK (stride 1, pad K/2) from NHWC bf16 (Cin % 8 == 0) to NCHW fp32 with COUT (<=4) outputs; one thread
 // per output pixel; optional tanh epilogue y = (tanh(v)+1)/2 (SRGAN, models.py:92).
 template <int COUT>
@@ -234,6 +297,17 @@ int conv_small_cin(const float* x, const float* w, const float* bias, const floa
                                        static_cast<int>(smem)));
   const size_t npix = static_cast<size_t>(B) * Ho * Wo;
   ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * (12.0 * H * W + 2.0 * Ho * Wo * Cout));
+  if (Cout == 64) {
+    static size_t attr_set = 0;
+    if (smem > 48 * 1024 && smem > attr_set) {
+      WC_CHECK_CUDA(cudaFuncSetAttribute(conv_stem64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      attr_set = smem;
+    }
+    conv_stem64_kernel<3><<<grid_for(npix, 128), 128, smem, st>>>(x, w, bias, scale, shift, y, B, H, W, Ho, Wo, K, stride, pad,
+                                                                 ldy, relu, prelu);
+    WC_LAUNCH_CHECK();
+    return 0;
+  }
   conv_small_cin_kernel<3><<<grid_for(npix, threads / octs), threads, smem, st>>>(
       x, w, bias, scale, shift, y, B, H, W, Ho, Wo, Cout, K, stride, pad, ldy, relu, prelu);
   WC_LAUNCH_CHECK();

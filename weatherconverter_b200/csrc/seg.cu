@@ -32,6 +32,8 @@ int logits_bilinear_bwd(const float* dhi, __nv_bfloat16* dlo, int B, int h, int 
 int conv1_dgrad(const __nv_bfloat16* dz, const float* w, const float* scale, float* dx, int B, int H, int W, int Cout,
                 cudaStream_t st);
 int relu_mask_inplace(__nv_bfloat16* d, const __nv_bfloat16* m, size_t npix, int C, int ldd, int ldm, cudaStream_t st);
+int conv1_dgrad_weff(const float* w, const float* scale, float* weff, int P, cudaStream_t st);
+int conv1_dgrad_pooled(const __nv_bfloat16* dz, const float* weff, float* out, int B, int H, int W, int P, cudaStream_t st);
 }  // namespace wc
 
 struct wc_seg {
@@ -39,7 +41,7 @@ struct wc_seg {
   int num_classes;
   wc::ParamTable params;
   std::unique_ptr<wc::DeviceArena> arena;
-  int B = 0, H = 0, W = 0, with_grad = 0;
+  int B = 0, H = 0, W = 0, with_grad = 0, grad_pool = 1;
   void* ws = nullptr;
   size_t ws_bytes = 0;
   wc::OpList fwd_ops, bwd_ops;
@@ -335,8 +337,17 @@ int build(wc_seg* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
     wc_seg* n = net;
     const Act gp = g;
     const float* sc = bn1.first;
+    const int P = net->grad_pool;
+    float* weff = nullptr;
+    if (!dry && P > 1) {
+      const int R = P / 2 + 3;
+      weff = static_cast<float*>(b.arena->alloc(static_cast<size_t>(R) * R * 192 * sizeof(float)));
+      if (!weff) return 1;
+      if (int e = conv1_dgrad_weff(w_conv1, sc, weff, P, st)) return e;
+    }
     b.push([=](cudaStream_t s) {
       if (int e = maxpool_bwd(gp.ptr, pool_idx, c1.ptr, dc1.ptr, B, H2, W2, 64, s)) return e;
+      if (P > 1) return conv1_dgrad_pooled(dc1.ptr, weff, n->grad_out, B, H, W, P, s);
       return conv1_dgrad(dc1.ptr, w_conv1, sc, n->grad_out, B, H, W, 64, s);
     });
     net->flops_bwd += 2.0 * B * H2 * W2 * 147.0 * 64;
@@ -378,17 +389,28 @@ size_t wc_seg_workspace_bytes(const wc_seg* net_c, int batch, int H, int W, int 
   return need;
 }
 
+int wc_seg_infer_pooled(wc_seg* net, const float* x, const int64_t* labels, int64_t* pred, float* input_grad, float* loss,
+                        float* logits, int batch, int H, int W, int grad_pool, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 int wc_seg_infer(wc_seg* net, const float* x, const int64_t* labels, int64_t* pred, float* input_grad, float* loss,
                  float* logits, int batch, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  return wc_seg_infer_pooled(net, x, labels, pred, input_grad, loss, logits, batch, H, W, 1, workspace, workspace_bytes, stream);
+}
+
+int wc_seg_infer_pooled(wc_seg* net, const float* x, const int64_t* labels, int64_t* pred, float* input_grad, float* loss,
+                        float* logits, int batch, int H, int W, int grad_pool, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  WC_REQUIRE(grad_pool >= 1, "grad_pool must be >= 1");
   WC_REQUIRE(net && x && labels && workspace, "null argument");
   WC_REQUIRE(H % 32 == 0 && W % 32 == 0, "H and W must be multiples of 32 (output stride 16, stride-2 phase views)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int with_grad = input_grad != nullptr;
-  if (net->B != batch || net->H != H || net->W != W || net->with_grad != with_grad || net->ws != workspace ||
+  if (net->B != batch || net->H != H || net->W != W || net->with_grad != with_grad || net->grad_pool != grad_pool || net->ws != workspace ||
       net->ws_bytes != workspace_bytes) {
     net->fwd_ops.clear(); net->bwd_ops.clear();
     net->arena = std::make_unique<DeviceArena>();
-    net->B = batch; net->H = H; net->W = W; net->with_grad = with_grad; net->ws = workspace; net->ws_bytes = workspace_bytes;
+    net->B = batch; net->H = H; net->W = W; net->with_grad = with_grad; net->grad_pool = grad_pool; net->ws = workspace; net->ws_bytes = workspace_bytes;
     net->flops_fwd = net->flops_bwd = 0;
     if (int e = build(net, false, workspace, workspace_bytes, st)) {
       net->B = 0;

@@ -77,31 +77,48 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 
 // dX[b,iy,ix,c] = sum over the (<= 4) pooling windows containing (iy,ix) whose argmax is this pixel; then the
 // ReLU mask of the pre-pool activation (x > 0) is applied (conv1+bn1+relu precede the pool, resnet.py:142-145).
+// 8 channels (16 bytes) per thread.
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                                    const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx, int B, int H,
                                    int W, int C, int Ho, int Wo) {
-  const size_t total = static_cast<size_t>(B) * H * W * C;
+  const int c8n = C / 8;
+  const size_t total = static_cast<size_t>(B) * H * W * c8n;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    size_t p = i / C;
+    const int c8 = static_cast<int>(i % c8n);
+    size_t p = i / c8n;
     const int ix = static_cast<int>(p % W), iy = static_cast<int>((p / W) % H), b = static_cast<int>(p / (static_cast<size_t>(W) * H));
-    float acc = 0.f;
-    if (__bfloat162float(x[i]) > 0.f) {
-      for (int oy = (iy) / 2; oy <= (iy + 1) / 2; ++oy) {   // windows with 2*oy-1 <= iy <= 2*oy+1
-        if (oy < 0 || oy >= Ho) continue;
-        const int ky = iy - (2 * oy - 1);
-        if (ky < 0 || ky > 2) continue;
-        for (int ox = (ix) / 2; ox <= (ix + 1) / 2; ++ox) {
-          if (ox < 0 || ox >= Wo) continue;
-          const int kx = ix - (2 * ox - 1);
-          if (kx < 0 || kx > 2) continue;
-          const size_t q = ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * C + c;
-          if (idx[q] == ky * 3 + kx) acc += __bfloat162float(dy[q]);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {   // windows with 2*oy-1 <= iy <= 2*oy+1
+      if (oy >= Ho) continue;
+      const int ky = iy - (2 * oy - 1);
+      for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
+        if (ox >= Wo) continue;
+        const int kx = ix - (2 * ox - 1);
+        const uint32_t tap = static_cast<uint32_t>(ky * 3 + kx);
+        const size_t q = ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * C + c8 * 8;
+        const uint2 ii = __ldg(reinterpret_cast<const uint2*>(idx + q));
+        const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy + q));
+        const uint32_t* gp = &g.x;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t t = ((j < 4 ? ii.x : ii.y) >> (8 * (j & 3))) & 0xffu;
+          const float2 f = unpack_bf16(gp[j >> 1]);
+          if (t == tap) acc[j] += (j & 1) ? f.y : f.x;
         }
       }
     }
-    dx[i] = __float2bfloat16_rn(acc);
+    const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + p * C + c8 * 8));
+    const uint32_t* xp = &xv.x;
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16(xp[j]);
+      o[j] = pack_bf16(f.x > 0.f ? acc[2 * j] : 0.f, f.y > 0.f ? acc[2 * j + 1] : 0.f);
+    }
+    *reinterpret_cast<uint4*>(dx + p * C + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -366,46 +383,119 @@ __global__ void logits_bilinear_bwd_kernel(const float* __restrict__ dhi, __nv_b
 
 // ---- data gradient of conv1 (7x7, stride 2, pad 3, 3 input channels) to the NCHW fp32 image:
 // dX[b,c,y,x] = sum_{ky,kx: parity ok} sum_o dZ[b,(y+3-ky)/2,(x+3-kx)/2,o] * W[o,c,ky,kx] * scale[o]
-__global__ void conv1_dgrad_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ w /*[64][3][7][7]*/,
-                                   const float* __restrict__ scale, float* __restrict__ dx, int B, int H, int W, int Ho,
-                                   int Wo, int Cout) {
-  extern __shared__ float sw[];  // [49][Cout][3]
-  for (int i = threadIdx.x; i < 49 * Cout * 3; i += blockDim.x) {
-    const int c = i % 3, o = (i / 3) % Cout, t = i / (3 * Cout);
+// blockIdx.y = parity class (y&1, x&1): every thread of a block uses the same tap subset, so the weight reads are
+// warp-uniform broadcasts ([tap][c][64] floats in shared memory, 16-byte vectors) and the MACs are packed FFMA2.
+__global__ void __launch_bounds__(128)
+conv1_dgrad_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ w /*[64][3][7][7]*/,
+                   const float* __restrict__ scale, float* __restrict__ dx, int B, int H, int W, int Ho, int Wo) {
+  extern __shared__ float sw[];  // [49][3][64]
+  for (int i = threadIdx.x; i < 49 * 3 * 64; i += blockDim.x) {
+    const int o = i & 63, c = (i >> 6) % 3, t = i / 192;
     sw[i] = w[(static_cast<size_t>(o) * 3 + c) * 49 + t] * (scale ? scale[o] : 1.f);
   }
   __syncthreads();
-  const size_t total = static_cast<size_t>(B) * H * W;
+  const int py = blockIdx.y >> 1, px = blockIdx.y & 1;
+  const int Hh = H / 2, Wh = W / 2;
+  const size_t total = static_cast<size_t>(B) * Hh * Wh;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int x = static_cast<int>(i % W), y = static_cast<int>((i / W) % H), b = static_cast<int>(i / (static_cast<size_t>(W) * H));
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    for (int ky = (y + 3) & 1; ky < 7; ky += 2) {
-      const int oy = (y + 3 - ky) / 2;
-      if (y + 3 - ky < 0 || oy >= Ho) continue;
-      for (int kx = (x + 3) & 1; kx < 7; kx += 2) {
-        const int ox = (x + 3 - kx) / 2;
-        if (x + 3 - kx < 0 || ox >= Wo) continue;
-        const uint4* zp = reinterpret_cast<const uint4*>(dz + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * Cout);
-        const float* wp = sw + static_cast<size_t>(ky * 7 + kx) * Cout * 3;
-        for (int o8 = 0; o8 < Cout / 8; ++o8) {
-          const uint4 u = __ldg(zp + o8);
-          float f[8];
-          float2 t;
-          t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
-          t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
-          t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
-          t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+    const int xh = static_cast<int>(i % Wh), yh = static_cast<int>((i / Wh) % Hh), b = static_cast<int>(i / (static_cast<size_t>(Wh) * Hh));
+    const int x = 2 * xh + px, y = 2 * yh + py;
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
+    for (int ky = (py + 1) & 1; ky < 7; ky += 2) {
+      const int ny = y + 3 - ky;
+      const int oy = ny >> 1;
+      if (ny < 0 || oy >= Ho) continue;
+      for (int kx = (px + 1) & 1; kx < 7; kx += 2) {
+        const int nx = x + 3 - kx;
+        const int ox = nx >> 1;
+        if (nx < 0 || ox >= Wo) continue;
+        const uint4* zp = reinterpret_cast<const uint4*>(dz + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * 64);
+        const float4* wp = reinterpret_cast<const float4*>(sw + (ky * 7 + kx) * 192);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float* ww = wp + (o8 * 8 + j) * 3;
-            a0 = fmaf(f[j], ww[0], a0); a1 = fmaf(f[j], ww[1], a1); a2 = fmaf(f[j], ww[2], a2);
-          }
+        for (int o8 = 0; o8 < 8; ++o8) {
+          const uint4 u = __ldg(zp + o8);
+          const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+          const float4 w0a = wp[o8 * 2], w0b = wp[o8 * 2 + 1];
+          const float4 w1a = wp[16 + o8 * 2], w1b = wp[16 + o8 * 2 + 1];
+          const float4 w2a = wp[32 + o8 * 2], w2b = wp[32 + o8 * 2 + 1];
+          a0 = ffma2(f0, make_float2(w0a.x, w0a.y), a0); a0 = ffma2(f1, make_float2(w0a.z, w0a.w), a0);
+          a0 = ffma2(f2, make_float2(w0b.x, w0b.y), a0); a0 = ffma2(f3, make_float2(w0b.z, w0b.w), a0);
+          a1 = ffma2(f0, make_float2(w1a.x, w1a.y), a1); a1 = ffma2(f1, make_float2(w1a.z, w1a.w), a1);
+          a1 = ffma2(f2, make_float2(w1b.x, w1b.y), a1); a1 = ffma2(f3, make_float2(w1b.z, w1b.w), a1);
+          a2 = ffma2(f0, make_float2(w2a.x, w2a.y), a2); a2 = ffma2(f1, make_float2(w2a.z, w2a.w), a2);
+          a2 = ffma2(f2, make_float2(w2b.x, w2b.y), a2); a2 = ffma2(f3, make_float2(w2b.z, w2b.w), a2);
         }
       }
     }
     const size_t plane = static_cast<size_t>(H) * W, o = static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(y) * W + x;
-    dx[o] = a0; dx[o + plane] = a1; dx[o + 2 * plane] = a2;
+    dx[o] = a0.x + a0.y; dx[o + plane] = a1.x + a1.y; dx[o + 2 * plane] = a2.x + a2.y;
+  }
+}
+
+// ---- avg_pool2d(P) of the conv1 data gradient, fused (both are linear):
+//   pooled[b,c,Y,X] = (1/P^2) sum_{j,i<P} dX[b,c,P*Y+j,P*X+i] = sum_{r,s} sum_o dZ[b,(P/2)*Y+r,(P/2)*X+s,o] * Weff[r,s,c,o]
+//   Weff[r,s,c,o] = scale[o]/P^2 * sum_{j: 0<=j+3-2r<=6} sum_{i: 0<=i+3-2s<=6} W[o,c,j+3-2r,i+3-2s],  r,s in [-1, P/2+1]
+// (position independent; dZ outside the map contributes nothing).  One thread per pooled pixel, weights in smem.
+__global__ void conv1_dgrad_weff_kernel(const float* __restrict__ w, const float* __restrict__ scale, float* __restrict__ weff,
+                                        int P) {
+  const int R = P / 2 + 3;
+  const int total = R * R * 3 * 64;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int o = idx & 63, c = (idx >> 6) % 3, rs = idx / 192, s_ = rs % R - 1, r_ = rs / R - 1;
+    float acc = 0.f;
+    for (int j = 0; j < P; ++j) {
+      const int ky = j + 3 - 2 * r_;
+      if (ky < 0 || ky > 6) continue;
+      for (int i = 0; i < P; ++i) {
+        const int kx = i + 3 - 2 * s_;
+        if (kx < 0 || kx > 6) continue;
+        acc += w[((static_cast<size_t>(o) * 3 + c) * 7 + ky) * 7 + kx];
+      }
+    }
+    weff[idx] = acc * (scale ? scale[o] : 1.f) / static_cast<float>(P * P);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+conv1_dgrad_pooled_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ weff, float* __restrict__ out, int B,
+                          int Ho, int Wo, int P) {
+  extern __shared__ float sw[];  // [R*R][3][64]
+  const int R = P / 2 + 3, half = P / 2;
+  for (int i = threadIdx.x; i < R * R * 192; i += blockDim.x) sw[i] = weff[i];
+  __syncthreads();
+  const int Hp = Ho / half, Wp = Wo / half;
+  const size_t total = static_cast<size_t>(B) * Hp * Wp;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(i % Wp), Y = static_cast<int>((i / Wp) % Hp), b = static_cast<int>(i / (static_cast<size_t>(Wp) * Hp));
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0;
+    for (int r = 0; r < R; ++r) {
+      const int oy = half * Y + r - 1;
+      if (oy < 0 || oy >= Ho) continue;
+      for (int s_ = 0; s_ < R; ++s_) {
+        const int ox = half * X + s_ - 1;
+        if (ox < 0 || ox >= Wo) continue;
+        const uint4* zp = reinterpret_cast<const uint4*>(dz + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * 64);
+        const float4* wp = reinterpret_cast<const float4*>(sw + (r * R + s_) * 192);
+#pragma unroll
+        for (int o8 = 0; o8 < 8; ++o8) {
+          const uint4 u = __ldg(zp + o8);
+          const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+          const float4 w0a = wp[o8 * 2], w0b = wp[o8 * 2 + 1];
+          const float4 w1a = wp[16 + o8 * 2], w1b = wp[16 + o8 * 2 + 1];
+          const float4 w2a = wp[32 + o8 * 2], w2b = wp[32 + o8 * 2 + 1];
+          a0 = ffma2(f0, make_float2(w0a.x, w0a.y), a0); a0 = ffma2(f1, make_float2(w0a.z, w0a.w), a0);
+          a0 = ffma2(f2, make_float2(w0b.x, w0b.y), a0); a0 = ffma2(f3, make_float2(w0b.z, w0b.w), a0);
+          a1 = ffma2(f0, make_float2(w1a.x, w1a.y), a1); a1 = ffma2(f1, make_float2(w1a.z, w1a.w), a1);
+          a1 = ffma2(f2, make_float2(w1b.x, w1b.y), a1); a1 = ffma2(f3, make_float2(w1b.z, w1b.w), a1);
+          a2 = ffma2(f0, make_float2(w2a.x, w2a.y), a2); a2 = ffma2(f1, make_float2(w2a.z, w2a.w), a2);
+          a2 = ffma2(f2, make_float2(w2b.x, w2b.y), a2); a2 = ffma2(f3, make_float2(w2b.z, w2b.w), a2);
+        }
+      }
+    }
+    const size_t plane = static_cast<size_t>(Hp) * Wp, o = static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(Y) * Wp + X;
+    out[o] = a0.x + a0.y; out[o + plane] = a1.x + a1.y; out[o + 2 * plane] = a2.x + a2.y;
   }
 }
 
@@ -462,7 +552,7 @@ int maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16
                 int W, int C, cudaStream_t st) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   ProfScope prof(kProfOther, st, 0);
-  maxpool_bwd_kernel<<<grid_for(static_cast<size_t>(B) * H * W * C), 256, 0, st>>>(dy, idx, x, dx, B, H, W, C, Ho, Wo);
+  maxpool_bwd_kernel<<<grid_for(static_cast<size_t>(B) * H * W * C / 8), 256, 0, st>>>(dy, idx, x, dx, B, H, W, C, Ho, Wo);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -527,10 +617,32 @@ int logits_bilinear_bwd(const float* dhi, __nv_bfloat16* dlo, int B, int h, int 
 }
 int conv1_dgrad(const __nv_bfloat16* dz, const float* w, const float* scale, float* dx, int B, int H, int W, int Cout,
                 cudaStream_t st) {
+  WC_REQUIRE(Cout == 64 && H % 2 == 0 && W % 2 == 0, "conv1 data gradient is built for 64 output channels and even image dims");
   const int Ho = H / 2, Wo = W / 2;
-  const size_t smem = static_cast<size_t>(49) * Cout * 3 * sizeof(float);
+  const size_t smem = static_cast<size_t>(49) * 64 * 3 * sizeof(float);
   ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * (12.0 * H * W + 2.0 * Ho * Wo * Cout));
-  conv1_dgrad_kernel<<<grid_for(static_cast<size_t>(B) * H * W, 128), 128, smem, st>>>(dz, w, scale, dx, B, H, W, Ho, Wo, Cout);
+  const int gx = std::max(1, grid_for(static_cast<size_t>(B) * Ho * Wo, 128) / 2);
+  conv1_dgrad_kernel<<<dim3(gx, 4), 128, smem, st>>>(dz, w, scale, dx, B, H, W, Ho, Wo);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int conv1_dgrad_weff(const float* w, const float* scale, float* weff, int P, cudaStream_t st) {
+  conv1_dgrad_weff_kernel<<<8, 256, 0, st>>>(w, scale, weff, P);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+// out: [B,3,H/P,W/P] fp32 = avg_pool2d(conv1 data gradient, P); dz: [B,H/2,W/2,64] bf16
+int conv1_dgrad_pooled(const __nv_bfloat16* dz, const float* weff, float* out, int B, int H, int W, int P, cudaStream_t st) {
+  WC_REQUIRE(P >= 2 && P % 2 == 0 && P <= 8 && H % P == 0 && W % P == 0, "pooled stem gradient needs an even pool <= 8 dividing H and W");
+  const int R = P / 2 + 3;
+  const size_t smem = static_cast<size_t>(R) * R * 192 * sizeof(float);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    WC_CHECK_CUDA(cudaFuncSetAttribute(conv1_dgrad_pooled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * (12.0 * (H / P) * (W / P) + 2.0 * (H / 2) * (W / 2) * 64));
+  conv1_dgrad_pooled_kernel<<<grid_for(static_cast<size_t>(B) * (H / P) * (W / P), 128), 128, smem, st>>>(dz, weff, out, B, H / 2, W / 2, P);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -560,17 +672,17 @@ namespace {
 constexpr int kFT_H = 8, kFT_W = 64, kFHalo = 4, kFPlaneW = kFT_W + 2 * kFHalo /*72*/, kFPlaneH = kFT_H + 2 * kFHalo /*16*/;
 constexpr int kFPlane = kFPlaneW * kFPlaneH + 1;  // +1 word: de-phase the planes across banks for the staging writes
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dw /*[64][81]*/,
                    const float* __restrict__ dwb, const float* __restrict__ pw /*[3][64]*/, const float* __restrict__ pwb,
                    float* __restrict__ y, int B, int H, int W, int ldx) {
   extern __shared__ uint32_t sm[];
   uint32_t* tile = sm;                                            // [32][kFPlane] bf16x2
   float* wsm = reinterpret_cast<float*>(sm + 32 * kFPlane);       // [32][81][2]
-  float* red = wsm + 32 * 81 * 2;                                 // [128 threads][12]
+  float* red = wsm + 32 * 81 * 2;                                 // [3 groups][128 threads][12]
   const int tiles_x = (W + kFT_W - 1) / kFT_W, tiles_y = (H + kFT_H - 1) / kFT_H;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 32 * 81 * 2; i += 256) {
+  for (int i = tid; i < 32 * 81 * 2; i += 512) {
     const int j = i & 1, tap = (i >> 1) % 81, c2 = (i >> 1) / 81;
     wsm[i] = dw[(c2 * 2 + j) * 81 + tap];
   }
@@ -579,7 +691,7 @@ srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     const int b = tl / (tiles_x * tiles_y), r = tl % (tiles_x * tiles_y), y0 = (r / tiles_x) * kFT_H, x0 = (r % tiles_x) * kFT_W;
     __syncthreads();
     // stage the halo tile: one 16-byte (8-channel) chunk per thread-iteration
-    for (int i = tid; i < kFPlaneH * kFPlaneW * 8; i += 256) {
+    for (int i = tid; i < kFPlaneH * kFPlaneW * 8; i += 512) {
       const int c8 = i & 7, px = (i >> 3) % kFPlaneW, py = (i >> 3) / kFPlaneW;
       const int gy = y0 + py - kFHalo, gx = x0 + px - kFHalo;
       uint4 u = make_uint4(0, 0, 0, 0);
@@ -594,43 +706,37 @@ srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     for (int n = 0; n < 3; ++n)
 #pragma unroll
       for (int p = 0; p < 4; ++p) o[n][p] = 0.f;
-    for (int c2 = grp * 16; c2 < grp * 16 + 16; ++c2) {
-      float a0[4], a1[4];
+    for (int c2 = grp * 8; c2 < grp * 8 + 8; ++c2) {
+      float2 acc2[4];
       const float b0 = dwb ? dwb[2 * c2] : 0.f, b1 = dwb ? dwb[2 * c2 + 1] : 0.f;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) { a0[p] = b0; a1[p] = b1; }
+      for (int p = 0; p < 4; ++p) acc2[p] = make_float2(b0, b1);
       const uint32_t* pl = tile + c2 * kFPlane + ty * kFPlaneW + tx;
       const float2* wp = reinterpret_cast<const float2*>(wsm) + c2 * 81;
 #pragma unroll
       for (int ky = 0; ky < 9; ++ky) {
-        float v0[12], v1[12];
+        float2 v[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
-          const float2 f = unpack_bf16(pl[ky * kFPlaneW + i]);
-          v0[i] = f.x; v1[i] = f.y;
-        }
+        for (int i = 0; i < 12; ++i) v[i] = unpack_bf16(pl[ky * kFPlaneW + i]);
 #pragma unroll
         for (int kx = 0; kx < 9; ++kx) {
           const float2 wv = wp[ky * 9 + kx];
 #pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            a0[p] = fmaf(v0[p + kx], wv.x, a0[p]);
-            a1[p] = fmaf(v1[p + kx], wv.y, a1[p]);
-          }
+          for (int p = 0; p < 4; ++p) acc2[p] = ffma2(v[p + kx], wv, acc2[p]);
         }
       }
 #pragma unroll
       for (int n = 0; n < 3; ++n) {
         const float w0 = pw[n * 64 + 2 * c2], w1 = pw[n * 64 + 2 * c2 + 1];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) o[n][p] = fmaf(a0[p], w0, fmaf(a1[p], w1, o[n][p]));
+        for (int p = 0; p < 4; ++p) o[n][p] = fmaf(acc2[p].x, w0, fmaf(acc2[p].y, w1, o[n][p]));
       }
     }
-    if (grp == 1) {
+    if (grp > 0) {
 #pragma unroll
       for (int n = 0; n < 3; ++n)
 #pragma unroll
-        for (int p = 0; p < 4; ++p) red[t * 12 + n * 4 + p] = o[n][p];
+        for (int p = 0; p < 4; ++p) red[((grp - 1) * 128 + t) * 12 + n * 4 + p] = o[n][p];
     }
     __syncthreads();
     if (grp == 0) {
@@ -642,7 +748,8 @@ srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
         for (int p = 0; p < 4; ++p) {
           const int gx = x0 + tx + p;
           if (gy < H && gx < W) {
-            const float v = o[n][p] + red[t * 12 + n * 4 + p] + (pwb ? pwb[n] : 0.f);
+            const float v = o[n][p] + red[t * 12 + n * 4 + p] + red[(128 + t) * 12 + n * 4 + p] + red[(256 + t) * 12 + n * 4 + p] +
+                            (pwb ? pwb[n] : 0.f);
             y[(static_cast<size_t>(b) * 3 + n) * plane + static_cast<size_t>(gy) * W + gx] = (tanhf(v) + 1.f) * 0.5f;
           }
         }
@@ -659,7 +766,7 @@ __global__ void gather_stride_kernel(const float* src, float* dst, int n, int mu
 
 int srgan_final(const __nv_bfloat16* x, const float* dw, const float* dwb, const float* pw, const float* pwb, float* y, int B,
                 int H, int W, int ldx, cudaStream_t st) {
-  const size_t smem = (32 * kFPlane) * 4 + 32 * 81 * 2 * 4 + 128 * 12 * 4;
+  const size_t smem = (32 * kFPlane) * 4 + 32 * 81 * 2 * 4 + 3 * 128 * 12 * 4;
   static bool attr = false;
   if (!attr) {
     WC_CHECK_CUDA(cudaFuncSetAttribute(srgan_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -667,7 +774,7 @@ int srgan_final(const __nv_bfloat16* x, const float* dw, const float* dwb, const
   }
   const int tiles = B * ((W + kFT_W - 1) / kFT_W) * ((H + kFT_H - 1) / kFT_H);
   ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * H * W * (128.0 + 12.0));
-  srgan_final_kernel<<<std::min(tiles, num_sms()), 256, smem, st>>>(x, dw, dwb, pw, pwb, y, B, H, W, ldx);
+  srgan_final_kernel<<<std::min(tiles, num_sms()), 512, smem, st>>>(x, dw, dwb, pw, pwb, y, B, H, W, ldx);
   WC_LAUNCH_CHECK();
   return 0;
 }

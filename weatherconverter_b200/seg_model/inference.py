@@ -32,13 +32,13 @@ def load_model(model_path, model_config) -> torch.nn.Module:
     return model
 
 
-def infer_batch(model, input_tensor, encoded_label_tensor, want_grad=True):
+def infer_batch(model, input_tensor, encoded_label_tensor, want_grad=True, grad_pool=1):
     """Batched, stream-ordered: returns dict(pred int64 [B,H,W], grad [B,3,H,W], loss [B]); image b's loss is the CE
     mean over its own valid pixels, i.e. a vmap of the reference's B = 1 call."""
     labels = encoded_label_tensor
     if labels.dim() == 4:
         labels = labels.squeeze(1)
-    return model.infer(input_tensor, labels, want_grad=want_grad)
+    return model.infer(input_tensor, labels, want_grad=want_grad, grad_pool=grad_pool)
 
 
 def infer(model, input_tensor, encoded_label_tensor, verbose=False):

@@ -137,9 +137,10 @@ class DeepLabV3(nn.Module):
             self._ws = {k: torch.empty(nbytes, dtype=torch.uint8, device=device)}
         return self._ws[k]
 
-    def infer(self, x, labels, want_grad=True, want_logits=False):
+    def infer(self, x, labels, want_grad=True, want_logits=False, grad_pool=1):
         """Forward + argmax + per-image CE(ignore 255) + input gradient in one stream-ordered plan.
-        Returns dict(pred int64 [B,H,W], grad fp32 [B,3,H,W] | None, loss [B], logits | None)."""
+        Returns dict(pred int64 [B,H,W], grad fp32 [B,3,H/grad_pool,W/grad_pool] | None, loss [B], logits | None).
+        grad_pool > 1 returns F.avg_pool2d(grad, grad_pool) computed by a fused stem kernel (sgg/sgg.py:18)."""
         _lib.require_cuda(x, labels)
         if self.training:
             raise RuntimeError("the B200 DeepLabV3+ path implements eval-mode BatchNorm only; call .eval()")
@@ -149,11 +150,11 @@ class DeepLabV3(nn.Module):
         self._ensure(x.device)
         ws = self._workspace(B, H, W, want_grad, x.device)
         pred = torch.empty(B, H, W, dtype=torch.long, device=x.device)
-        grad = torch.empty_like(x) if want_grad else None
+        grad = torch.empty(B, 3, H // grad_pool, W // grad_pool, device=x.device) if want_grad else None
         loss = torch.empty(B, dtype=torch.float32, device=x.device)
         logits = torch.empty(B, self.num_classes, H, W, device=x.device) if want_logits else None
-        check(lib().wc_seg_infer(self._handle, ptr(x), ptr(labels), ptr(pred), ptr(grad), ptr(loss), ptr(logits), B, H, W,
-                                 ptr(ws), ws.numel(), stream_ptr()))
+        check(lib().wc_seg_infer_pooled(self._handle, ptr(x), ptr(labels), ptr(pred), ptr(grad), ptr(loss), ptr(logits), B, H, W,
+                                        int(grad_pool), ptr(ws), ws.numel(), stream_ptr()))
         self._last = (x, labels)
         return dict(pred=pred, grad=grad, loss=loss, logits=logits)
 

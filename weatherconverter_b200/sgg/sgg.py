@@ -13,17 +13,19 @@ from .._lib import check, lib, ptr, stream_ptr
 from ..seg_model.inference import infer_batch
 
 
-def apply_gsg_batch(seg_model, mu, sigma, sr_xt, gt, _lambda, pool=None, return_aux=False):
+def apply_gsg_batch(seg_model, mu, sigma, sr_xt, gt, _lambda, pool=None, return_aux=False, fused_pool=True):
     """Batched GSG: every image uses its own loss/gradient (vmap of the reference's B = 1 semantics)."""
     _lib.require_cuda(mu, sigma, sr_xt, gt)
-    out = infer_batch(seg_model, sr_xt, gt)
     B, _, h, w = mu.shape
     if pool is None:
         pool = sr_xt.shape[-1] // w
+    # avg_pool2d(grad, pool) (sgg.py:18) is folded into the segmentor's stem data-gradient kernel when possible
+    fused = fused_pool and pool in (2, 4, 6, 8)
+    out = infer_batch(seg_model, sr_xt, gt, grad_pool=pool if fused else 1)
     mu, sigma = mu.contiguous().float(), sigma.contiguous().float()
     xt = torch.empty_like(mu)
-    check(lib().wc_sgg_update(ptr(out["grad"]), ptr(mu), ptr(sigma), ptr(xt), None, B, h, w, pool, float(_lambda),
-                              stream_ptr()))
+    check(lib().wc_sgg_update(ptr(out["grad"]), ptr(mu), ptr(sigma), ptr(xt), None, B, h, w, 1 if fused else pool,
+                              float(_lambda), stream_ptr()))
     return (xt, out) if return_aux else xt
 
 
