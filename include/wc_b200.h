@@ -35,6 +35,9 @@ long long wc_launch_count(void);
  * launch counts and algorithmic work (FLOPs for classes 0-1, bytes for 2-4). */
 void wc_profile_begin(void);
 int wc_profile_end(double* ms_by_class, long long* count_by_class, double* work_by_class);
+/* Per-launch records of the current profiling window (call BEFORE wc_profile_end): class, milliseconds, work and six
+ * shape integers (igemm: pixels, N, K, N-tile, taps, grid).  Returns the number of records (may exceed cap). */
+int wc_profile_detail(int cap, int* cls, double* ms, double* work, int* info);
 
 /* ---- DDPM scheduler (diffusion_model/scheduler/linear_noise_scheduler.py) ------------------------------ */
 /* :79-116 sample_prev_timestep + sample_ddpm.py:44.  mean = (xt - beta*eps/s)/sqrt_alpha ; out = mean + sigma*z.

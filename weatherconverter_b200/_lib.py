@@ -35,6 +35,7 @@ _SIGS = {
     "wc_abi_version": (C.c_int, []),
     "wc_launch_count": (C.c_longlong, []),
     "wc_profile_begin": (None, []),
+    "wc_profile_detail": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "wc_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     "wc_ddpm_step": (C.c_int, [c_ptr] * 6 + [C.c_size_t, C.c_int] + [C.c_float] * 4 + [c_ptr]),
     "wc_ddpm_step_batched": (C.c_int, [c_ptr] * 6 + [C.c_size_t, C.c_int] + [c_ptr] * 4 + [c_ptr]),

@@ -7,7 +7,7 @@ namespace wc {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two groups of 4, one per TMEM lane quadrant)
 constexpr uint32_t kABytes = kIgemmBM * kIgemmBK * 2;  // 16 KiB
 constexpr uint32_t kBBytesMax = 256 * kIgemmBK * 2;    // 32 KiB
 constexpr uint32_t kStageBytes = kABytes + kBBytesMax;
@@ -20,16 +20,39 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NC]) {
   else tmem_ld16(taddr, r);
 }
 
+// Epilogue of one accumulator tile for one thread (= one output pixel row of the tile).  `grp` in {0,1}: the two
+// epilogue warpgroups interleave the N chunks.  Residual / ReLU-mask rows are prefetched one chunk ahead so their global
+// latency overlaps the TMEM load and the math of the current chunk.
 template <int NC>
 __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc, int n0, int b, int y, int x,
-                                              bool valid) {
+                                              bool valid, int grp) {
+  constexpr int NV = NC / 8;
   const int oy = y * p.sy + p.py, ox = x * p.sx + p.px;
   const size_t opix = (static_cast<size_t>(b) * p.Ho + oy) * p.Wo + ox;
-  for (int c0 = 0; c0 < p.BN; c0 += NC) {
+  const uint4* res_row = p.res ? reinterpret_cast<const uint4*>(p.res + opix * p.ldr) : nullptr;
+  const uint4* mask_row = p.mask ? reinterpret_cast<const uint4*>(p.mask + opix * p.ldm) : nullptr;
+  uint4 res_nxt[NV], mask_nxt[NV];
+  auto prefetch = [&](int nb) {
+    if (!valid || nb >= p.N) return;
+    if (res_row) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) res_nxt[j] = __ldg(res_row + (nb >> 3) + j);
+    }
+    if (mask_row) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) mask_nxt[j] = __ldg(mask_row + (nb >> 3) + j);
+    }
+  };
+  prefetch(n0 + grp * NC);
+  for (int c0 = grp * NC; c0 < p.BN; c0 += 2 * NC) {
     const int nb = n0 + c0;
     if (nb >= p.N) break;  // warp-uniform
     uint32_t r[NC];
     tmem_ld_n<NC>(tacc + c0, r);
+    uint4 res_cur[NV], mask_cur[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) { res_cur[j] = res_nxt[j]; mask_cur[j] = mask_nxt[j]; }
+    if (c0 + 2 * NC < p.BN) prefetch(nb + 2 * NC);
     tmem_wait_ld();
     if (!valid) continue;
     float v[NC];
@@ -51,10 +74,9 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
       }
     }
     if (p.res) {
-      const uint4* rp = reinterpret_cast<const uint4*>(p.res + opix * p.ldr + nb);
 #pragma unroll
-      for (int j = 0; j < NC / 8; ++j) {
-        uint4 u = __ldg(rp + j);
+      for (int j = 0; j < NV; ++j) {
+        const uint4 u = res_cur[j];
         float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
         v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
         v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
@@ -73,10 +95,9 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
       }
     }
     if (p.mask) {
-      const uint4* mp = reinterpret_cast<const uint4*>(p.mask + opix * p.ldm + nb);
 #pragma unroll
-      for (int j = 0; j < NC / 8; ++j) {
-        uint4 u = __ldg(mp + j);
+      for (int j = 0; j < NV; ++j) {
+        const uint4 u = mask_cur[j];
         float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
         if (!(f0.x > 0.f)) v[8 * j + 0] = 0.f;
         if (!(f0.y > 0.f)) v[8 * j + 1] = 0.f;
@@ -91,7 +112,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
     if (p.out_mode == kOutNHWC) {
       uint4* op = reinterpret_cast<uint4*>(p.out + opix * p.ldc + nb);
 #pragma unroll
-      for (int j = 0; j < NC / 8; ++j) {
+      for (int j = 0; j < NV; ++j) {
         uint4 u;
         u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
         u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
@@ -114,7 +135,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
         __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + (bh * ntok + tok) * p.hd + d;
         uint4* op = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-        for (int j = 0; j < NC / 8; ++j) {
+        for (int j = 0; j < NV; ++j) {
           uint4 u;
           u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
           u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
@@ -164,7 +185,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), 128);
+        mbar_init(tempty_bar(a), 256);
       }
       fence_barrier_init();
     }
@@ -238,8 +259,9 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int grp = (warp - 2) >> 2;  // 0 or 1: which half of the interleaved N chunks
     const int row = quad * 32 + lane;
     const int bb = row / (p.th * p.tw), rem = row % (p.th * p.tw), yy = rem / p.tw, xx = rem % p.tw;
     int it = 0;
@@ -254,9 +276,9 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       tc_fence_after();
       const uint32_t tacc = tmem_base + static_cast<uint32_t>(a) * 256u + (static_cast<uint32_t>(quad * 32) << 16);
       if (p.out_mode != kOutQKV && (p.BN % 32 == 0) && (p.N % 32 == 0))
-        epilogue_tile<32>(p, tacc, n0, b, y, x, valid);
+        epilogue_tile<32>(p, tacc, n0, b, y, x, valid, grp);
       else
-        epilogue_tile<16>(p, tacc, n0, b, y, x, valid);
+        epilogue_tile<16>(p, tacc, n0, b, y, x, valid, grp);
       tc_fence_before();
       mbar_arrive(tempty_bar(a));
     }
@@ -278,6 +300,7 @@ int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
     attr_set = true;
   }
   ProfScope prof(kProfIgemm, stream, plan.flops);
+  prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.total_kb * kIgemmBK, plan.args.BN, plan.args.ntaps, plan.grid);
   igemm_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
   WC_LAUNCH_CHECK();
   return 0;

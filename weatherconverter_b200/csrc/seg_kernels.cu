@@ -222,38 +222,58 @@ __global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 __global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ m,
                                     __nv_bfloat16* __restrict__ dx, int B, int Hi, int Wi, int Ho, int Wo, int C,
                                     int ldy, int ldm, int ldx) {
-  const size_t total = static_cast<size_t>(B) * Hi * Wi * C;
+  const int c8n = C / 8;
+  const size_t total = static_cast<size_t>(B) * Hi * Wi * c8n;
   const float sy = static_cast<float>(Hi) / Ho, sx = static_cast<float>(Wi) / Wo;
   const int fy = (Ho + Hi - 1) / Hi, fx = (Wo + Wi - 1) / Wi;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    size_t p = i / C;
+    const int c8 = static_cast<int>(i % c8n);
+    size_t p = i / c8n;
     const int ix = static_cast<int>(p % Wi), iy = static_cast<int>((p / Wi) % Hi), b = static_cast<int>(p / (static_cast<size_t>(Wi) * Hi));
-    float acc = 0.f;
-    const bool live = !m || (__bfloat162float(m[p * ldm + c]) > 0.f);
-    if (live) {
-      const int oy_lo = max(0, fy * iy - fy - 1), oy_hi = min(Ho - 1, fy * iy + 2 * fy);
-      const int ox_lo = max(0, fx * ix - fx - 1), ox_hi = min(Wo - 1, fx * ix + 2 * fx);
-      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-        int y0, y1; float ly;
-        bilinear_src(oy, sy, Hi, y0, y1, ly);
-        float wy = 0.f;
-        if (y0 == iy) wy += 1.f - ly;
-        if (y1 == iy) wy += ly;
-        if (wy == 0.f) continue;
-        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-          int x0, x1; float lx;
-          bilinear_src(ox, sx, Wi, x0, x1, lx);
-          float wx = 0.f;
-          if (x0 == ix) wx += 1.f - lx;
-          if (x1 == ix) wx += lx;
-          if (wx == 0.f) continue;
-          acc += wy * wx * __bfloat162float(dy[((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * ldy + c]);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int oy_lo = max(0, fy * iy - fy - 1), oy_hi = min(Ho - 1, fy * iy + 2 * fy);
+    const int ox_lo = max(0, fx * ix - fx - 1), ox_hi = min(Wo - 1, fx * ix + 2 * fx);
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      int y0, y1; float ly;
+      bilinear_src(oy, sy, Hi, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        int x0, x1; float lx;
+        bilinear_src(ox, sx, Wi, x0, x1, lx);
+        float wx = 0.f;
+        if (x0 == ix) wx += 1.f - lx;
+        if (x1 == ix) wx += lx;
+        if (wx == 0.f) continue;
+        const float ww = wy * wx;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * ldy + c8 * 8));
+        const uint32_t* up = &u.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16(up[j]);
+          acc[2 * j] = fmaf(ww, f.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(ww, f.y, acc[2 * j + 1]);
         }
       }
     }
-    dx[p * ldx + c] = __float2bfloat16_rn(acc);
+    if (m) {
+      const uint4 mv = __ldg(reinterpret_cast<const uint4*>(m + p * ldm + c8 * 8));
+      const uint32_t* mp = &mv.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16(mp[j]);
+        if (!(f.x > 0.f)) acc[2 * j] = 0.f;
+        if (!(f.y > 0.f)) acc[2 * j + 1] = 0.f;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]); o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(dx + p * ldx + c8 * 8) = o;
   }
 }
 
@@ -591,7 +611,8 @@ int bilinear_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int Hi, int Wi
 int bilinear_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* mask, __nv_bfloat16* dx, int B, int Hi, int Wi, int Ho,
                  int Wo, int C, int ldy, int ldm, int ldx, cudaStream_t st) {
   ProfScope prof(kProfOther, st, 0);
-  bilinear_bwd_kernel<<<grid_for(static_cast<size_t>(B) * Hi * Wi * C), 256, 0, st>>>(dy, mask, dx, B, Hi, Wi, Ho, Wo, C, ldy, ldm, ldx);
+  WC_REQUIRE(C % 8 == 0 && ldy % 8 == 0 && ldx % 8 == 0, "bilinear_bwd: channels / strides must be multiples of 8");
+  bilinear_bwd_kernel<<<grid_for(static_cast<size_t>(B) * Hi * Wi * C / 8), 256, 0, st>>>(dy, mask, dx, B, Hi, Wi, Ho, Wo, C, ldy, ldm, ldx);
   WC_LAUNCH_CHECK();
   return 0;
 }

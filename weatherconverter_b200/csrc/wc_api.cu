@@ -24,6 +24,7 @@ int conv_small_cout(const __nv_bfloat16* x, const float* w, const float* bias, f
 int nchw_f32_to_nhwc_bf16(const float* x, __nv_bfloat16* y, int B, int C, int HW, int ldy, cudaStream_t st);
 int nhwc_bf16_to_nchw_f32(const __nv_bfloat16* x, float* y, int B, int C, int HW, int ldx, cudaStream_t st);
 void prof_start();
+int prof_detail(int cap, int* cls, double* ms, double* work, int* info);
 int prof_stop(double* ms, long long* count, double* work);
 int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                       int heads, int ntok, int hd, int ldo, cudaStream_t st);
@@ -53,6 +54,7 @@ const char* wc_last_error(void) { return last_error_cstr(); }
 int wc_abi_version(void) { return 1; }
 long long wc_launch_count(void) { return launch_count(); }
 void wc_profile_begin(void) { prof_start(); }
+int wc_profile_detail(int cap, int* cls, double* ms, double* work, int* info) { return prof_detail(cap, cls, ms, work, info); }
 int wc_profile_end(double* ms_by_class, long long* count_by_class, double* work_by_class) {
   return prof_stop(ms_by_class, count_by_class, work_by_class);
 }

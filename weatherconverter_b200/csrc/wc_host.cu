@@ -23,19 +23,39 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 namespace {
-struct ProfRec { int cls; cudaEvent_t a, b; double work; };
+struct ProfRec { int cls; cudaEvent_t a, b; double work; int info[6]; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 }  // namespace
 bool profiling_enabled() { return g_prof_on; }
 void prof_begin_launch(int cls, cudaStream_t st, double work) {
-  ProfRec r{cls, nullptr, nullptr, work};
+  ProfRec r{cls, nullptr, nullptr, work, {0, 0, 0, 0, 0, 0}};
   cudaEventCreate(&r.a);
   cudaEventCreate(&r.b);
   cudaEventRecord(r.a, st);
   g_prof.push_back(r);
 }
 void prof_end_launch(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
+void prof_annotate(int a, int b, int c, int d, int e, int f) {
+  if (g_prof.empty()) return;
+  int* p = g_prof.back().info;
+  p[0] = a; p[1] = b; p[2] = c; p[3] = d; p[4] = e; p[5] = f;
+}
+// Per-launch detail: fills up to `cap` records {cls, ms, work, info[6]}; returns the number of records available.
+int prof_detail(int cap, int* cls, double* ms, double* work, int* info) {
+  int n = 0;
+  for (auto& r : g_prof) {
+    if (n < cap) {
+      cudaEventSynchronize(r.b);
+      float t = 0;
+      cudaEventElapsedTime(&t, r.a, r.b);
+      cls[n] = r.cls; ms[n] = t; work[n] = r.work;
+      for (int i = 0; i < 6; ++i) info[n * 6 + i] = r.info[i];
+    }
+    ++n;
+  }
+  return n;
+}
 void prof_start() {
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_prof.clear();

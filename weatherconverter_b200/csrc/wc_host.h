@@ -38,12 +38,16 @@ enum ProfClass : int { kProfIgemm = 0, kProfAttention = 1, kProfGroupNorm = 2, k
                        kProfOther = 5, kProfNumClasses = 8 };
 bool profiling_enabled();
 void prof_begin_launch(int cls, cudaStream_t st, double work);
+void prof_annotate(int a, int b, int c, int d, int e, int f);  // shape info attached to the most recent launch record
 void prof_end_launch(cudaStream_t st);
 struct ProfScope {
   cudaStream_t st;
   bool on;
   ProfScope(int cls, cudaStream_t s, double work) : st(s), on(profiling_enabled()) {
     if (on) prof_begin_launch(cls, st, work);
+  }
+  void note(int a, int b = 0, int c = 0, int d = 0, int e = 0, int f = 0) const {
+    if (on) prof_annotate(a, b, c, d, e, f);
   }
   ~ProfScope() {
     if (on) prof_end_launch(st);
