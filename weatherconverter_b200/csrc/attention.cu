@@ -156,25 +156,34 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
       // ===================== MMA issuer =====================
       const uint32_t idesc_s = umma_idesc_bf16(128, BKV);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD);
+      // Descriptors: constant high words, low words advanced with 32-bit adds (the issuing lane's integer work is
+      // exposed latency between MMAs).
+      const uint64_t dq = umma_smem_desc(q_smem, Cfg::kSwz, 8 * Cfg::kRowBytes);
+      const uint64_t dp = umma_smem_desc(p_smem, 128, 1024);
+      const uint32_t hi_qk = umma_desc_hi(dq), hi_pv = umma_desc_hi(dp);
+      const uint32_t q_lo0 = umma_desc_lo(dq), k_lo0 = q_lo0 + ((k_smem - q_smem) >> 4);
+      const uint32_t p_lo0 = umma_desc_lo(dp), v_lo0 = p_lo0 - ((p_smem - v_smem) >> 4);
       auto issue_s = [&](int q, int j) {
-        const int s = j & 1;
         const uint32_t d = tmem_base + q * Cfg::kColsPerQ;
-        for (int kb = 0; kb < Cfg::kKBlocks; ++kb) {
-          const uint64_t ad = umma_smem_desc(q_smem + q * Cfg::kQTile + kb * (128 * Cfg::kRowBytes), Cfg::kSwz, 8 * Cfg::kRowBytes);
-          const uint64_t bd = umma_smem_desc(k_smem + s * Cfg::kKTile + kb * (BKV * Cfg::kRowBytes), Cfg::kSwz, 8 * Cfg::kRowBytes);
+        const uint32_t q_lo = q_lo0 + q * (Cfg::kQTile >> 4), k_lo = k_lo0 + (j & 1) * (Cfg::kKTile >> 4);
 #pragma unroll
-          for (int k = 0; k < Cfg::kKSteps; ++k) umma_bf16(d, ad + 2u * k, bd + 2u * k, idesc_s, (kb | k) != 0 ? 1u : 0u);
+        for (int kb = 0; kb < Cfg::kKBlocks; ++kb) {
+#pragma unroll
+          for (int k = 0; k < Cfg::kKSteps; ++k)
+            umma_bf16(d, umma_desc_join(q_lo + kb * ((128 * Cfg::kRowBytes) >> 4) + 2u * k, hi_qk),
+                      umma_desc_join(k_lo + kb * ((BKV * Cfg::kRowBytes) >> 4) + 2u * k, hi_qk), idesc_s, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(s_full(q));
       };
       auto issue_pv = [&](int q, int j) {
-        const int s = j & 1;
         const uint32_t d = tmem_base + q * Cfg::kColsPerQ + BKV;
-        for (int vb = 0; vb < BKV / 64; ++vb) {
-          const uint64_t ad = umma_smem_desc(p_smem + q * Cfg::kPTile + vb * (128 * 128), 128, 1024);
-          const uint64_t bd = umma_smem_desc(v_smem + s * Cfg::kVTile + vb * (HD * 128), 128, 1024);
+        const uint32_t p_lo = p_lo0 + q * (Cfg::kPTile >> 4), v_lo = v_lo0 + (j & 1) * (Cfg::kVTile >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(d, ad + 2u * k, bd + 2u * k, idesc_o, (j | vb | k) != 0 ? 1u : 0u);
+        for (int vb = 0; vb < BKV / 64; ++vb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d, umma_desc_join(p_lo + vb * ((128 * 128) >> 4) + 2u * k, hi_pv),
+                      umma_desc_join(v_lo + vb * ((HD * 128) >> 4) + 2u * k, hi_pv), idesc_o, (j | vb | k) != 0 ? 1u : 0u);
         }
         umma_commit(pv_done(q));
       };

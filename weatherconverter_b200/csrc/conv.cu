@@ -1,6 +1,7 @@
 #include "conv.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace wc {
 
@@ -23,6 +24,20 @@ void* DeviceArena::alloc(size_t bytes) {
 }
 
 namespace {
+
+int row3_mode() {  // 1: descriptors rely on address-based swizzling; 2 (WC_ROW3=2): explicit base_offset
+  const char* e = getenv("WC_ROW3");
+  return (e && e[0] == '2') ? 2 : 1;
+}
+
+bool row3_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WC_ROW3");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 struct TapDef {
   int map, dy, dx;
@@ -127,6 +142,7 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   op->plans.emplace_back();
   IgemmPlan& plan = op->plans.back();
   std::vector<TapDef> taps;
+  bool want_row3 = false;
   int B = x.B, H, W, tb, th, tw;
   if (g.stride == 1) {
     WC_REQUIRE(2 * g.pad == g.dil * (g.K - 1), "stride-1 convolutions must be 'same' sized");
@@ -144,6 +160,11 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
       nmaps = 2;
     }
     for (int i = nmaps; i < kMaxMaps; ++i) plan.maps.a[i] = plan.maps.a[0];
+    // Row-segment mode: 3x3 / dilation 1 on maps at least 128 pixels wide with narrow N (the L2->SM bound layers)
+    if (g.K == 3 && g.dil == 1 && tw == 128 && th == 1 && tb == 1 && N <= 128 && row3_enabled()) {
+      if (int e = igemm_make_rowseg_map(&plan.maps.a[2], x)) return e;
+      want_row3 = true;
+    }
   } else {
     WC_REQUIRE(g.stride == 2 && g.dil == 1 && !x2, "only stride 1 or 2 (undilated, unfused) supported");
     WC_REQUIRE(x.H % 2 == 0 && x.W % 2 == 0, "stride-2 convolution needs even input dims");
@@ -161,6 +182,10 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
       }
   }
   if (int e = finish_plan(&plan, arena, taps, B, H, W, tb, th, tw, N, ep, out, out.up, out.up, out.py, out.px, st)) return e;
+  plan.args.row3 = (want_row3 && plan.args.BN <= 128) ? row3_mode() : 0;
+  plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3);
+  { const char* e = getenv("WC_IGEMM_DBG"); plan.args.dbg = e ? atoi(e) : 0; }
+  { const char* e = getenv("WC_IGEMM_TRACE"); plan.args.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   op->flops = plan.flops;
   return 0;
 }
@@ -185,6 +210,7 @@ int build_conv_transposed_s2(ConvOp* op, DeviceArena* arena, const Act& x, const
       if (int e = igemm_make_amap(&plan.maps.a[0], x, tb, th, tw)) return e;
       for (int i = 1; i < kMaxMaps; ++i) plan.maps.a[i] = plan.maps.a[0];
       if (int e = finish_plan(&plan, arena, taps, x.B, x.H, x.W, tb, th, tw, N, ep, out, 2, 2, qy, qx, st)) return e;
+      plan.args.nstages = igemm_stages_for(plan.args.BN, 0);
       op->flops += plan.flops;
     }
   return 0;

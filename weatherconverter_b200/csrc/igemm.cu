@@ -9,10 +9,18 @@ namespace {
 
 constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two groups of 4, one per TMEM lane quadrant)
 constexpr uint32_t kABytes = kIgemmBM * kIgemmBK * 2;  // 16 KiB
-constexpr uint32_t kBBytesMax = 256 * kIgemmBK * 2;    // 32 KiB
-constexpr uint32_t kStageBytes = kABytes + kBBytesMax;
-constexpr uint32_t kSmemBytes = kIgemmStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kPipeBytes = 204800;  // shared-memory budget of the TMA ring (both modes), multiple of 1024
+constexpr int kMaxStages = 8;
+constexpr int kVecMaxN = 1024;  // bias / PReLU vectors up to this many channels are staged in shared memory
+constexpr uint32_t kVecBytes = 2 * kVecMaxN * 4;
+constexpr uint32_t kSmemBytes = kPipeBytes + 1024 /*align*/ + 256 /*barriers*/ + kVecBytes;
 constexpr uint32_t kTmemCols = 512;
+// Row-segment mode (3x3, stride 1, dilation 1, tiles of 128 pixels of ONE image row): per (channel block, ky) one TMA
+// box of 130 pixels [x0-1, x0+129) is loaded once and the three kx taps read it through UMMA descriptors whose start is
+// shifted by kx*128 bytes (base_offset = kx keeps the 128-byte swizzle phase right) -> A traffic / 3.
+constexpr uint32_t kRowSegPixels = 130;
+constexpr uint32_t kRowABytes = 18432;                       // 130*128 = 16640, padded to a multiple of 1024
+constexpr uint32_t kRowSmemBytes = kSmemBytes;
 
 template <int NC>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NC]) {
@@ -25,7 +33,8 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NC]) {
 // latency overlaps the TMEM load and the math of the current chunk.
 template <int NC>
 __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc, int n0, int b, int y, int x,
-                                              bool valid, int grp) {
+                                              bool valid, int grp, const float* s_bias, const float* s_prelu,
+                                              uint32_t tfull_addr, uint32_t tfull_parity) {
   constexpr int NV = NC / 8;
   const int oy = y * p.sy + p.py, ox = x * p.sx + p.px;
   const size_t opix = (static_cast<size_t>(b) * p.Ho + oy) * p.Wo + ox;
@@ -43,7 +52,9 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
       for (int j = 0; j < NV; ++j) mask_nxt[j] = __ldg(mask_row + (nb >> 3) + j);
     }
   };
-  prefetch(n0 + grp * NC);
+  prefetch(n0 + grp * NC);            // issued BEFORE waiting for the accumulator: overlaps the main loop's tail
+  mbar_wait(tfull_addr, tfull_parity);
+  tc_fence_after();
   for (int c0 = grp * NC; c0 < p.BN; c0 += 2 * NC) {
     const int nb = n0 + c0;
     if (nb >= p.N) break;  // warp-uniform
@@ -61,7 +72,8 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
     if (p.bias) {
 #pragma unroll
       for (int j = 0; j < NC; j += 4) {
-        float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+        const float4 bv = s_bias ? *reinterpret_cast<const float4*>(s_bias + nb + j)
+                                 : __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
         v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
       }
     }
@@ -89,7 +101,8 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
     if (p.prelu) {
 #pragma unroll
       for (int j = 0; j < NC; j += 4) {
-        float4 sv = __ldg(reinterpret_cast<const float4*>(p.prelu + nb + j));
+        const float4 sv = s_prelu ? *reinterpret_cast<const float4*>(s_prelu + nb + j)
+                                  : __ldg(reinterpret_cast<const float4*>(p.prelu + nb + j));
         v[j] = v[j] > 0.f ? v[j] : v[j] * sv.x; v[j + 1] = v[j + 1] > 0.f ? v[j + 1] : v[j + 1] * sv.y;
         v[j + 2] = v[j + 2] > 0.f ? v[j + 2] : v[j + 2] * sv.z; v[j + 3] = v[j + 3] > 0.f ? v[j + 3] : v[j + 3] * sv.w;
       }
@@ -109,6 +122,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
         if (!(f3.y > 0.f)) v[8 * j + 7] = 0.f;
       }
     }
+    if (p.dbg & 1) continue;
     if (p.out_mode == kOutNHWC) {
       uint4* op = reinterpret_cast<uint4*>(p.out + opix * p.ldc + nb);
 #pragma unroll
@@ -152,21 +166,38 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
   }
 }
 
+template <bool ROW3>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
+  // Pipeline depth is chosen per launch: narrow N tiles have small stages, so more of them fit and more bytes are in
+  // flight per SM (these layers are TMA-latency bound, not tensor bound).
+  constexpr uint32_t kAOff = ROW3 ? kRowABytes : kABytes;   // offset of the B tile(s) inside a stage
+  const int kStages = p.nstages;
+  const uint32_t kStageSz = kAOff + (ROW3 ? 3u : 1u) * static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kIgemmStages * kStageBytes;
+  const uint32_t bar_base = smem_base + kPipeBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kIgemmStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kIgemmStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kIgemmStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kIgemmStages + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // bias / PReLU vectors -> shared memory (read once per CTA instead of once per tile from L2)
+  float* s_vec = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+  const bool vec_in_smem = p.N <= kVecMaxN;
+  if (vec_in_smem) {
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+      if (p.bias) s_vec[i] = p.bias[i];
+      if (p.prelu) s_vec[kVecMaxN + i] = p.prelu[i];
+    }
+  }
+  const float* s_bias = (vec_in_smem && p.bias) ? s_vec : nullptr;
+  const float* s_prelu = (vec_in_smem && p.prelu) ? s_vec + kVecMaxN : nullptr;
 
   const int tiles_x = (p.W + p.tw - 1) / p.tw, tiles_y = (p.H + p.th - 1) / p.th, tiles_b = (p.B + p.tb - 1) / p.tb;
   const int m_tiles = tiles_x * tiles_y * tiles_b;
@@ -179,7 +210,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < kIgemmStages; ++s) {
+      for (int s = 0; s < kStages; ++s) {
         mbar_init(full_bar(s), 1);
         mbar_init(empty_bar(s), 1);
       }
@@ -197,6 +228,15 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // debug trace: role r in {0 producer, 1 mma, 2 epilogue warp 2 lane 0} appends (event id, clock) pairs
+  int trace_n = 0;
+  auto trace = [&](int role, int ev) {
+    if (p.trace && blockIdx.x == 0 && trace_n < 2000) {
+      p.trace[(role * 2000 + trace_n) * 2] = ev;
+      p.trace[(role * 2000 + trace_n) * 2 + 1] = clock64();
+      ++trace_n;
+    }
+  };
 
   auto decode = [&](int tile, int& n0, int& b0, int& y0, int& x0) {
     const int nt = tile % n_tiles, mt = tile / n_tiles;
@@ -216,16 +256,36 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         int n0, b0, y0, x0;
         decode(tile, n0, b0, y0, x0);
         int kb_global = 0;
-        for (int t = 0; t < p.ntaps; ++t) {
+        int t_first = 0;
+        if (ROW3) {
+          // taps 0..8 are the 3x3 window (ky-major) over map 0, all with nkb = p.taps[0].nkb channel blocks
+          const int nkb = p.taps[0].nkb;
+          const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
+          for (int ky = 0; ky < 3; ++ky)
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              trace(0, 1);
+              const uint32_t sa = smem_base + stage * kStageSz;
+              mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0u : kRowSegPixels * 128u) + ((p.dbg & 4) ? 0u : 3u * b_bytes));
+              if (!(p.dbg & 8)) tma_load_4d(sa, &maps.a[2], full_bar(stage), kb * kIgemmBK, x0 - 1, y0 + ky - 1, b0);
+              for (int kx = 0; kx < 3 && !(p.dbg & 4); ++kx)
+                tma_load_2d(sa + kAOff + kx * b_bytes, &maps.b, full_bar(stage), ((ky * 3 + kx) * nkb + kb) * kIgemmBK, n0);
+              trace(0, 2);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+          t_first = 9;
+          kb_global = 9 * nkb;
+        }
+        for (int t = t_first; t < p.ntaps; ++t) {
           const IgemmTap tap = p.taps[t];
           const CUtensorMap* amap = &maps.a[tap.map];
           for (int kb = 0; kb < tap.nkb; ++kb, ++kb_global) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage * kStageBytes;
+            const uint32_t sa = smem_base + stage * kStageSz;
             mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
             tma_load_4d(sa, amap, full_bar(stage), kb * kIgemmBK, x0 + tap.dx, y0 + tap.dy, b0);
-            tma_load_2d(sa + kABytes, &maps.b, full_bar(stage), kb_global * kIgemmBK, n0);
-            if (++stage == kIgemmStages) { stage = 0; phase ^= 1u; }
+            tma_load_2d(sa + kAOff, &maps.b, full_bar(stage), kb_global * kIgemmBK, n0);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -234,6 +294,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     if (lane == 0) {
       // ===================== MMA issuer =====================
       const uint32_t idesc = umma_idesc_bf16(kIgemmBM, static_cast<uint32_t>(p.BN));
+      // descriptor pieces (see umma_desc_join): constant high word, low words for stage 0, per-stage increment
+      const uint64_t d0 = umma_smem_desc(smem_base, 128, 1024);
+      const uint32_t dhi = umma_desc_hi(d0), a_lo0 = umma_desc_lo(d0), b_lo0 = a_lo0 + (kAOff >> 4);
+      const uint32_t stage16 = kStageSz >> 4, bt16 = (static_cast<uint32_t>(p.BN) * kIgemmBK * 2) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -241,21 +305,44 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         const int a = it & 1;
         const uint32_t aphase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(a), aphase ^ 1u);
+        trace(1, 10);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a) * 256u;
-        for (int ks = 0; ks < p.total_kb; ++ks) {
+        int ks_first = 0;
+        if (ROW3) {
+          const int nseg = 3 * p.taps[0].nkb;
+          for (int sg = 0; sg < nseg; ++sg) {
+            mbar_wait(full_bar(stage), phase);
+            trace(1, 11);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + stage * stage16, b_lo = b_lo0 + stage * stage16;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              // window of 128 pixels starting kx pixels (kx*128 B = 8 descriptor units) into the 130-pixel segment; the
+              // UMMA swizzle is a function of the absolute shared-memory address, so the shifted start needs no fix-up
+#pragma unroll
+              for (int k = 0; k < kIgemmBK / 16; ++k)
+                umma_bf16(d_tmem, umma_desc_join(a_lo + 8u * kx + 2u * k, dhi), umma_desc_join(b_lo + kx * bt16 + 2u * k, dhi), idesc,
+                          (sg | kx | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));
+            trace(1, 12);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          ks_first = 9 * p.taps[0].nkb;
+        }
+        for (int ks = ks_first; ks < p.total_kb; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * kStageBytes;
-          const uint64_t adesc = umma_smem_desc(sa, 128, 1024);
-          const uint64_t bdesc = umma_smem_desc(sa + kABytes, 128, 1024);
+          const uint32_t a_lo = a_lo0 + stage * stage16, b_lo = b_lo0 + stage * stage16;
 #pragma unroll
           for (int k = 0; k < kIgemmBK / 16; ++k)
-            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (ks | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, umma_desc_join(a_lo + 2u * k, dhi), umma_desc_join(b_lo + 2u * k, dhi), idesc, (ks | k) != 0 ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (++stage == kIgemmStages) { stage = 0; phase ^= 1u; }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(a));
+        trace(1, 13);
       }
     }
   } else {
@@ -272,15 +359,15 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       decode(tile, n0, b0, y0, x0);
       const int b = b0 + bb, y = y0 + yy, x = x0 + xx;
       const bool valid = (b < p.B) && (y < p.H) && (x < p.W);
-      mbar_wait(tfull_bar(a), aphase);
-      tc_fence_after();
       const uint32_t tacc = tmem_base + static_cast<uint32_t>(a) * 256u + (static_cast<uint32_t>(quad * 32) << 16);
+      if (warp == 2 && lane == 0) trace(2, 20);
       if (p.out_mode != kOutQKV && (p.BN % 32 == 0) && (p.N % 32 == 0))
-        epilogue_tile<32>(p, tacc, n0, b, y, x, valid, grp);
+        epilogue_tile<32>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase);
       else
-        epilogue_tile<16>(p, tacc, n0, b, y, x, valid, grp);
+        epilogue_tile<16>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase);
       tc_fence_before();
       mbar_arrive(tempty_bar(a));
+      if (warp == 2 && lane == 0) trace(2, 22);
     }
   }
   tc_fence_before();
@@ -293,15 +380,26 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
 
 }  // namespace
 
+int igemm_stages_for(int BN, int row3) {
+  const uint32_t stage = (row3 ? kRowABytes : kABytes) + (row3 ? 3u : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2;
+  // stages must stay 1024-byte aligned: BN is a multiple of 16 -> BN*128 is a multiple of 2048
+  int n = static_cast<int>(kPipeBytes / stage);
+  return n > kMaxStages ? kMaxStages : n;
+}
+
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
     attr_set = true;
   }
   ProfScope prof(kProfIgemm, stream, plan.flops);
-  prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.total_kb * kIgemmBK, plan.args.BN, plan.args.ntaps, plan.grid);
-  igemm_kernel<<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
+  prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.total_kb * kIgemmBK, plan.args.BN, plan.args.ntaps + 100 * plan.args.row3, plan.grid);
+  if (plan.args.row3)
+    igemm_kernel<true><<<plan.grid, kThreads, kRowSmemBytes, stream>>>(plan.maps, plan.args);
+  else
+    igemm_kernel<false><<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -354,6 +452,15 @@ int igemm_make_amap(CUtensorMap* out, const Act& act, int tb, int th, int tw, in
   uint32_t box[4] = {static_cast<uint32_t>(kIgemmBK), static_cast<uint32_t>(tw), static_cast<uint32_t>(th),
                      static_cast<uint32_t>(tb)};
   return encode_tmap_bf16(out, base, 4, dims, strides, box, 128);
+}
+
+int igemm_make_rowseg_map(CUtensorMap* out, const Act& act) {
+  uint64_t dims[4] = {static_cast<uint64_t>(act.C), static_cast<uint64_t>(act.W), static_cast<uint64_t>(act.H),
+                      static_cast<uint64_t>(act.B)};
+  uint64_t strides[4] = {1, static_cast<uint64_t>(act.ld), static_cast<uint64_t>(act.ld) * act.W,
+                         static_cast<uint64_t>(act.ld) * act.W * act.H};
+  uint32_t box[4] = {static_cast<uint32_t>(kIgemmBK), kRowSegPixels, 1, 1};
+  return encode_tmap_bf16(out, act.ptr, 4, dims, strides, box, 128);
 }
 
 int igemm_make_bmap(CUtensorMap* out, const __nv_bfloat16* wpacked, int n_rows, int ktotal, int BN) {

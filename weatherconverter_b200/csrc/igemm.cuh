@@ -37,6 +37,10 @@ struct IgemmArgs {
   int tb, th, tw;  // tile shape, tb*th*tw == 128
   int N, BN;       // true output channels (multiple of 16) and N tile
   int ntaps, total_kb;
+  long long* trace;  // debug: CTA 0 writes (event, clock) pairs here (WC_IGEMM_TRACE), else nullptr
+  int dbg;      // debug/experiment bits (WC_IGEMM_DBG): 1 skip epilogue global stores, 2 skip MMA issue, 4 skip B loads
+  int nstages;  // depth of the TMA ring (set by igemm_stages_for)
+  int row3;  // 1: taps 0..8 form a 3x3 stride-1 window executed in row-segment mode (see igemm.cu)
   IgemmTap taps[kMaxTaps];
   // epilogue
   const float* bias;     // [N] or nullptr
@@ -70,6 +74,7 @@ struct IgemmPlan {
 };
 
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
+int igemm_stages_for(int BN, int row3);
 
 // Choose the M-tile shape for a (B,H,W) grid: widest power-of-two span of x, then y, then b.
 void igemm_pick_tile(int B, int H, int W, int* tb, int* th, int* tw);
@@ -79,6 +84,8 @@ int igemm_pick_bn(int N, long m_tiles);
 // stride-2 convolutions): element (b, y, x, c) of the view = act(b, y*ys + y0, x*xs + x0, c), view dims Hv x Wv.
 int igemm_make_amap(CUtensorMap* out, const Act& act, int tb, int th, int tw, int y0 = 0, int ys = 1, int x0 = 0,
                     int xs = 1, int Hv = -1, int Wv = -1);
+// Row-segment A map (box 64 ch x 130 pixels of one image row) for the row3 mode.
+int igemm_make_rowseg_map(CUtensorMap* out, const Act& act);
 int igemm_make_bmap(CUtensorMap* out, const __nv_bfloat16* wpacked, int n_rows, int ktotal, int BN);
 
 }  // namespace wc

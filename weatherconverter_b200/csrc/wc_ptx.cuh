@@ -131,16 +131,27 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
 // Shared-memory matrix descriptor, K-major operand whose rows are `swizzle_bytes` (32/64/128) wide and
 // stored densely (row pitch == swizzle_bytes), 8-row groups `sbo_bytes` apart.  Matches the layout a TMA
 // tile load with the same swizzle mode produces.
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t swizzle_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t swizzle_bytes, uint32_t sbo_bytes,
+                                                   uint32_t base_offset = 0) {
   uint64_t layout = swizzle_bytes == 128 ? 2ull : (swizzle_bytes == 64 ? 4ull : 6ull);
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);             // start address, bits [0,14)
   d |= static_cast<uint64_t>(1) << 16;                            // LBO (unused for swizzled K-major) = 16 B
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;    // SBO, bits [32,46)
   d |= 1ull << 46;                                                // descriptor version 1 (Blackwell)
+  d |= static_cast<uint64_t>(base_offset & 7u) << 49;             // swizzle phase of a start address that is not 1024-B aligned
   d |= layout << 61;                                              // swizzle mode
   return d;
 }
+
+// The MMA-issuing thread is a single lane: every integer instruction it executes is exposed latency between two
+// tcgen05.mma issues.  So descriptors are split once into a constant high word and a low word whose start-address field
+// (bits [0,14), units of 16 bytes) is advanced with plain 32-bit adds.
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint64_t d) { return static_cast<uint32_t>(d); }
+__device__ __forceinline__ uint32_t umma_desc_hi(uint64_t d) { return static_cast<uint32_t>(d >> 32); }
 
 // TMEM -> registers: 32 lanes x 32-bit, N consecutive columns; thread i of the warp gets lane (base+i).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
