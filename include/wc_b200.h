@@ -94,7 +94,7 @@ int wc_bilinear(const wc_bf16* x, wc_bf16* y, int batch, int Hi, int Wi, int Ho,
 int wc_bilinear_bwd(const wc_bf16* dy, const wc_bf16* mask, wc_bf16* dx, int batch, int Hi, int Wi, int Ho, int Wo, int C,
                     void* stream);
 /* Loss head (network/utils.py:17 + inference.py:135-141): low-res logits nchw_f32 [B,19,h,w] -> full-res argmax,
- * per-image CE(ignore 255) and d loss / d logits, full-res (f32 [B,H,W,19]) and pulled back to low-res
+ * per-image CE(ignore 255) and d loss / d logits, full-res (f32 class planes [B,19,H,W]) and pulled back to low-res
  * (nhwc_bf16 [B,h,w,32], optional).  n_valid_ws: int[B] scratch. */
 int wc_seg_loss_head(const float* logits_lo, const int64_t* labels, int* n_valid_ws, int64_t* pred, float* dlogit_hi,
                      float* loss, float* logits_hi, wc_bf16* dlogit_lo, int batch, int h, int w, int H, int W, void* stream);

@@ -111,7 +111,7 @@ def test_loss_head():
     losses = torch.stack([F.cross_entropy(hi[b:b + 1], lab[b:b + 1], ignore_index=255) for b in range(B)])
     losses.sum().backward()
     pred = torch.empty(B, H, W, dtype=torch.long, device=dev)
-    dhi = torch.empty(B, H, W, 19, device=dev)
+    dhi = torch.empty(B, 19, H, W, device=dev)
     loss = torch.empty(B, device=dev)
     nv = torch.empty(B, dtype=torch.int32, device=dev)
     dlo = torch.empty(B, h, w, 32, device=dev, dtype=torch.bfloat16)

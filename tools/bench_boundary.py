@@ -42,7 +42,7 @@ timeit("bilinear fwd 16x32->64x128 x256", lambda: check(lib().wc_bilinear(ptr(a)
 da = torch.empty_like(a)
 timeit("bilinear bwd", lambda: check(lib().wc_bilinear_bwd(ptr(up), None, ptr(da), B, 16, 32, 64, 128, 256, stream_ptr())))
 lo = torch.randn(B, 19, 64, 128, device=dev); lab = torch.randint(0, 19, (B, 256, 512), device=dev)
-pred = torch.empty(B, 256, 512, dtype=torch.long, device=dev); dhi = torch.empty(B, 256, 512, 19, device=dev)
+pred = torch.empty(B, 256, 512, dtype=torch.long, device=dev); dhi = torch.empty(B, 19, 256, 512, device=dev)
 loss = torch.empty(B, device=dev); nv = torch.empty(B, dtype=torch.int32, device=dev); dlo = torch.empty(B, 64, 128, 32, device=dev, dtype=torch.bfloat16)
 timeit("loss head (fwd+adjoint)", lambda: check(lib().wc_seg_loss_head(ptr(lo), ptr(lab), ptr(nv), ptr(pred), ptr(dhi), ptr(loss), None, ptr(dlo), B, 64, 128, 256, 512, stream_ptr())))
 # srgan full forward

@@ -289,7 +289,7 @@ __global__ void count_valid_kernel(const long long* __restrict__ labels, int HW,
 }
 
 // One thread per full-resolution pixel: bilinear logits (from low-res NCHW fp32 planes), argmax -> pred,
-// softmax-CE: dlogit = (softmax - onehot) / n_valid[b] (0 where ignored) written as fp32 [B,H,W,NCP] (NCP >= NC);
+// softmax-CE: dlogit = (softmax - onehot) / n_valid[b] (0 where ignored) written as fp32 class planes [B,NC,H,W];
 // per-image loss accumulated with one atomic per warp.
 template <int NC>
 __global__ void seg_loss_grad_kernel(const float* __restrict__ logits_lo, const long long* __restrict__ labels,
@@ -331,17 +331,18 @@ __global__ void seg_loss_grad_kernel(const float* __restrict__ logits_lo, const 
         for (int c = 0; c < NC; ++c) logits_hi[(static_cast<size_t>(b) * NC + c) * pl_hi + static_cast<size_t>(oy) * W + ox] = v[c];
       }
       const long long lab = labels[i];
-      float* d = dlogit_hi + i * NC;
+      const size_t pl_hi2 = static_cast<size_t>(H) * W;
+      float* d = dlogit_hi + static_cast<size_t>(b) * NC * pl_hi2 + static_cast<size_t>(oy) * W + ox;   // class planes
       if (lab == ignore) {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) d[c] = 0.f;
+        for (int c = 0; c < NC; ++c) d[c * pl_hi2] = 0.f;
       } else {
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < NC; ++c) { v[c] = __expf(v[c] - mx); s += v[c]; }
         const float inv = 1.f / s, invn = 1.f / static_cast<float>(n_valid[b]);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) d[c] = (v[c] * inv - (c == lab ? 1.f : 0.f)) * invn;
+        for (int c = 0; c < NC; ++c) d[c * pl_hi2] = (v[c] * inv - (c == lab ? 1.f : 0.f)) * invn;
         lsum = -__logf(v[lab < NC && lab >= 0 ? lab : 0] * inv) * invn;
       }
     }
@@ -391,9 +392,10 @@ __global__ void logits_bilinear_bwd_kernel(const float* __restrict__ dhi, __nv_b
         if (x1 == ix) wx += lx;
         if (wx == 0.f) continue;
         const float ww = wy * wx;
-        const float* d = dhi + ((static_cast<size_t>(b) * H + oy) * W + ox) * NC;
+        const size_t plane = static_cast<size_t>(H) * W;
+        const float* d = dhi + static_cast<size_t>(b) * NC * plane + static_cast<size_t>(oy) * W + ox;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) acc[c] += ww * d[c];
+        for (int c = 0; c < NC; ++c) acc[c] += ww * __ldg(d + c * plane);
       }
     }
     __nv_bfloat16* o = dlo + i * ldo;
@@ -707,7 +709,8 @@ srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     const int j = i & 1, tap = (i >> 1) % 81, c2 = (i >> 1) / 81;
     wsm[i] = dw[(c2 * 2 + j) * 81 + tap];
   }
-  const int grp = tid >> 7, t = tid & 127, ty = t >> 4, tx = (t & 15) * 4;
+  // thread -> column tx (lanes sweep x: conflict-free shared-memory reads) and 4 vertically adjacent output rows
+  const int grp = tid >> 7, t = tid & 127, tx = t & 63, ty = (t >> 6) * 4;
   for (int tl = blockIdx.x; tl < B * tiles_x * tiles_y; tl += gridDim.x) {
     const int b = tl / (tiles_x * tiles_y), r = tl % (tiles_x * tiles_y), y0 = (r / tiles_x) * kFT_H, x0 = (r % tiles_x) * kFT_W;
     __syncthreads();
@@ -735,15 +738,18 @@ srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
       const uint32_t* pl = tile + c2 * kFPlane + ty * kFPlaneW + tx;
       const float2* wp = reinterpret_cast<const float2*>(wsm) + c2 * 81;
 #pragma unroll
-      for (int ky = 0; ky < 9; ++ky) {
-        float2 v[12];
+      for (int kx = 0; kx < 9; ++kx) {
+        float2 v[12];   // 12-row register window of column tx + kx (rows ty .. ty+11 of the halo tile)
 #pragma unroll
-        for (int i = 0; i < 12; ++i) v[i] = unpack_bf16(pl[ky * kFPlaneW + i]);
+        for (int i = 0; i < 12; ++i) {
+          const uint32_t u = pl[i * kFPlaneW + kx];
+          v[i] = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+        }
 #pragma unroll
-        for (int kx = 0; kx < 9; ++kx) {
+        for (int ky = 0; ky < 9; ++ky) {
           const float2 wv = wp[ky * 9 + kx];
 #pragma unroll
-          for (int p = 0; p < 4; ++p) acc2[p] = ffma2(v[p + kx], wv, acc2[p]);
+          for (int p = 0; p < 4; ++p) acc2[p] = ffma2(v[p + ky], wv, acc2[p]);
         }
       }
 #pragma unroll
@@ -761,13 +767,13 @@ srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
     }
     __syncthreads();
     if (grp == 0) {
-      const int gy = y0 + ty;
+      const int gx = x0 + tx;
       const size_t plane = static_cast<size_t>(H) * W;
 #pragma unroll
       for (int n = 0; n < 3; ++n)
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const int gx = x0 + tx + p;
+          const int gy = y0 + ty + p;
           if (gy < H && gx < W) {
             const float v = o[n][p] + red[t * 12 + n * 4 + p] + red[(128 + t) * 12 + n * 4 + p] + red[(256 + t) * 12 + n * 4 + p] +
                             (pwb ? pwb[n] : 0.f);
