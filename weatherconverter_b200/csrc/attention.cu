@@ -15,6 +15,7 @@
 #include "wc_host.h"
 #include "wc_ptx.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace wc {
@@ -47,7 +48,6 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
   return o;
 }
 
-constexpr int kPolyPerChunk = 14;  // of every 32 exponentials, this many run on the FMA pipe (must be even)
 
 struct AttnArgs {
   int ntok, heads, ldo;
@@ -76,7 +76,8 @@ struct AttnCfg {
   static constexpr uint32_t kTmemCols = NQ * kColsPerQ <= 256 ? 256 : 512;
 };
 
-template <int HD, int BKV, int NQ>
+// POLY: of every 32 exponentials, this many run on the FMA pipe (even)
+template <int HD, int BKV, int NQ, int POLY>
 __global__ void __launch_bounds__(AttnCfg<HD, BKV, NQ>::kThreads, 1)
 attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnArgs p) {
   using Cfg = AttnCfg<HD, BKV, NQ>;
@@ -94,9 +95,9 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
   auto v_full = [&](int s) { return bars + 8u * (5 + s); };
   auto v_empty = [&](int s) { return bars + 8u * (7 + s); };
   auto s_full = [&](int q) { return bars + 8u * (9 + q); };
-  auto p_full = [&](int q) { return bars + 8u * (11 + q); };
-  auto pv_done = [&](int q) { return bars + 8u * (13 + q); };
-  const uint32_t tmem_slot = bars + 8u * 15;
+  auto p_full = [&](int q) { return bars + 8u * (12 + q); };
+  auto pv_done = [&](int q) { return bars + 8u * (15 + q); };
+  const uint32_t tmem_slot = bars + 8u * 18;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -289,7 +290,7 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
         for (int i = 0; i < 32; i += 2) {
           const float2 xs = ffma2(make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sl2v, mnegv);
           float2 v;
-          if (i < kPolyPerChunk) {
+          if (i < POLY) {
             v = exp2_poly2(xs);
           } else {
             v.x = ex2_approx(xs.x);
@@ -358,8 +359,8 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
   }
 }
 
-template <int HD, int BKV, int NQ>
-int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
+template <int HD, int BKV, int NQ, int POLY>
+int launch_attention_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                      int heads, int ntok, int ldo, cudaStream_t st) {
   using Cfg = AttnCfg<HD, BKV, NQ>;
   AttnMaps maps;
@@ -384,15 +385,31 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
   args.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   static bool attr_set = false;
   if (!attr_set) {
-    WC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD, BKV, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    WC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD, BKV, NQ, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmem));
     attr_set = true;
   }
   dim3 grid((ntok + 128 * NQ - 1) / (128 * NQ), BH);
   ProfScope prof(kProfAttention, st, 4.0 * BH * static_cast<double>(ntok) * ntok * HD);
-  attention_kernel<HD, BKV, NQ><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
+  attention_kernel<HD, BKV, NQ, POLY><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
   WC_LAUNCH_CHECK();
   return 0;
+}
+
+template <int HD, int BKV, int NQ>
+int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
+                     int heads, int ntok, int ldo, cudaStream_t st) {
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("WC_ATTN_POLY");
+    poly = e ? atoi(e) : 14;
+  }
+  switch (poly) {   // tuning knob; 14 is the shipped setting
+    case 0: return launch_attention_p<HD, BKV, NQ, 0>(q, k, vt, out, B, heads, ntok, ldo, st);
+    case 8: return launch_attention_p<HD, BKV, NQ, 8>(q, k, vt, out, B, heads, ntok, ldo, st);
+    case 20: return launch_attention_p<HD, BKV, NQ, 20>(q, k, vt, out, B, heads, ntok, ldo, st);
+    default: return launch_attention_p<HD, BKV, NQ, 14>(q, k, vt, out, B, heads, ntok, ldo, st);
+  }
 }
 
 }  // namespace
@@ -403,8 +420,8 @@ int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv
   WC_REQUIRE(ntok % 8 == 0, "token count must be a multiple of 8");
   WC_REQUIRE(ldo % 8 == 0, "output row stride must be a multiple of 8");
   switch (hd) {
-    case 16: return launch_attention<16, 128, 2>(q, k, vt, out, B, heads, ntok, ldo, st);
-    case 32: return launch_attention<32, 128, 2>(q, k, vt, out, B, heads, ntok, ldo, st);
+    case 16: return launch_attention<16, 128, 3>(q, k, vt, out, B, heads, ntok, ldo, st);
+    case 32: return launch_attention<32, 128, 3>(q, k, vt, out, B, heads, ntok, ldo, st);
     case 64: return launch_attention<64, 128, 2>(q, k, vt, out, B, heads, ntok, ldo, st);
     case 128: return launch_attention<128, 64, 2>(q, k, vt, out, B, heads, ntok, ldo, st);
     case 192: return launch_attention<192, 64, 1>(q, k, vt, out, B, heads, ntok, ldo, st);
