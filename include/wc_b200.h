@@ -58,6 +58,15 @@ int wc_add_noise(const float* x0, const float* noise, float* out, size_t n_per_s
 int wc_sgg_update(const float* grad, const float* mu, const float* sigz, float* out, float* mag_out, int batch, int h,
                   int w, int pool, float lambda, void* stream);
 
+/* Local class guidance, sgg/sgg.py:27-60 (the shipped final sum raises; repaired as documented in DESIGN.md):
+ * prepare builds, for every image b and class c, x_masked[b*NC+c] = sr_xt[b]*(gt[b]==c) and gt_masked = gt[b]*(gt[b]==c)
+ * (sgg.py:41-45); after wc_seg_infer_pooled on that batch, combine evaluates
+ * xt = mu + lambda*sigz*sum_c avg_pool(gt==c)*|pooled_grad_c| + sigz.  pooled_grads f32 [B*NC,3,h,w]; gt int64 [B,pool*h,pool*w]. */
+int wc_lcg_prepare(const float* sr_xt, const int64_t* gt, float* x_masked, int64_t* gt_masked, int batch, int num_classes,
+                   int H, int W, void* stream);
+int wc_lcg_combine(const float* pooled_grads, const int64_t* gt, const float* mu, const float* sigz, float* out, int batch,
+                   int num_classes, int h, int w, int pool, float lambda, void* stream);
+
 /* ---- op-level building blocks (unit-test surface; the model-level calls below use the same kernels) ------ */
 /* nn.GroupNorm(8, C) [+ nn.SiLU] on NHWC bf16 (unet_base.py:89-90).  workspace >= wc_groupnorm_workspace_bytes. */
 size_t wc_groupnorm_workspace_bytes(int batch);

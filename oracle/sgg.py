@@ -35,6 +35,31 @@ def apply_gsg(seg_sd, mu, sigma, sr_xt, gt, lam, backbone="resnet50", pool=4):
     return torch.cat(outs), torch.cat(preds), torch.cat(grads)
 
 
+def apply_lcg(seg_sd, mu, sigma, sr_xt, gt, lam, backbone="resnet50", pool=4, num_classes=19):
+    """Repaired local class guidance (sgg/sgg.py:27-60; the shipped version raises).
+
+    Per class c (sgg.py:39-54, verbatim): mc = (gt == c); gradient of CE(seg(sr_xt * mc), gt * mc) w.r.t. the masked
+    input; avg_pool2d(4); float64 magnitude; xt_c = mu + lambda * sigma * mag_c + sigma.
+    Repair of the final masked sum (sgg.py:58 multiplies 128x128 tensors by 512x512 masks): the class masks are
+    average-pooled to the latent resolution, mc_lat = avg_pool2d(mc, pool), and pixels not covered by any class
+    (label 255) keep the unguided value:
+        xt = sum_c mc_lat_c * xt_c + (1 - sum_c mc_lat_c) * (mu + sigma) = mu + sigma + lambda * sigma * sum_c mc_lat_c * mag_c
+    Returns xt (fp32, like the repaired driver casts it)."""
+    outs = []
+    for b in range(mu.shape[0]):
+        acc = torch.zeros(mu.shape[2:], dtype=torch.float64)
+        for c in range(num_classes):
+            mc = (gt[b:b + 1] == c).long().unsqueeze(1)                              # sgg.py:41
+            x_m = sr_xt[b:b + 1] * mc                                                # sgg.py:44
+            gt_m = gt[b:b + 1] * mc.squeeze(1)                                       # sgg.py:45
+            _, g, _ = deeplab.infer(seg_sd, x_m, gt_m, backbone)                     # sgg.py:47
+            mag = compute_gradient_magnitude(F.avg_pool2d(g, pool, pool))            # sgg.py:49-50
+            mc_lat = F.avg_pool2d(mc.float(), pool, pool)[0, 0].double()
+            acc = acc + mc_lat * mag
+        outs.append(((mu[b:b + 1] + lam * sigma[b:b + 1] * acc) + sigma[b:b + 1]).float())
+    return torch.cat(outs)
+
+
 def sample_with_sgg(unet_sd, unet_cfg, sched, seg_sd, srgan_sd, x0, gt, noise, t_fwd, zs,
                     lam=60.0, n_steps=500, backbone="resnet50", guidance=True, record=None):
     """Repaired translation driver (translation.py:46-97 + SURVEY.md 8c repairs).

@@ -189,6 +189,19 @@ def g_gsg_and_driver(G):
     with contextlib.redirect_stdout(io.StringIO()):
         xt = apply_gsg(seg, mu, sig, sr.clone(), gt, 60.0)
     out["gsg"] = dict(mu=mu, sigma=sig, sr_xt=sr, gt=gt, lam=60.0, xt=xt)       # xt is float64 (D7)
+    # repaired LCG (sgg.py:27-60 per-class body verbatim through the reference's infer / compute_gradient_magnitude;
+    # final masked sum repaired as documented in oracle/sgg.py:apply_lcg)
+    import torch.nn.functional as F
+    acc = torch.zeros(h, w, dtype=torch.float64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        for c in range(19):
+            mc = (gt == c).long().unsqueeze(1)
+            xm = (sr * mc).clone()
+            gm = gt * mc.squeeze(0)
+            _, gr, _ = seg_infer.infer(seg, xm, gm)
+            mag = seg_infer.compute_gradient_magnitude(F.avg_pool2d(gr, 4, 4), denormalize=True, norm=False)
+            acc = acc + F.avg_pool2d(mc.float(), 4, 4)[0, 0].double() * mag
+    out["lcg"] = dict(mu=mu, sigma=sig, sr_xt=sr, gt=gt, lam=60.0, xt=((mu + 60.0 * sig * acc) + sig).float())
     # repaired driver
     cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = 64
     m = unet_for(cfg, 3455)

@@ -151,3 +151,17 @@ def test_apply_gsg_end_to_end(golden):
     print(f"apply_gsg: guidance-term rms-rel {rel:.3e}, total max-abs {float((xt - ref).abs().max()):.3e}")
     assert rel < 0.25
     assert (xt - ref).abs().max() < 1e-3
+
+
+def test_apply_lcg_vs_golden(golden):
+    """Repaired local class guidance: 19 masked passes batched through the plan vs the reference's per-class loop."""
+    from weatherconverter_b200.sgg.sgg import apply_lcg
+    dev = _dev()
+    d = golden("sgg.pt")["lcg"]
+    m = _seg("resnet50", 42, dev)
+    xt = apply_lcg(m, d["mu"].to(dev), d["sigma"].to(dev), d["sr_xt"].to(dev), d["gt"].to(dev), d["lam"]).cpu()
+    ref = d["xt"]
+    base = d["mu"] + d["sigma"]
+    rel = float(((xt - base) - (ref - base)).norm() / (ref - base).norm())
+    print(f"apply_lcg: guidance-term rms-rel {rel:.3e}, total max-abs {float((xt - ref).abs().max()):.3e}")
+    assert rel < 0.25 and (xt - ref).abs().max() < 1e-3

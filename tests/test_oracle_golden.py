@@ -83,6 +83,9 @@ def test_gsg_and_repaired_driver(golden):
     seg_sd = synth_state_dict(deeplab.deeplab_param_spec("resnet50"), 42)
     xt, _, _ = sgg.apply_gsg(seg_sd, d["mu"], d["sigma"], d["sr_xt"], d["gt"], d["lam"])
     assert (xt.double() - d["xt"]).abs().max() < 1e-5
+    d = g["lcg"]
+    xt = sgg.apply_lcg(seg_sd, d["mu"], d["sigma"], d["sr_xt"], d["gt"], d["lam"])
+    assert (xt - d["xt"]).abs().max() < 1e-5
     d = g["driver"]
     usd = synth_state_dict(unet.unet_param_spec(d["cfg"]), d["unet_seed"])
     gsd = synth_state_dict(srgan.srgan_param_spec(), d["srgan_seed"])

@@ -41,6 +41,8 @@ _SIGS = {
     "wc_ddpm_step_batched": (C.c_int, [c_ptr] * 6 + [C.c_size_t, C.c_int] + [c_ptr] * 4 + [c_ptr]),
     "wc_add_noise": (C.c_int, [c_ptr] * 3 + [C.c_size_t, C.c_int] + [c_ptr] * 3 + [c_ptr]),
     "wc_sgg_update": (C.c_int, [c_ptr] * 5 + [C.c_int] * 4 + [C.c_float, c_ptr]),
+    "wc_lcg_prepare": (C.c_int, [c_ptr] * 4 + [C.c_int] * 4 + [c_ptr]),
+    "wc_lcg_combine": (C.c_int, [c_ptr] * 5 + [C.c_int] * 5 + [C.c_float, c_ptr]),
     "wc_groupnorm_workspace_bytes": (C.c_size_t, [C.c_int]),
     "wc_groupnorm_silu": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_float, C.c_int, c_ptr, c_ptr]),
     "wc_conv2d": (C.c_int, [c_ptr] + [C.c_int] * 5 + [c_ptr, c_ptr] + [C.c_int] * 6 + [c_ptr, c_ptr, C.c_int, c_ptr,

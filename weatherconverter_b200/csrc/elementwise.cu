@@ -109,6 +109,58 @@ sgg_update_kernel(const float* __restrict__ grad, const float* __restrict__ mu, 
   }
 }
 
+// Local class guidance (sgg/sgg.py:39-58, repaired final sum):
+//   prepare: for class c, x_m[b*NC+c] = sr_xt[b] * (gt[b] == c), gt_m[b*NC+c] = (gt[b] == c) ? c : 0
+__global__ void __launch_bounds__(256)
+lcg_prepare_kernel(const float* __restrict__ sr, const long long* __restrict__ gt, float* __restrict__ xm,
+                   long long* __restrict__ gm, int B, int NC, size_t hw) {
+  const size_t total = static_cast<size_t>(B) * NC * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t p = i % hw;
+    const int c = static_cast<int>((i / hw) % NC), b = static_cast<int>(i / (hw * NC));
+    const bool on = gt[b * hw + p] == c;
+    gm[i] = on ? c : 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) xm[((static_cast<size_t>(b) * NC + c) * 3 + ch) * hw + p] = on ? sr[(static_cast<size_t>(b) * 3 + ch) * hw + p] : 0.f;
+  }
+}
+//   combine: xt = (mu + (lam*sigz) * sum_c avg_pool(gt == c) * |g4_c|) + sigz, g4 = pooled gradients [B*NC,3,h,w]
+__global__ void __launch_bounds__(256)
+lcg_combine_kernel(const float* __restrict__ g4, const long long* __restrict__ gt, const float* __restrict__ mu,
+                   const float* __restrict__ sigz, float* __restrict__ out, int B, int NC, int h, int w, int pool, float lam) {
+  const size_t hw = static_cast<size_t>(h) * w;
+  const double stdv[3] = {0.229, 0.224, 0.225};
+  const int Ws = w * pool;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < hw * B;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / hw), y = static_cast<int>((i % hw) / w), x = static_cast<int>(i % w);
+    int cnt[32];
+    for (int c = 0; c < NC; ++c) cnt[c] = 0;
+    for (int dy = 0; dy < pool; ++dy)
+      for (int dx = 0; dx < pool; ++dx) {
+        const long long l = gt[(static_cast<size_t>(b) * h * pool + y * pool + dy) * Ws + x * pool + dx];
+        if (l >= 0 && l < NC) ++cnt[l];
+      }
+    double acc = 0.0;
+    for (int c = 0; c < NC; ++c) {
+      if (!cnt[c]) continue;
+      double m2 = 0.0;
+      for (int ch = 0; ch < 3; ++ch) {
+        const double g = __dmul_rn(static_cast<double>(g4[((static_cast<size_t>(b) * NC + c) * 3 + ch) * hw + static_cast<size_t>(y) * w + x]), stdv[ch]);
+        m2 = __dadd_rn(m2, __dmul_rn(g, g));
+      }
+      const double frac = static_cast<double>(__fdiv_rn(static_cast<float>(cnt[c]), static_cast<float>(pool * pool)));
+      acc = __dadd_rn(acc, __dmul_rn(frac, sqrt(m2)));
+    }
+    for (int ch = 0; ch < 3; ++ch) {
+      const size_t o = (static_cast<size_t>(b) * 3 + ch) * hw + static_cast<size_t>(y) * w + x;
+      const double lam_s = static_cast<double>(__fmul_rn(lam, sigz[o]));
+      out[o] = static_cast<float>(__dadd_rn(__dadd_rn(static_cast<double>(mu[o]), __dmul_rn(lam_s, acc)), static_cast<double>(sigz[o])));
+    }
+  }
+}
+
 inline int grid_for(size_t n_items) {
   const size_t blocks = (n_items + 255) / 256;
   const size_t cap = static_cast<size_t>(num_sms()) * 8;
@@ -152,6 +204,20 @@ int add_noise(const float* x0, const float* noise, float* out, size_t n_per_samp
   add_noise_kernel<<<grid_for(n4 * B), 256, 0, st>>>(reinterpret_cast<const float4*>(x0),
                                                       reinterpret_cast<const float4*>(noise),
                                                       reinterpret_cast<float4*>(out), n4, B, sqrt_acp, sqrt_1m_acp, t);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+int lcg_prepare(const float* sr, const long long* gt, float* xm, long long* gm, int B, int NC, size_t hw, cudaStream_t st) {
+  WC_REQUIRE(NC <= 32, "at most 32 classes");
+  lcg_prepare_kernel<<<grid_for(static_cast<size_t>(B) * NC * hw), 256, 0, st>>>(sr, gt, xm, gm, B, NC, hw);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int lcg_combine(const float* g4, const long long* gt, const float* mu, const float* sigz, float* out, int B, int NC, int h,
+                int w, int pool, float lam, cudaStream_t st) {
+  WC_REQUIRE(NC <= 32, "at most 32 classes");
+  lcg_combine_kernel<<<grid_for(static_cast<size_t>(B) * h * w), 256, 0, st>>>(g4, gt, mu, sigz, out, B, NC, h, w, pool, lam);
   WC_LAUNCH_CHECK();
   return 0;
 }

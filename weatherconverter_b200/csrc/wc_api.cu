@@ -13,6 +13,9 @@ int add_noise(const float* x0, const float* noise, float* out, size_t n_per_samp
               const float* sqrt_1m_acp, const long long* t, cudaStream_t st);
 int sgg_update(const float* grad, const float* mu, const float* sigz, float* out, float* mag_out, int B, int h, int w,
                int pool, float lam, cudaStream_t st);
+int lcg_prepare(const float* sr, const long long* gt, float* xm, long long* gm, int B, int NC, size_t hw, cudaStream_t st);
+int lcg_combine(const float* g4, const long long* gt, const float* mu, const float* sigz, float* out, int B, int NC, int h,
+                int w, int pool, float lam, cudaStream_t st);
 int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, int ld, int ldy, const float* gamma,
                    const float* beta, float eps, int silu, void* workspace, cudaStream_t st);
 size_t groupnorm_workspace_bytes(int B);
@@ -79,6 +82,16 @@ int wc_add_noise(const float* x0, const float* noise, float* out, size_t n_per_s
 int wc_sgg_update(const float* grad, const float* mu, const float* sigz, float* out, float* mag_out, int batch, int h,
                   int w, int pool, float lambda, void* stream) {
   return sgg_update(grad, mu, sigz, out, mag_out, batch, h, w, pool, lambda, S(stream));
+}
+int wc_lcg_prepare(const float* sr_xt, const int64_t* gt, float* x_masked, int64_t* gt_masked, int batch, int num_classes,
+                   int H, int W, void* stream) {
+  return lcg_prepare(sr_xt, reinterpret_cast<const long long*>(gt), x_masked, reinterpret_cast<long long*>(gt_masked), batch,
+                     num_classes, static_cast<size_t>(H) * W, S(stream));
+}
+int wc_lcg_combine(const float* pooled_grads, const int64_t* gt, const float* mu, const float* sigz, float* out, int batch,
+                   int num_classes, int h, int w, int pool, float lambda, void* stream) {
+  return lcg_combine(pooled_grads, reinterpret_cast<const long long*>(gt), mu, sigz, out, batch, num_classes, h, w, pool, lambda,
+                     S(stream));
 }
 size_t wc_groupnorm_workspace_bytes(int batch) { return groupnorm_workspace_bytes(batch); }
 int wc_groupnorm_silu(const wc_bf16* x, wc_bf16* y, int batch, int hw, int channels, int ldx, int ldy,

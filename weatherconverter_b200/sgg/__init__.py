@@ -1,1 +1,1 @@
-from .sgg import apply_gsg, apply_gsg_batch  # noqa: F401
+from .sgg import apply_gsg, apply_gsg_batch, apply_lcg  # noqa: F401
