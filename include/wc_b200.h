@@ -117,6 +117,39 @@ int wc_nhwc_bf16_to_nchw_f32(const wc_bf16* x, float* y, int batch, int C, int h
 int wc_attention(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, int batch, int heads, int ntok,
                  int hd, int ldo, void* stream);
 
+/* ---- training-step building blocks (diffusion_model/train_ddpm.py:95-114: what loss.backward() and
+ * optimizer.step() compute; the model-level wc_unet_train_* calls below use the same kernels) ------------------ */
+/* wc_attention that also writes lse [B*heads][ntok] (log2-domain log-sum-exp of every softmax row). */
+int wc_attention_lse(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, float* lse, int batch, int heads,
+                     int ntok, int hd, int ldo, void* stream);
+/* Backward of the attention core: q,k,v [B,heads,ntok,hd]; o, d_o [B,ntok,heads*hd]; lse from wc_attention_lse;
+ * d_scratch fp32 [B*heads*ntok]; dqkv [B,ntok,3*heads*hd] receives dQ | dK | dV. */
+int wc_attention_bwd(const wc_bf16* q, const wc_bf16* k, const wc_bf16* v, const wc_bf16* o, const wc_bf16* d_o, const float* lse,
+                     float* d_scratch, wc_bf16* dqkv, int batch, int heads, int ntok, int hd, void* stream);
+/* Weight gradient of nn.Conv2d (dw [Cout,Cin,K,K]; optional fused 1x1 second input: dw2 [Cout,Cin2,1,1]) or of
+ * nn.ConvTranspose2d (transposed != 0, stride 2: dw [Cin,Cout,K,K]); x [B,H,W,Cin], dy on the output grid. */
+int wc_conv2d_wgrad(const wc_bf16* x, const wc_bf16* dy, int batch, int H, int W, int Cin, int Cout, int K, int stride, int pad,
+                    int dil, int transposed, const wc_bf16* x2, int Cin2, float* dw, float* dw2, void* stream);
+/* Backward of wc_groupnorm_silu: fwd_workspace is the workspace the forward call filled; dx = dGN(dy) (+add1) (+add2). */
+size_t wc_groupnorm_bwd_workspace_bytes(int batch, int channels);
+int wc_groupnorm_silu_bwd(const wc_bf16* x, const wc_bf16* dy, wc_bf16* dx, int batch, int hw, int channels, const float* gamma,
+                          const float* beta, float eps, int silu, const void* fwd_workspace, const wc_bf16* add1,
+                          const wc_bf16* add2, float* dgamma, float* dbeta, void* workspace, void* stream);
+/* Column sums of x [B,hw,C]: out_rows [B,C] (may be NULL), out_total [C] (may be NULL): bias / t-embedding gradients. */
+int wc_colsum(const wc_bf16* x, int batch, int hw, int channels, float* out_rows, float* out_total, void* workspace, void* stream);
+/* nn.MSELoss (train_ddpm.py:107): loss = mean((pred-target)^2), dpred = grad_scale * 2 (pred-target)/n. scratch: 8 KiB. */
+int wc_mse_loss_grad(const float* pred, const float* target, float* dpred, size_t n, float grad_scale, float* loss, void* scratch,
+                     void* stream);
+/* Weight + bias gradient of the 3-channel boundary convs.  sign +1: conv_in (wide = d(conv_in output) nhwc_bf16 64 ch,
+ * narrow = input image nchw_f32; dw [64,3,3,3], dbias [64]); sign -1: conv_out (wide = its input, narrow = dpred;
+ * dw [3,64,3,3], dbias [3]). */
+size_t wc_boundary_wgrad_scratch_bytes(void);
+int wc_boundary_wgrad(const wc_bf16* wide, const float* narrow, int batch, int H, int W, int sign, float* dw, float* dbias,
+                      void* scratch, void* stream);
+/* torch.optim.Adam step (train_ddpm.py:151,113) over flat fp32 buffers; g is multiplied by grad_scale first. */
+int wc_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, int step,
+                 float grad_scale, void* stream);
+
 /* ---- model-level: UNet (diffusion_model/models/unet_base.py:372-488) ------------------------------------- */
 typedef struct wc_unet wc_unet;
 typedef struct {

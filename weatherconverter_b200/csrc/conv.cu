@@ -122,7 +122,7 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
   } else if (out.mode == kOutNCHWf32) {
     a.out_f32 = out.out_f32; a.n_store = out.n_store;
   } else {
-    a.q = out.q; a.k = out.k; a.vt = out.vt; a.heads = out.heads; a.hd = out.hd; a.C = out.heads * out.hd;
+    a.q = out.q; a.k = out.k; a.vt = out.vt; a.v = out.v; a.heads = out.heads; a.hd = out.hd; a.C = out.heads * out.hd;
     WC_REQUIRE(N == 3 * a.C, "QKV epilogue needs N == 3*C");
     WC_REQUIRE((H * W) % 8 == 0, "token count must be a multiple of 8");
   }

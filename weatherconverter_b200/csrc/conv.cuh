@@ -50,7 +50,7 @@ struct OutSpec {
   Act out;  // kOutNHWC destination (full-resolution grid for transposed convs)
   float* out_f32 = nullptr;
   int n_store = 0;
-  __nv_bfloat16 *q = nullptr, *k = nullptr, *vt = nullptr;
+  __nv_bfloat16 *q = nullptr, *k = nullptr, *vt = nullptr, *v = nullptr;
   int heads = 0, hd = 0;
   int up = 1, py = 0, px = 0;  // build_conv only: write pixel (y,x) to (y*up+py, x*up+px) of an up-times larger grid
 };

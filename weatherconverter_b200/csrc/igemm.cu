@@ -161,6 +161,18 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
         __nv_bfloat16* dst = p.vt + (bh * p.hd + d) * ntok + tok;
 #pragma unroll
         for (int j = 0; j < NC; ++j) dst[static_cast<size_t>(j) * ntok] = __float2bfloat16_rn(v[j]);
+        if (p.v) {
+          uint4* op = reinterpret_cast<uint4*>(p.v + (bh * ntok + tok) * p.hd + d);
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            uint4 u;
+            u.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+            u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+            u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+            u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+            op[j] = u;
+          }
+        }
       }
     }
   }

@@ -58,6 +58,7 @@ struct IgemmArgs {
   float* out_f32;  // kOutNCHWf32: [B, N_store, Ho, Wo] fp32 planes
   int n_store;
   __nv_bfloat16 *q, *k, *vt;  // kOutQKV: Q,K [B,heads,ntok,hd]; V^T [B,heads,hd,ntok]
+  __nv_bfloat16* v;           // kOutQKV, optional: V [B,heads,ntok,hd] as well (the attention backward reads it)
   int heads, hd, C;
 };
 

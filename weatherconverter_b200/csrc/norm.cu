@@ -104,9 +104,231 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ backward
+// y = act(gamma * xhat + beta), xhat = (x - mean) * rstd, act = SiLU or identity.  With dz = dy * act'(z):
+//   dgamma_c = sum dz * xhat,  dbeta_c = sum dz,
+//   dx = rstd * (gamma*dz - S1/n - xhat * S2/n),  S1 = sum_group gamma*dz,  S2 = sum_group gamma*dz*xhat.
+// (autograd of nn.GroupNorm + nn.SiLU in loss.backward(), diffusion_model/train_ddpm.py:108.)
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  float2 t;
+  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+}
+
+__device__ __forceinline__ void group_stats(const float2* partial, int b, int nsplit_stats, int HW, int C, float eps,
+                                            float* s_mean, float* s_rstd) {
+  if (threadIdx.x < kGroups) {
+    double s = 0.0, ss = 0.0;
+    for (int i = 0; i < nsplit_stats; ++i) {
+      const float2 t = partial[(static_cast<size_t>(b) * nsplit_stats + i) * kGroups + threadIdx.x];
+      s += t.x; ss += t.y;
+    }
+    const double n = static_cast<double>(HW) * (C / kGroups);
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float act_grad(float z, float dy, int silu) {
+  if (!silu) return dy;
+  const float s = 1.f / (1.f + __expf(-z));
+  return dy * s * (1.f + z * (1.f - s));
+}
+
+// pass 1: per (sample, slab, channel) sums of dz and dz*xhat
+__global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int HW, int C,
+                                    int ld, int ldd, int nsplit_stats, int nsplit, const float2* __restrict__ partial,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                    float2* __restrict__ part) {
+  __shared__ float s_mean[kGroups], s_rstd[kGroups];
+  extern __shared__ float2 stash[];  // [rows][C]
+  const int b = blockIdx.y, split = blockIdx.x;
+  group_stats(partial, b, nsplit_stats, HW, C, eps, s_mean, s_rstd);
+  const int vpp = C / 8, cpg = C / kGroups;
+  const int rows = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
+  const int g = (v * 8) / cpg;
+  const float mean = s_mean[g], rstd = s_rstd[g];
+  float ga[8], be[8], a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ga[j] = gamma[v * 8 + j]; be[j] = beta[v * 8 + j]; a0[j] = 0.f; a1[j] = 0.f; }
+  const int p0 = static_cast<int>(static_cast<long long>(HW) * split / nsplit);
+  const int p1 = static_cast<int>(static_cast<long long>(HW) * (split + 1) / nsplit);
+  const __nv_bfloat16* xb = x + static_cast<size_t>(b) * HW * ld + v * 8;
+  const __nv_bfloat16* db = dy + static_cast<size_t>(b) * HW * ldd + v * 8;
+  for (int p = p0 + r; p < p1; p += rows) {
+    float f[8], d[8];
+    load8(xb + static_cast<size_t>(p) * ld, f);
+    load8(db + static_cast<size_t>(p) * ldd, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (f[j] - mean) * rstd;
+      const float dz = act_grad(fmaf(ga[j], xh, be[j]), d[j], silu);
+      a0[j] += dz;
+      a1[j] = fmaf(dz, xh, a1[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) stash[static_cast<size_t>(r) * C + v * 8 + j] = make_float2(a0[j], a1[j]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int rr = 0; rr < rows; ++rr) { const float2 t = stash[static_cast<size_t>(rr) * C + c]; s0 += t.x; s1 += t.y; }
+    part[(static_cast<size_t>(b) * nsplit + split) * C + c] = make_float2(s0, s1);
+  }
+}
+
+// pass 2: per-sample channel sums bc[b][c] and group sums gs[b][g] = (S1, S2)
+__global__ void gn_bwd_reduce_kernel(const float2* __restrict__ part, int C, int nsplit, const float* __restrict__ gamma,
+                                     float2* __restrict__ bc, float2* __restrict__ gs) {
+  extern __shared__ float2 prod[];  // [C]
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = 0; i < nsplit; ++i) { const float2 t = part[(static_cast<size_t>(b) * nsplit + i) * C + c]; s0 += t.x; s1 += t.y; }
+    bc[static_cast<size_t>(b) * C + c] = make_float2(s0, s1);
+    const float gm = gamma[c];
+    prod[c] = make_float2(gm * s0, gm * s1);
+  }
+  __syncthreads();
+  if (threadIdx.x < kGroups) {
+    const int cpg = C / kGroups;
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { s0 += prod[c].x; s1 += prod[c].y; }
+    gs[b * kGroups + threadIdx.x] = make_float2(s0, s1);
+  }
+}
+
+__global__ void gn_bwd_param_kernel(const float2* __restrict__ bc, int B, int C, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (int b = 0; b < B; ++b) { const float2 t = bc[static_cast<size_t>(b) * C + c]; s0 += t.x; s1 += t.y; }
+  dbeta[c] = s0;
+  dgamma[c] = s1;
+}
+
+// pass 3: dx (+ up to two additive gradient inputs)
+__global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                    __nv_bfloat16* __restrict__ dx, int HW, int C, int ld, int ldd, int ldo, int nsplit_stats,
+                                    int nsplit, const float2* __restrict__ partial, const float2* __restrict__ gs,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                    const __nv_bfloat16* __restrict__ add1, int lda1, const __nv_bfloat16* __restrict__ add2,
+                                    int lda2) {
+  __shared__ float s_mean[kGroups], s_rstd[kGroups];
+  const int b = blockIdx.y, split = blockIdx.x;
+  group_stats(partial, b, nsplit_stats, HW, C, eps, s_mean, s_rstd);
+  const int vpp = C / 8, cpg = C / kGroups;
+  const int rows = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
+  const int g = (v * 8) / cpg;
+  const float mean = s_mean[g], rstd = s_rstd[g];
+  const float inv_n = 1.f / (static_cast<float>(HW) * cpg);
+  const float2 sg = gs[b * kGroups + g];
+  const float m1 = sg.x * inv_n, m2 = sg.y * inv_n;
+  float ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ga[j] = gamma[v * 8 + j]; be[j] = beta[v * 8 + j]; }
+  const int p0 = static_cast<int>(static_cast<long long>(HW) * split / nsplit);
+  const int p1 = static_cast<int>(static_cast<long long>(HW) * (split + 1) / nsplit);
+  const size_t boff = static_cast<size_t>(b) * HW;
+  for (int p = p0 + r; p < p1; p += rows) {
+    float f[8], d[8], o[8];
+    load8(x + (boff + p) * ld + v * 8, f);
+    load8(dy + (boff + p) * ldd + v * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (f[j] - mean) * rstd;
+      const float dz = act_grad(fmaf(ga[j], xh, be[j]), d[j], silu);
+      o[j] = rstd * (ga[j] * dz - m1 - xh * m2);
+    }
+    if (add1) {
+      float t[8];
+      load8(add1 + (boff + p) * lda1 + v * 8, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += t[j];
+    }
+    if (add2) {
+      float t[8];
+      load8(add2 + (boff + p) * lda2 + v * 8, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += t[j];
+    }
+    uint4 w;
+    w.x = pack_bf16(o[0], o[1]); w.y = pack_bf16(o[2], o[3]); w.z = pack_bf16(o[4], o[5]); w.w = pack_bf16(o[6], o[7]);
+    *reinterpret_cast<uint4*>(dx + (boff + p) * ldo + v * 8) = w;
+  }
+}
+
+// per-sample column sums of an NHWC bf16 tensor: part[b][split][c]
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int ld, int nsplit, float* __restrict__ part) {
+  extern __shared__ float cstash[];  // [rows][C]
+  const int b = blockIdx.y, split = blockIdx.x;
+  const int vpp = C / 8;
+  const int rows = blockDim.x / vpp;
+  const int v = threadIdx.x % vpp, r = threadIdx.x / vpp;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  const int p0 = static_cast<int>(static_cast<long long>(HW) * split / nsplit);
+  const int p1 = static_cast<int>(static_cast<long long>(HW) * (split + 1) / nsplit);
+  const __nv_bfloat16* xb = x + static_cast<size_t>(b) * HW * ld + v * 8;
+  if (r < rows) {
+    for (int p = p0 + r; p < p1; p += rows) {
+      float f[8];
+      load8(xb + static_cast<size_t>(p) * ld, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cstash[static_cast<size_t>(r) * C + v * 8 + j] = a[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int rr = 0; rr < rows; ++rr) s += cstash[static_cast<size_t>(rr) * C + c];
+    part[(static_cast<size_t>(b) * nsplit + split) * C + c] = s;
+  }
+}
+
+// out_rows[b*ldo + c] = sum_split part (optional), out_total[c] = sum_b sum_split part (optional); one block, fixed order
+__global__ void colsum_finish_kernel(const float* __restrict__ part, int B, int C, int nsplit, float* __restrict__ out_rows,
+                                     int ldo, float* __restrict__ out_total) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float tot = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float s = 0.f;
+    for (int i = 0; i < nsplit; ++i) s += part[(static_cast<size_t>(b) * nsplit + i) * C + c];
+    if (out_rows) out_rows[static_cast<size_t>(b) * ldo + c] = s;
+    tot += s;
+  }
+  if (out_total) out_total[c] = tot;
+}
+
 }  // namespace
 
 size_t groupnorm_workspace_bytes(int B) { return static_cast<size_t>(B) * 64 * kGroups * sizeof(float2); }
+
+// Number of per-sample slabs the statistics pass of groupnorm_silu uses for a [B,HW,C] input (the backward pass
+// re-combines the same partial sums).
+int groupnorm_stats_splits(int B, int HW) {
+  int nsplit = (4 * num_sms() + B - 1) / B;
+  const int max_split = (HW + 31) / 32;
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit > 64) nsplit = 64;
+  if (nsplit < 1) nsplit = 1;
+  return nsplit;
+}
 
 // x: [B,HW,C] bf16 with pixel stride ld; y likewise with ldy; workspace >= groupnorm_workspace_bytes(B).
 int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, int ld, int ldy, const float* gamma,
@@ -115,11 +337,8 @@ int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int 
   WC_REQUIRE(ld % 8 == 0 && ldy % 8 == 0, "pixel strides must be multiples of 8 elements");
   const int vpp = C / 8;
   const int threads = (256 / vpp) * vpp;
-  int nsplit = (4 * num_sms() + B - 1) / B;
+  const int nsplit = groupnorm_stats_splits(B, HW);
   const int max_split = (HW + 31) / 32;
-  if (nsplit > max_split) nsplit = max_split;
-  if (nsplit > 64) nsplit = 64;
-  if (nsplit < 1) nsplit = 1;
   float2* partial = reinterpret_cast<float2*>(workspace);
   ProfScope prof(kProfGroupNorm, st, 6.0 * B * static_cast<double>(HW) * C);  // algorithmic bytes: 2 reads + 1 write, bf16
   gn_stats_kernel<<<dim3(nsplit, B), threads, threads * sizeof(float2), st>>>(x, HW, C, ld, nsplit, partial);
@@ -129,6 +348,82 @@ int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int 
   if (asplit < 1) asplit = 1;
   gn_apply_kernel<<<dim3(asplit, B), threads, 0, st>>>(x, y, HW, C, ld, ldy, nsplit, asplit, partial, gamma, beta, eps,
                                                        silu);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace wc
+
+namespace wc {
+
+namespace {
+int bwd_splits(int B, int HW) {
+  int n = (2 * num_sms() + B - 1) / B;
+  const int max_split = (HW + 31) / 32;
+  if (n > max_split) n = max_split;
+  if (n > 32) n = 32;
+  if (n < 1) n = 1;
+  return n;
+}
+}  // namespace
+
+// Scratch for groupnorm_silu_bwd / colsum: part [B][32][C] float2 + bc [B][C] float2 + gs [B][8] float2.
+size_t groupnorm_bwd_workspace_bytes(int B, int Cmax) {
+  return static_cast<size_t>(B) * 32 * Cmax * sizeof(float2) + static_cast<size_t>(B) * Cmax * sizeof(float2) +
+         static_cast<size_t>(B) * kGroups * sizeof(float2) + 1024;
+}
+
+// Backward of groupnorm_silu.  `stats` is the workspace the forward call wrote (per-slab partial sums).  dx = dGN(dy)
+// (+ add1) (+ add2); dgamma/dbeta fp32 [C] are overwritten.
+int groupnorm_silu_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfloat16* dx, int B, int HW, int C, int ld,
+                       int ldd, int ldo, const float* gamma, const float* beta, float eps, int silu, const void* stats,
+                       const __nv_bfloat16* add1, int lda1, const __nv_bfloat16* add2, int lda2, float* dgamma, float* dbeta,
+                       void* workspace, cudaStream_t st) {
+  WC_REQUIRE(C % 64 == 0 && C / 8 <= 256, "GroupNorm(8) kernel needs C % 64 == 0 and C <= 2048");
+  WC_REQUIRE(ld % 8 == 0 && ldd % 8 == 0 && ldo % 8 == 0 && lda1 % 8 == 0 && lda2 % 8 == 0, "pixel strides must be multiples of 8");
+  const int vpp = C / 8;
+  const int threads = (256 / vpp) * vpp;
+  const int rows = threads / vpp;
+  const int ns_stats = groupnorm_stats_splits(B, HW);
+  const int nsplit = bwd_splits(B, HW);
+  float2* part = reinterpret_cast<float2*>(workspace);
+  float2* bc = part + static_cast<size_t>(B) * 32 * C;
+  float2* gs = bc + static_cast<size_t>(B) * C;
+  const float2* partial = reinterpret_cast<const float2*>(stats);
+  ProfScope prof(kProfGroupNorm, st, 10.0 * B * static_cast<double>(HW) * C);  // x, dy read twice, dx written (bf16)
+  gn_bwd_stats_kernel<<<dim3(nsplit, B), threads, static_cast<size_t>(rows) * C * sizeof(float2), st>>>(
+      x, dy, HW, C, ld, ldd, ns_stats, nsplit, partial, gamma, beta, eps, silu, part);
+  WC_LAUNCH_CHECK();
+  gn_bwd_reduce_kernel<<<B, 256, C * sizeof(float2), st>>>(part, C, nsplit, gamma, bc, gs);
+  WC_LAUNCH_CHECK();
+  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>(bc, B, C, dgamma, dbeta);
+  WC_LAUNCH_CHECK();
+  int asplit = (8 * num_sms() + B - 1) / B;
+  const int max_split = (HW + 31) / 32;
+  if (asplit > max_split) asplit = max_split;
+  if (asplit < 1) asplit = 1;
+  gn_bwd_apply_kernel<<<dim3(asplit, B), threads, 0, st>>>(x, dy, dx, HW, C, ld, ldd, ldo, ns_stats, asplit, partial, gs, gamma,
+                                                           beta, eps, silu, add1, lda1, add2, lda2);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+// Column sums of x [B,HW,C] (bf16, pixel stride ld): out_rows[b*ldo + c] per sample (may be null) and out_total[c]
+// over the whole batch (may be null) -- the bias gradients of the convolutions / linears and the per-sample gradient
+// of the t-embedding projection (unet_base.py:148).  workspace >= groupnorm_bwd_workspace_bytes(B, C).
+int colsum(const __nv_bfloat16* x, int B, int HW, int C, int ld, float* out_rows, int ldo, float* out_total, void* workspace,
+           cudaStream_t st) {
+  WC_REQUIRE(C % 8 == 0 && ld % 8 == 0 && C <= 4096, "colsum: C must be a multiple of 8 (<= 4096)");
+  const int vpp = C / 8;
+  int threads = vpp >= 256 ? ((vpp + 31) / 32) * 32 : (256 / vpp) * vpp;
+  if (threads > 1024) return fail("colsum: too many channels");
+  const int rows = threads / vpp > 0 ? threads / vpp : 1;
+  const int nsplit = bwd_splits(B, HW);
+  float* part = reinterpret_cast<float*>(workspace);
+  ProfScope prof(kProfOther, st, 2.0 * B * static_cast<double>(HW) * C);
+  colsum_kernel<<<dim3(nsplit, B), threads, static_cast<size_t>(rows) * C * sizeof(float), st>>>(x, HW, C, ld, nsplit, part);
+  WC_LAUNCH_CHECK();
+  colsum_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, B, C, nsplit, out_rows, ldo, out_total);
   WC_LAUNCH_CHECK();
   return 0;
 }

@@ -2,6 +2,7 @@
 #include "../../include/wc_b200.h"
 
 #include "conv.cuh"
+#include "wgrad.cuh"
 
 namespace wc {
 int ddpm_step(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
@@ -30,7 +31,7 @@ void prof_start();
 int prof_detail(int cap, int* cls, double* ms, double* work, int* info);
 int prof_stop(double* ms, long long* count, double* work);
 int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
-                      int heads, int ntok, int hd, int ldo, cudaStream_t st);
+                      int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse = nullptr);
 int maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st);
 int maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* x, __nv_bfloat16* dx, int B, int H,
                 int W, int C, cudaStream_t st);
@@ -44,6 +45,25 @@ int logits_bilinear_bwd(const float* dhi, __nv_bfloat16* dlo, int B, int h, int 
                         cudaStream_t st);
 int conv1_dgrad(const __nv_bfloat16* dz, const float* w, const float* scale, float* dx, int B, int H, int W, int Cout,
                 cudaStream_t st);
+int groupnorm_silu_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfloat16* dx, int B, int HW, int C, int ld,
+                       int ldd, int ldo, const float* gamma, const float* beta, float eps, int silu, const void* stats,
+                       const __nv_bfloat16* add1, int lda1, const __nv_bfloat16* add2, int lda2, float* dgamma, float* dbeta,
+                       void* workspace, cudaStream_t st);
+size_t groupnorm_bwd_workspace_bytes(int B, int Cmax);
+int colsum(const __nv_bfloat16* x, int B, int HW, int C, int ld, float* out_rows, int ldo, float* out_total, void* workspace,
+           cudaStream_t st);
+int attention_backward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* d_o, int ldd,
+                       const float* lse, const float* D, __nv_bfloat16* dqkv, int ld3, int B, int heads, int ntok, int hd,
+                       cudaStream_t st);
+int attn_rowdot(const __nv_bfloat16* o, const __nv_bfloat16* d_o, int ldo, int ldd, int B, int ntok, int heads, int hd, float* D,
+                cudaStream_t st);
+int mse_loss_grad(const float* pred, const float* target, float* dpred, size_t n, float grad_scale, float* loss, void* scratch,
+                  cudaStream_t st);
+size_t boundary_wgrad_scratch_bytes();
+int boundary_wgrad(const __nv_bfloat16* wide, int ldw, const float* narrow, int B, int H, int W, int sign, float* dw,
+                   float* dbias, void* scratch, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, int step,
+              float grad_scale, cudaStream_t st);
 }  // namespace wc
 
 using namespace wc;
@@ -203,6 +223,62 @@ int wc_nhwc_bf16_to_nchw_f32(const wc_bf16* x, float* y, int batch, int C, int h
 int wc_attention(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, int batch, int heads, int ntok,
                  int hd, int ldo, void* stream) {
   return attention_forward(BF(q), BF(k), BF(vt), BF(out), batch, heads, ntok, hd, ldo, S(stream));
+}
+
+
+int wc_attention_lse(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, float* lse, int batch, int heads,
+                     int ntok, int hd, int ldo, void* stream) {
+  return attention_forward(BF(q), BF(k), BF(vt), BF(out), batch, heads, ntok, hd, ldo, S(stream), lse);
+}
+
+int wc_attention_bwd(const wc_bf16* q, const wc_bf16* k, const wc_bf16* v, const wc_bf16* o, const wc_bf16* d_o, const float* lse,
+                     float* d_scratch, wc_bf16* dqkv, int batch, int heads, int ntok, int hd, void* stream) {
+  const int C = heads * hd;
+  if (int e = attn_rowdot(BF(o), BF(d_o), C, C, batch, ntok, heads, hd, d_scratch, S(stream))) return e;
+  return attention_backward(BF(q), BF(k), BF(v), BF(d_o), C, lse, d_scratch, BF(dqkv), 3 * C, batch, heads, ntok, hd, S(stream));
+}
+
+int wc_conv2d_wgrad(const wc_bf16* x, const wc_bf16* dy, int batch, int H, int W, int Cin, int Cout, int K, int stride, int pad,
+                    int dil, int transposed, const wc_bf16* x2, int Cin2, float* dw, float* dw2, void* stream) {
+  cudaStream_t st = S(stream);
+  DeviceArena arena;
+  float* partial = static_cast<float*>(arena.alloc(kWgradPartialBytes));
+  if (!partial) return 1;
+  const int Ho = transposed ? H * 2 : H / stride, Wo = transposed ? W * 2 : W / stride;
+  Act xa; xa.ptr = const_cast<__nv_bfloat16*>(BF(x)); xa.B = batch; xa.H = H; xa.W = W; xa.C = Cin; xa.ld = Cin;
+  Act dya; dya.ptr = const_cast<__nv_bfloat16*>(BF(dy)); dya.B = batch; dya.H = Ho; dya.W = Wo; dya.C = Cout; dya.ld = Cout;
+  Act x2a = xa; x2a.ptr = const_cast<__nv_bfloat16*>(BF(x2)); x2a.C = Cin2; x2a.ld = Cin2;
+  WgradOp op;
+  int e = transposed ? build_convT_wgrad(&op, xa, dya, K, pad, dw, partial)
+                     : build_conv_wgrad(&op, xa, dya, K, stride, pad, dil, dw, x2 ? &x2a : nullptr, dw2, partial);
+  if (e) return e;
+  if ((e = op.run(st))) return e;
+  WC_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+size_t wc_groupnorm_bwd_workspace_bytes(int batch, int channels) { return groupnorm_bwd_workspace_bytes(batch, channels); }
+int wc_groupnorm_silu_bwd(const wc_bf16* x, const wc_bf16* dy, wc_bf16* dx, int batch, int hw, int channels, const float* gamma,
+                          const float* beta, float eps, int silu, const void* fwd_workspace, const wc_bf16* add1,
+                          const wc_bf16* add2, float* dgamma, float* dbeta, void* workspace, void* stream) {
+  return groupnorm_silu_bwd(BF(x), BF(dy), BF(dx), batch, hw, channels, channels, channels, channels, gamma, beta, eps, silu,
+                            fwd_workspace, BF(add1), channels, BF(add2), channels, dgamma, dbeta, workspace, S(stream));
+}
+int wc_colsum(const wc_bf16* x, int batch, int hw, int channels, float* out_rows, float* out_total, void* workspace, void* stream) {
+  return colsum(BF(x), batch, hw, channels, channels, out_rows, channels, out_total, workspace, S(stream));
+}
+int wc_mse_loss_grad(const float* pred, const float* target, float* dpred, size_t n, float grad_scale, float* loss, void* scratch,
+                     void* stream) {
+  return mse_loss_grad(pred, target, dpred, n, grad_scale, loss, scratch, S(stream));
+}
+size_t wc_boundary_wgrad_scratch_bytes(void) { return boundary_wgrad_scratch_bytes(); }
+int wc_boundary_wgrad(const wc_bf16* wide, const float* narrow, int batch, int H, int W, int sign, float* dw, float* dbias,
+                      void* scratch, void* stream) {
+  return boundary_wgrad(BF(wide), 64, narrow, batch, H, W, sign, dw, dbias, scratch, S(stream));
+}
+int wc_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, int step,
+                 float grad_scale, void* stream) {
+  return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale, S(stream));
 }
 
 }  // extern "C"
