@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the WeatherConverter hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1|c5]
 
 Default workload (every N, weak scaling) = the configuration BASELINE.json's metric is quoted on:
   c3  SGG-guided translation at 256x512 (BASELINE.json configs[2]/[3]), batch 32 per GPU, N = 500 reverse steps,
@@ -9,6 +9,8 @@ Default workload (every N, weak scaling) = the configuration BASELINE.json's met
       DeepLabV3+-ResNet-50 (os16, 19 classes) forward + CE + input gradient at 256x512 -> avg-pool 4 -> guidance
       update (lambda = 60), GSG on every step (the repaired driver of SURVEY.md 8c).
   c2  UNet DDPM sampling at 128x256, batch 16 per GPU, 1000-step schedule (BASELINE.json configs[1]).
+  c5  denoising-loss TRAINING step at 128x256, batch 64 per GPU, NCCL gradient all-reduce at N > 1 (BASELINE.json
+      configs[4]; metric = trained images/s; step = add_noise + forward + MSE + backward + all-reduce + Adam).
 A "step" is ONE reverse-diffusion step over the batch; per-step cost does not depend on t, so
     images/s = (N_gpus * batch) / (schedule_steps * seconds_per_step).
 `value` times the steps with inputs resident in HBM; `e2e` times the same steps through the public Python API with
@@ -37,6 +39,9 @@ WORKLOADS = {
                     "step, lambda 60), batch 32/GPU, 500 reverse steps (BASELINE.json configs[2]/[3], geometry A)"),
     "c2": dict(kind="ddpm", im_size=128, batch=16, h=128, w=256, T=1000,
                desc="C2: UNet DDPM sampling 128x256, batch 16/GPU, 1000-step schedule (BASELINE.json configs[1])"),
+    "c5": dict(kind="train", im_size=128, batch=64, h=128, w=256, T=1000,
+               desc="C5: denoising-loss training step 128x256, batch 64/GPU, Adam, NCCL gradient all-reduce across GPUs "
+                    "(BASELINE.json configs[4])"),
     "c1": dict(kind="ddpm", im_size=64, batch=4, h=64, w=64, T=50,
                desc="C1: UNet DDPM sampling 64x64, batch 4, 50 steps (BASELINE.json configs[0])"),
 }
@@ -213,11 +218,190 @@ def cpu_reference_rate(spec, steps, warmup):
     return 1.0 / (T * sec), sec, cores
 
 
+TRAIN_METRIC = "denoising-loss training images/sec (128x256, batch 64/GPU, Adam, NCCL gradient all-reduce)"
+
+
+def cpu_train_rate(spec, steps, warmup):
+    """Oracle port of the training step (PyTorch fp32 autograd + Adam, all host threads) on ONE image."""
+    import torch
+    from oracle.scheduler import OracleScheduler
+    from oracle.train import train_step
+    from oracle.unet import DEFAULT_MODEL_CONFIG, unet_param_spec
+    from oracle.weights import synth_state_dict
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = spec["im_size"]
+    sd = synth_state_dict(unet_param_spec(cfg), 3455)
+    sched = OracleScheduler(1000, 1e-4, 0.02)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(1, 3, spec["h"], spec["w"], generator=g) * 2 - 1
+    times = []
+    for k in range(warmup + steps):
+        noise = torch.randn(x.shape, generator=g)
+        t = torch.randint(0, 1000, (1,), generator=g)
+        t0 = time.perf_counter()
+        _, _, sd = train_step(sd, cfg, x, noise, t, sched, step=k + 1)
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return 1.0 / sec, sec, cores
+
+
+def run_train(args):
+    """C5: training step.  value = images trained per second over all ranks (inputs resident in HBM); e2e = the same
+    step with the image batch coming from pinned host memory and the loss read back every step."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from weatherconverter_b200 import _lib, ops
+    from weatherconverter_b200.diffusion_model.config.models import ModelConfig
+    from weatherconverter_b200.diffusion_model.models.unet_base import Unet
+    from weatherconverter_b200.diffusion_model.scheduler.linear_noise_scheduler import LinearNoiseScheduler
+    from weatherconverter_b200.diffusion_model.train_ddpm import DenoisingTrainer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    spec = dict(WORKLOADS["c5"])
+    if args.batch:
+        spec["batch"] = args.batch
+    B, h, w = spec["batch"], spec["h"], spec["w"]
+    W_, K = max(args.warmup, 3), args.steps
+    peaks = read_peaks()
+    torch.manual_seed(3455)                       # same initial replica on every rank (config.yaml:32)
+    model = Unet(ModelConfig(im_size=spec["im_size"])).to(dev)
+    sched = LinearNoiseScheduler(1000, 1e-4, 0.02)
+    trainer = DenoisingTrainer(model, sched, lr=1e-4)
+    g = torch.Generator().manual_seed(1234 + rank)   # every rank trains on its own shard of the global batch
+    imgs_host = [(torch.rand(B, 3, h, w, generator=g) * 2 - 1).pin_memory() for _ in range(2)]
+    imgs = [x.to(dev) for x in imgs_host]
+    ts = [torch.randint(0, 1000, (B,), generator=g) for _ in range(4)]
+    gz = torch.Generator(device=dev).manual_seed(99 + rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one(k, x):
+        noise = torch.randn(x.shape, device=dev, generator=gz)
+        return trainer.step(x, noise=noise, t=ts[k % 4])
+
+    for k in range(W_):
+        one(k, imgs[k % 2])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(W_, W_ + K):
+        loss = one(k, imgs[k % 2])
+    e1.record()
+    barrier()
+    clocks = sampler.finish()
+    launches = ops.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    loss_val = float(loss)
+    # e2e: batch from pinned host memory, loss read back each step (as the reference's loss.item(), train_ddpm.py:116)
+    x_dev = torch.empty_like(imgs[0])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for k in range(K):
+        x_dev.copy_(imgs_host[k % 2], non_blocking=True)
+        loss_val = float(one(k, x_dev))
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    classes, roofline = {}, None
+    flops_step = trainer.flops_per_step
+    if not args.no_profile and not args.resident_only:
+        lib = _lib.lib()
+        KP = 1
+        lib.wc_profile_begin()
+        one(0, imgs[0])
+        ms_c, cnt_c, work_c = (C.c_double * 8)(), (C.c_longlong * 8)(), (C.c_double * 8)()
+        _lib.check(lib.wc_profile_end(ms_c, cnt_c, work_c))
+        names = ["igemm_wgrad_tcgen05", "flash_attention_fwd_bwd_tcgen05", "groupnorm_fwd_bwd", "boundary_conv", "elementwise_adam_mse", "other"]
+        for i, n in enumerate(names):
+            if cnt_c[i]:
+                classes[n] = {"ms_per_step": ms_c[i] / KP, "launches_per_step": cnt_c[i] / KP, "work_per_step": work_c[i] / KP}
+        prof_total = sum(v["ms_per_step"] for v in classes.values())
+        for n, v in classes.items():
+            if "tcgen05" in n:
+                v["tflops"] = v["work_per_step"] / (v["ms_per_step"] * 1e-3) / 1e12
+            elif v["work_per_step"] > 0:
+                v["gbs"] = v["work_per_step"] / (v["ms_per_step"] * 1e-3) / 1e9
+            v["share_of_step"] = v["ms_per_step"] / prof_total
+        dom = max(("igemm_wgrad_tcgen05", "flash_attention_fwd_bwd_tcgen05"), key=lambda n: classes.get(n, {}).get("ms_per_step", 0))
+        achieved = classes[dom]["tflops"]
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                    "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "share_of_step": classes[dom]["share_of_step"],
+                    "flops_per_launch": classes[dom]["work_per_step"] / classes[dom]["launches_per_step"],
+                    "avg_launch_ms": classes[dom]["ms_per_step"] / classes[dom]["launches_per_step"],
+                    "launches_per_step": classes[dom]["launches_per_step"]}
+    if world > 1:
+        tt = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(tt[0]), float(tt[1])
+    ms_step = ms_total / K
+    value = world * B / (ms_step * 1e-3)
+    e2e_value = world * B / (ms_e2e / K * 1e-3)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, cores = cpu_train_rate(spec, 1, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sec_per_step_per_image": sec,
+                        "sample": f"oracle port (PyTorch fp32 autograd + Adam, {cores} threads): batch of 1 image, 1 timed step after 1 warm-up"}
+    if rank == 0:
+        line = {
+            "metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": spec["desc"], "batch_per_gpu": B, "image": [h, w],
+                       "step": "add_noise + UNet forward + MSE + full backward (data + weight gradients) + bucketed NCCL all-reduce + fused Adam",
+                       "l2": "per-step working set (tens of GB of saved activations) exceeds the 126 MB L2; no explicit flush",
+                       "weights": "random init (seed 3455), fp32 master weights, bf16 activations / GEMM operands, fp32 accumulation"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 3 * h * w * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches), "launches_per_step": launches / K, "clocks": clocks, "roofline": roofline,
+            "kernel_classes": classes, "step_gflop_per_image": flops_step / B / 1e9,
+            "step_tflops": flops_step / (ms_step * 1e-3) / 1e12,
+            "step_frac_of_tensor_peak": flops_step / (ms_step * 1e-3) / 1e12 / peaks["tf_sustained"],
+            "cpu_baseline": cpu_baseline, "final_loss": loss_val, "finite": loss_val == loss_val,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """Reference arm: rank 0 only; CPU implementation of the same step on a bounded sample."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     spec = WORKLOADS[args.workload]
+    if spec["kind"] == "train":
+        steps, warm = min(args.steps, 2), 1
+        value, sec, cores = cpu_train_rate(spec, steps, warm)
+        sample = (f"oracle port (PyTorch fp32 autograd + Adam, {cores} threads): batch of 1 image, {steps} timed training steps "
+                  f"after {warm} warm-up")
+        print(json.dumps({
+            "impl": "reference", "metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": spec["desc"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
     steps = min(args.steps, 5)
     warm = min(args.warmup, 1)
     value, sec, cores = cpu_reference_rate(spec, steps, warm)
@@ -251,6 +435,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if WORKLOADS[args.workload]["kind"] == "train":
+        return run_train(args)
 
     import ctypes as C
     import torch

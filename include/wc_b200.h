@@ -177,6 +177,28 @@ double wc_unet_flops(const wc_unet* net);
 /* Kernel launches per forward of the last bound shape. */
 int wc_unet_launches(const wc_unet* net);
 
+/* ---- model-level: denoising-loss training step of the UNet (diffusion_model/train_ddpm.py:95-114) -----------------
+ * names / params / grads: the reference state_dict names with fp32 device pointers of every parameter and of its
+ * gradient buffer (the host keeps them in flat buffers; see weatherconverter_b200/diffusion_model/train_ddpm.py).
+ * bind builds the forward / backward launch plans for one [batch,3,H,W] shape in the given workspace.
+ * forward: (repack != 0: rebuild the bf16 packed weights from the fp32 parameters first) pred = Unet(x, t) with
+ * t int64 [batch]; loss[0] = mean((pred - target)^2) (nn.MSELoss, :107); pred_out may be NULL.
+ * backward(op_begin, op_end): runs that slice of the backward plan (loss.backward(), :108); running all
+ * [0, num_backward_ops) fills every gradient buffer (overwrite, like zero_grad + backward).  grad_ready_op(name) is
+ * the op count after which that parameter's gradient is final, so the host can overlap bucketed all-reduces. */
+typedef struct wc_unet_train wc_unet_train;
+int wc_unet_train_create(wc_unet_train** out, const wc_unet_config* cfg, int n_params, const char* const* names,
+                         float* const* params, float* const* grads);
+void wc_unet_train_destroy(wc_unet_train* net);
+size_t wc_unet_train_workspace_bytes(wc_unet_train* net, int batch, int H, int W);
+int wc_unet_train_bind(wc_unet_train* net, int batch, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+int wc_unet_train_forward(wc_unet_train* net, const float* x, const int64_t* t, const float* target, float* pred_out,
+                          float* loss_out, float grad_scale, int repack, void* stream);
+int wc_unet_train_num_backward_ops(const wc_unet_train* net);
+int wc_unet_train_backward(wc_unet_train* net, int op_begin, int op_end, void* stream);
+int wc_unet_train_grad_ready_op(const wc_unet_train* net, const char* name);
+double wc_unet_train_flops(const wc_unet_train* net, int backward);
+
 /* ---- model-level: DeepLabV3+ ResNet-50/101 os16 forward + CE + input gradient ------------------------------
  * (seg_model/network/*, seg_model/inference.py:118-152).  blocks_per_layer = {3,4,6,3} (R50) or {3,4,23,3} (R101).
  * names/ptrs: the reference state_dict (fp32 device tensors; num_batches_tracked entries may be omitted). */

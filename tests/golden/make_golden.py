@@ -231,10 +231,50 @@ def g_gsg_and_driver(G):
     save("sgg.pt", out)
 
 
+def sample_idx(name, numel, k=32):
+    """Fixed pseudo-random element indices of a parameter (shared with tests/test_oracle_golden.py)."""
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    return torch.randint(0, numel, (min(k, numel),), generator=g)
+
+
+def g_train():
+    """One training step exactly as train_ddpm.py:95-114 runs it (add_noise -> model -> MSELoss -> backward ->
+    Adam(lr=1e-4).step()), B=2, 64x64, im_size=64.  The full gradients are 110 M floats, so the fixture keeps the loss,
+    every parameter's gradient norm and 32 sampled entries of its gradient and of its post-step value."""
+    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = 64
+    m = unet_for(cfg, 3455).train()
+    sched = LinearNoiseScheduler(1000, 1e-4, 0.02)
+    g = torch.Generator().manual_seed(77)
+    images = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    noise = torch.randn(2, 3, 64, 64, generator=g)
+    t = torch.tensor([37, 811])
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    crit = torch.nn.MSELoss()
+    opt.zero_grad()
+    noisy = sched.add_noise(images, noise, t)
+    pred = m(noisy, t)
+    loss = crit(pred, noise)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+    opt.step()
+    out = dict(cfg=cfg, seed=3455, images=images, noise=noise, t=t, loss=loss.detach(), pred=pred.detach(), lr=1e-4, params={})
+    for k, p in m.named_parameters():
+        idx = sample_idx(k, p.numel())
+        out["params"][k] = dict(grad_norm=grads[k].norm(), grad_sum=grads[k].double().sum().float(),
+                                grad_samples=grads[k].flatten()[idx].clone(), new_samples=p.detach().flatten()[idx].clone())
+    save("train_step.pt", out)
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only == ["train"]:
+        g_train()
+        sys.exit(0)
     g_scheduler()
     g_unet()
     g_sample()
     g_seg()
     G = g_srgan()
     g_gsg_and_driver(G)
+    g_train()

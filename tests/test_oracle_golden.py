@@ -94,3 +94,22 @@ def test_gsg_and_repaired_driver(golden):
                               d["noise"], d["t_fwd"], list(d["zs"]), lam=60.0, n_steps=d["N"], record=rec)
     assert (torch.stack(rec) - d["traj"]).abs().max() < 1e-3
     assert (out - d["sr_x0"]).abs().max() < 1e-3
+
+
+def test_train_step(golden):
+    """oracle.train.train_step vs the reference's own step (train_ddpm.py:95-114, golden made by make_golden.g_train)."""
+    import zlib
+    from oracle.train import train_step
+    d = golden("train_step.pt")
+    sd = synth_state_dict(unet.unet_param_spec(d["cfg"]), d["seed"])
+    loss, grads, new_sd = train_step(sd, d["cfg"], d["images"], d["noise"], d["t"], OracleScheduler(1000, 1e-4, 0.02), lr=d["lr"])
+    assert abs(float(loss) - float(d["loss"])) < 1e-5 * abs(float(d["loss"]))
+    assert set(grads) == set(d["params"])
+    for k, ref in d["params"].items():
+        g = torch.Generator().manual_seed(zlib.crc32(k.encode()) & 0x7FFFFFFF)
+        idx = torch.randint(0, grads[k].numel(), (min(32, grads[k].numel()),), generator=g)
+        gn = float(ref["grad_norm"])
+        assert abs(float(grads[k].norm()) - gn) <= 2e-3 * gn + 1e-7, k
+        assert (grads[k].flatten()[idx] - ref["grad_samples"]).abs().max() <= 2e-3 * gn / grads[k].numel() ** 0.5 * 8 + 1e-7, k
+        # Adam's first step moves every weight by ~lr * sign(grad): compare the post-step values
+        assert (new_sd[k].flatten()[idx] - ref["new_samples"]).abs().max() < 2.5e-5, k

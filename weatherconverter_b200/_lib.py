@@ -77,6 +77,16 @@ _SIGS = {
                                   c_ptr]),
     "wc_unet_flops": (C.c_double, [c_ptr]),
     "wc_unet_launches": (C.c_int, [c_ptr]),
+    "wc_unet_train_create": (C.c_int, [C.POINTER(c_ptr), C.POINTER(UnetConfigStruct), C.c_int, C.POINTER(C.c_char_p),
+                                       C.POINTER(c_ptr), C.POINTER(c_ptr)]),
+    "wc_unet_train_destroy": (None, [c_ptr]),
+    "wc_unet_train_workspace_bytes": (C.c_size_t, [c_ptr, C.c_int, C.c_int, C.c_int]),
+    "wc_unet_train_bind": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, C.c_size_t, c_ptr]),
+    "wc_unet_train_forward": (C.c_int, [c_ptr] * 6 + [C.c_float, C.c_int, c_ptr]),
+    "wc_unet_train_num_backward_ops": (C.c_int, [c_ptr]),
+    "wc_unet_train_backward": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr]),
+    "wc_unet_train_grad_ready_op": (C.c_int, [c_ptr, C.c_char_p]),
+    "wc_unet_train_flops": (C.c_double, [c_ptr, C.c_int]),
     "wc_seg_create": (C.c_int, [C.POINTER(c_ptr), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_char_p),
                                 C.POINTER(c_ptr), c_ptr]),
     "wc_seg_destroy": (None, [c_ptr]),

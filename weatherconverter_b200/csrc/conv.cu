@@ -24,6 +24,11 @@ void* DeviceArena::alloc(size_t bytes) {
 }
 
 namespace {
+thread_local std::vector<std::function<int(cudaStream_t)>>* g_pack_recorder = nullptr;
+}
+void set_pack_recorder(std::vector<std::function<int(cudaStream_t)>>* recorder) { g_pack_recorder = recorder; }
+
+namespace {
 
 int row3_mode() {  // 1: descriptors rely on address-based swizzling; 2 (WC_ROW3=2): explicit base_offset
   const char* e = getenv("WC_ROW3");
@@ -88,6 +93,13 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
     const int cpad = (t.C + kIgemmBK - 1) / kIgemmBK * kIgemmBK;
     const int ky = w.flip ? w.KH - 1 - t.ky : t.ky, kx = w.flip ? w.KW - 1 - t.kx : t.kx;
     if (int e = pack_tap(wp, ktotal, koff, w.w, n_src, t.C, cpad, w.KH, w.KW, ky, kx, w.transpose, w.scale, w.row_mul, w.row_off, st)) return e;
+    if (g_pack_recorder) {
+      const WeightSrc wc = w;
+      const int tC = t.C, ko = koff;
+      g_pack_recorder->push_back([=](cudaStream_t s) {
+        return pack_tap(wp, ktotal, ko, wc.w, n_src, tC, cpad, wc.KH, wc.KW, ky, kx, wc.transpose, wc.scale, wc.row_mul, wc.row_off, s);
+      });
+    }
     koff += cpad;
     macs_per_pixel += static_cast<double>(t.C) * n_src;
   }

@@ -1,6 +1,7 @@
 // Convolution layers expressed as igemm plans: tap lists for stride-1 (dilated) convs, stride-2 convs (phase
 // views), transposed / data-gradient convs (one plan per output phase), with weights packed to bf16 K-major.
 #pragma once
+#include <functional>
 #include <memory>
 #include <vector>
 
@@ -19,6 +20,10 @@ class DeviceArena {
   std::vector<void*> ptrs_;
   size_t total_ = 0;
 };
+
+// While a recorder is set (training plans), every weight-packing launch issued by build_conv* is also appended to it,
+// so the bf16 packed copies can be rebuilt from the fp32 master weights after each optimizer step.
+void set_pack_recorder(std::vector<std::function<int(cudaStream_t)>>* recorder);
 
 struct WeightSrc {
   const float* w = nullptr;  // fp32 device tensor, PyTorch layout

@@ -205,6 +205,11 @@ __global__ void silu_rows_kernel(const float* __restrict__ x, float* __restrict_
   if (i < n) { const float v = x[i]; y[i] = v / (1.f + expf(-v)); }
 }
 
+__global__ void add_vectors_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] + b[i];
+}
+
 // ------------------------------------------------------------------------------------------------ Adam
 // torch.optim.Adam(lr, betas, eps), no weight decay / amsgrad (train_ddpm.py:151): one launch over the flat buffers.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -267,6 +272,12 @@ int boundary_wgrad(const __nv_bfloat16* wide, int ldw, const float* narrow, int 
   boundary_wgrad_kernel<<<blocks, kBwThreads, 0, st>>>(wide, ldw, narrow, B, H, W, sign, part);
   WC_LAUNCH_CHECK();
   boundary_wgrad_finish_kernel<<<(64 * 28 + 3 + 127) / 128, 128, 0, st>>>(part, blocks, sign, dw, dbias);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+int add_vectors(const float* a, const float* b, float* o, int n, cudaStream_t st) {
+  add_vectors_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, o, n);
   WC_LAUNCH_CHECK();
   return 0;
 }

@@ -135,6 +135,7 @@ class Unet(nn.Module):
         self._handle_key = None
         self._workspaces = {}
         self._keepalive = None
+        self._weights_epoch = 0      # bumped by DenoisingTrainer.optimizer_step (in-place kernel updates of the weights)
 
     def _register(self, dotted, param):
         node = self
@@ -177,7 +178,7 @@ class Unet(nn.Module):
 
     def _ensure_handle(self, device):
         params = dict(self.named_parameters())
-        key = (str(device), tuple((p.data_ptr(), p._version) for p in params.values()))
+        key = (str(device), self._weights_epoch, tuple((p.data_ptr(), p._version) for p in params.values()))
         if self._handle is not None and key == self._handle_key:
             return
         self._destroy()

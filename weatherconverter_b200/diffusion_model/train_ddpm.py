@@ -1,0 +1,224 @@
+"""Denoising-loss training with the reference's step semantics (diffusion_model/train_ddpm.py:71-133) on libwc_b200.so.
+
+The reference step is
+    noise = randn_like(images); t = randint(0, T, (B,)); noisy = scheduler.add_noise(images, noise, t)
+    loss = MSELoss(model(noisy, t), noise); loss.backward(); Adam.step()                      (:95-114)
+Here the forward, the loss, the whole backward and the Adam update run as static launch plans of hand-written kernels
+(csrc/unet_train.cu); PyTorch only owns the memory, the streams and, for more than one GPU, the NCCL communicator.
+
+Data parallelism (the reference itself is single-GPU): one process per GPU, each with a full replica and
+its own mini-batch; gradients are summed with NCCL all-reduces issued per bucket as soon as the backward plan has
+finished the bucket's parameters (the flat gradient buffer is laid out in backward-completion order so that every
+bucket is one contiguous slice), then every rank applies the same fused Adam update with the 1/world scale folded in.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+from .._lib import check, lib, ptr, stream_ptr
+from .models.unet_base import Unet
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def _backward_group(name: str, n_ups: int, n_mids: int, n_downs: int) -> int:
+    """Coarse backward-completion rank of a parameter (conv_out first ... conv_in, then the time-embedding path, whose
+    gradients are only complete after every ResNet block has contributed)."""
+    if "t_emb_layers" in name or name.startswith("t_proj"):
+        return 3 + n_ups + n_mids + n_downs
+    head = name.split(".")
+    if head[0] in ("conv_out", "norm_out"):
+        return 0
+    if head[0] == "ups":
+        return 1 + (n_ups - 1 - int(head[1]))
+    if head[0] == "mids":
+        return 1 + n_ups + (n_mids - 1 - int(head[1]))
+    if head[0] == "downs":
+        return 1 + n_ups + n_mids + (n_downs - 1 - int(head[1]))
+    if head[0] == "conv_in":
+        return 1 + n_ups + n_mids + n_downs
+    raise KeyError(name)
+
+
+class DenoisingTrainer:
+    """Owns flat fp32 parameter / gradient / Adam-moment buffers (the model's parameters become views into the flat
+    parameter buffer) and the C training plan bound to one (batch, H, W)."""
+
+    def __init__(self, model: Unet, scheduler, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, process_group=None,
+                 bucket_bytes=64 << 20):
+        if not torch.cuda.is_available():
+            raise RuntimeError("wc_b200 training needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.model, self.scheduler = model, scheduler
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.bucket_bytes = int(bucket_bytes)
+        self.step_count = 0
+        named = list(model.named_parameters())
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError("move the model to the GPU before building a DenoisingTrainer")
+        n_levels = len(model.down_channels) - 1
+        n_mids = len(model.mid_channels) - 1
+        order = sorted(range(len(named)), key=lambda i: (_backward_group(named[i][0], n_levels, n_mids, n_levels), i))
+        total = sum((p.numel() + 3) & ~3 for _, p in named)   # every tensor starts 16-byte aligned
+        self.flat_params = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_grads = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.slices, self.groups = {}, []
+        off = 0
+        for i in order:
+            name, p = named[i]
+            n = p.numel()
+            off = (off + 3) & ~3          # 16-byte alignment of every tensor
+            view = self.flat_params[off:off + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_grads[off:off + n].view(p.shape)
+            self.slices[name] = (off, n)
+            self.groups.append(_backward_group(name, n_levels, n_mids, n_levels))
+            off += n
+        self.used = off
+        self.names = [named[i][0] for i in order]
+        self._handle = None
+        self._bound = None
+        self._ws = None
+        self._buckets = []
+        self._keep = None
+        self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
+
+    # ---- torch.optim.Adam-compatible views of the optimizer state (for checkpoints, train_ddpm.py:55-61) ----
+    def export_optimizer_state(self, optimizer):
+        """Make ``optimizer.state`` point at this trainer's moment buffers so ``optimizer.state_dict()`` saves them."""
+        params = dict(self.model.named_parameters())
+        for name, (off, n) in self.slices.items():
+            p = params[name]
+            optimizer.state[p] = {"step": torch.tensor(float(self.step_count)),
+                                  "exp_avg": self.exp_avg[off:off + n].view(p.shape),
+                                  "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape)}
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                lib().wc_unet_train_destroy(self._handle)
+        except Exception:
+            pass
+
+    def _bind(self, B, H, W):
+        if self._bound == (B, H, W):
+            return
+        L = lib()
+        if self._handle is None:
+            n = len(self.names)
+            c_names = (C.c_char_p * n)(*[s.encode() for s in self.names])
+            pp = (C.c_void_p * n)(*[self.flat_params.data_ptr() + 4 * self.slices[s][0] for s in self.names])
+            gp = (C.c_void_p * n)(*[self.flat_grads.data_ptr() + 4 * self.slices[s][0] for s in self.names])
+            handle = C.c_void_p()
+            cfg = self.model._config_struct()
+            check(L.wc_unet_train_create(C.byref(handle), C.byref(cfg), n, c_names, pp, gp))
+            self._handle = handle
+        nbytes = L.wc_unet_train_workspace_bytes(self._handle, B, H, W)
+        if nbytes == 0:
+            check(1)
+        self._ws = None
+        self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.flat_params.device)
+        check(L.wc_unet_train_bind(self._handle, B, H, W, ptr(self._ws), self._ws.numel(), stream_ptr()))
+        self._bound = (B, H, W)
+        # ---- gradient buckets: contiguous slices of the flat buffer, closed when the backward plan is done with them
+        n_ops = L.wc_unet_train_num_backward_ops(self._handle)
+        ready = [L.wc_unet_train_grad_ready_op(self._handle, s.encode()) for s in self.names]
+        if min(ready) < 0:
+            raise RuntimeError("internal: a parameter has no gradient producer: " + self.names[ready.index(min(ready))])
+        buckets, start, cur_group, cur_ready = [], 0, self.groups[0], 0
+        for i, name in enumerate(self.names):
+            off, n = self.slices[name]
+            if self.groups[i] != cur_group and (off - start) * 4 >= self.bucket_bytes:
+                buckets.append((start, off, cur_ready))
+                start, cur_ready = off, 0
+            cur_group = self.groups[i]
+            cur_ready = max(cur_ready, ready[i])
+        buckets.append((start, self.used, max(cur_ready, n_ops)))
+        # op indices must not decrease from bucket to bucket
+        fixed, hi = [], 0
+        for (a, b, r) in buckets:
+            hi = max(hi, r)
+            fixed.append((a, b, hi))
+        self._buckets, self._n_bwd_ops = fixed, n_ops
+
+    @property
+    def flops_per_step(self):
+        L = lib()
+        return float(L.wc_unet_train_flops(self._handle, 0) + L.wc_unet_train_flops(self._handle, 1)) if self._handle else 0.0
+
+    def forward_backward(self, noisy, t, target, pred_out=None):
+        """loss (device scalar) and all gradients for pred = model(noisy, t), loss = MSE(pred, target)."""
+        _lib.require_cuda(noisy, target)
+        noisy, target = noisy.contiguous().float(), target.contiguous().float()
+        B, _, H, W = noisy.shape
+        t = torch.as_tensor(t).long().to(noisy.device).reshape(-1).contiguous()
+        if t.numel() != B:
+            raise RuntimeError("training needs one timestep per sample")
+        self._bind(B, H, W)
+        L, st = lib(), stream_ptr()
+        check(L.wc_unet_train_forward(self._handle, ptr(noisy), ptr(t), ptr(target), ptr(pred_out), ptr(self.loss), 1.0, 1, st))
+        works, cursor = [], 0
+        for (a, b, upto) in self._buckets:
+            if upto > cursor:
+                check(L.wc_unet_train_backward(self._handle, cursor, upto, st))
+                cursor = upto
+            if self.world > 1:
+                works.append(dist.all_reduce(self.flat_grads[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if cursor < self._n_bwd_ops:
+            check(L.wc_unet_train_backward(self._handle, cursor, self._n_bwd_ops, st))
+        for w in works:
+            w.wait()
+        self._keep = (noisy, t, target, pred_out)
+        return self.loss
+
+    def optimizer_step(self):
+        self.step_count += 1
+        self.model._weights_epoch += 1      # the inference plan re-packs its weights on its next call
+        check(lib().wc_adam_step(ptr(self.flat_params), ptr(self.flat_grads), ptr(self.exp_avg), ptr(self.exp_avg_sq),
+                                 self.used, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
+                                 1.0 / self.world, stream_ptr()))
+
+    def step(self, images, noise=None, t=None):
+        """One reference training step (train_ddpm.py:95-114); returns the loss as a device scalar tensor."""
+        images = images.float().to(self.flat_params.device)
+        if noise is None:
+            noise = torch.randn_like(images)                                        # :99
+        if t is None:
+            t = torch.randint(0, self.scheduler.num_timesteps, (images.shape[0],))  # :102 (CPU generator, then H2D)
+        t = torch.as_tensor(t).to(images.device)
+        noisy = self.scheduler.add_noise(images, noise, t)                          # :105
+        loss = self.forward_backward(noisy, t, noise)                               # :106-109
+        self.optimizer_step()                                                       # :113
+        return loss
+
+
+def train(dataloader, model: Unet, optimizer, criterion, scheduler, epochs=1, log_interval=10, on_log=None):
+    """Drop-in for the reference's ``train`` (train_ddpm.py:71-133): same arguments; the Adam hyper-parameters are read
+    from ``optimizer`` (built as ``Adam(model.parameters(), lr)`` at :151) and ``criterion`` must be ``nn.MSELoss()``.
+    wandb / tqdm / checkpoint I/O of the reference are host-side plumbing and are left to ``on_log(epoch, batch, loss)``."""
+    if not isinstance(criterion, torch.nn.MSELoss):
+        raise RuntimeError("the fused training step implements nn.MSELoss (train_ddpm.py:152)")
+    g = optimizer.param_groups[0]
+    if g.get("weight_decay", 0) or g.get("amsgrad", False):
+        raise RuntimeError("the fused Adam implements torch.optim.Adam without weight decay / amsgrad (train_ddpm.py:151)")
+    trainer = DenoisingTrainer(model, scheduler, lr=g["lr"], betas=g["betas"], eps=g["eps"])
+    losses = []
+    for epoch_idx in range(1, epochs + 1):
+        interval = 0.0
+        for batch_idx, images in enumerate(dataloader):
+            loss = trainer.step(images)
+            interval += float(loss)          # the reference also reads loss.item() every step (:116)
+            losses.append(float(loss))
+            if (batch_idx + 1) % log_interval == 0:
+                if on_log is not None:
+                    on_log(epoch_idx, batch_idx + 1, interval / log_interval)
+                interval = 0.0
+    trainer.export_optimizer_state(optimizer)
+    return losses
