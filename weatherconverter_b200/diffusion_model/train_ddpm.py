@@ -42,6 +42,41 @@ def _backward_group(name: str, n_ups: int, n_mids: int, n_downs: int) -> int:
     raise KeyError(name)
 
 
+def make_buckets(names, slices, groups, ready, n_ops, used, bucket_bytes):
+    """Contiguous [start, stop) slices of the flat gradient buffer + the backward-op count after which each is final.
+    A bucket is closed at a block boundary (change of backward group) once it holds >= bucket_bytes."""
+    buckets, start, cur_group, cur_ready = [], 0, groups[0], 0
+    for i, name in enumerate(names):
+        off, _ = slices[name]
+        if groups[i] != cur_group and (off - start) * 4 >= bucket_bytes:
+            buckets.append((start, off, cur_ready))
+            start, cur_ready = off, 0
+        cur_group = groups[i]
+        cur_ready = max(cur_ready, ready[i])
+    buckets.append((start, used, max(cur_ready, n_ops)))
+    fixed, hi = [], 0
+    for (a, b, r) in buckets:      # op counts must not decrease from bucket to bucket
+        hi = max(hi, r)
+        fixed.append((a, b, hi))
+    return fixed
+
+
+def backward_with_buckets(run_ops, n_ops, flat_grads, buckets, world, group=None):
+    """Run the backward plan slice by slice; as soon as a bucket's gradients are final, start its all-reduce (async: NCCL
+    runs it on its own stream, ordered after the work already queued on the current stream) and keep computing."""
+    works, cursor = [], 0
+    for (a, b, upto) in buckets:
+        if upto > cursor:
+            run_ops(cursor, upto)
+            cursor = upto
+        if world > 1:
+            works.append(dist.all_reduce(flat_grads[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True))
+    if cursor < n_ops:
+        run_ops(cursor, n_ops)
+    for w in works:
+        w.wait()
+
+
 class DenoisingTrainer:
     """Owns flat fp32 parameter / gradient / Adam-moment buffers (the model's parameters become views into the flat
     parameter buffer) and the C training plan bound to one (batch, H, W)."""
@@ -132,21 +167,8 @@ class DenoisingTrainer:
         ready = [L.wc_unet_train_grad_ready_op(self._handle, s.encode()) for s in self.names]
         if min(ready) < 0:
             raise RuntimeError("internal: a parameter has no gradient producer: " + self.names[ready.index(min(ready))])
-        buckets, start, cur_group, cur_ready = [], 0, self.groups[0], 0
-        for i, name in enumerate(self.names):
-            off, n = self.slices[name]
-            if self.groups[i] != cur_group and (off - start) * 4 >= self.bucket_bytes:
-                buckets.append((start, off, cur_ready))
-                start, cur_ready = off, 0
-            cur_group = self.groups[i]
-            cur_ready = max(cur_ready, ready[i])
-        buckets.append((start, self.used, max(cur_ready, n_ops)))
-        # op indices must not decrease from bucket to bucket
-        fixed, hi = [], 0
-        for (a, b, r) in buckets:
-            hi = max(hi, r)
-            fixed.append((a, b, hi))
-        self._buckets, self._n_bwd_ops = fixed, n_ops
+        self._buckets = make_buckets(self.names, self.slices, self.groups, ready, n_ops, self.used, self.bucket_bytes)
+        self._n_bwd_ops = n_ops
 
     @property
     def flops_per_step(self):
@@ -164,17 +186,8 @@ class DenoisingTrainer:
         self._bind(B, H, W)
         L, st = lib(), stream_ptr()
         check(L.wc_unet_train_forward(self._handle, ptr(noisy), ptr(t), ptr(target), ptr(pred_out), ptr(self.loss), 1.0, 1, st))
-        works, cursor = [], 0
-        for (a, b, upto) in self._buckets:
-            if upto > cursor:
-                check(L.wc_unet_train_backward(self._handle, cursor, upto, st))
-                cursor = upto
-            if self.world > 1:
-                works.append(dist.all_reduce(self.flat_grads[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        if cursor < self._n_bwd_ops:
-            check(L.wc_unet_train_backward(self._handle, cursor, self._n_bwd_ops, st))
-        for w in works:
-            w.wait()
+        backward_with_buckets(lambda a, b: check(L.wc_unet_train_backward(self._handle, a, b, st)), self._n_bwd_ops,
+                              self.flat_grads, self._buckets, self.world, self.group)
         self._keep = (noisy, t, target, pred_out)
         return self.loss
 
