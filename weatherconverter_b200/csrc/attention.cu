@@ -22,33 +22,6 @@ namespace wc {
 
 namespace {
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// 2^x for a PAIR of inputs on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3
-// minimax polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of P), exponent patched with one
-// integer multiply-add.  Used for a fixed share of every 32-column chunk so the MUFU and FMA pipes work in parallel
-// (the softmax of the N = 8192 layers is exp-throughput bound: N^2 exponentials per head).
-__device__ __forceinline__ float2 exp2_poly2(float2 x) {
-  const float kMagic = 12582912.f;  // 1.5 * 2^23: adding it rounds x to the nearest integer in the low mantissa bits
-  x.x = fmaxf(x.x, -125.f);
-  x.y = fmaxf(x.y, -125.f);
-  const float2 r = fadd2(x, make_float2(kMagic, kMagic));
-  const float2 n = fadd2(r, make_float2(-kMagic, -kMagic));
-  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
-  float2 p = ffma2(f, make_float2(0.05517163872718811f, 0.05517163872718811f), make_float2(0.2426111251115799f, 0.2426111251115799f));
-  p = ffma2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
-  p = ffma2(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
-  float2 o;
-  o.x = __uint_as_float(__float_as_uint(r.x) * 0x800000u + __float_as_uint(p.x));  // bits(p) + (n << 23)
-  o.y = __uint_as_float(__float_as_uint(r.y) * 0x800000u + __float_as_uint(p.y));
-  return o;
-}
-
-
 struct AttnArgs {
   int ntok, heads, ldo;
   float scale_log2;  // log2(e) / sqrt(hd)

@@ -20,12 +20,6 @@ namespace wc {
 
 namespace {
 
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
 struct AttnBwdArgs {
   int ntok, heads, C, ld3;  // ld3: row stride of the dqkv buffer (>= 3C)
   float scale_log2, scale;
@@ -38,6 +32,9 @@ struct AttnBwdMaps {
   CUtensorMap r1, r2, t1, t2;
 };
 
+constexpr int kSoftmaxThreads = 256;  // warps 4-11: two warps per TMEM lane quadrant, interleaving the 32-column chunks
+constexpr int kPoly = 12;             // of every 32 exponentials, this many run on the FMA pipe (exp2_poly2)
+
 template <int HD, int BT, int STAGES, bool KV>
 struct BwdCfg {
   static constexpr int kKBlocks = HD >= 64 ? HD / 64 : 1;
@@ -48,8 +45,12 @@ struct BwdCfg {
   static constexpr uint32_t kPTile = 128 * BT * 2;
   static constexpr int kNP = KV ? 2 : 1;
   static constexpr uint32_t kVecBytes = KV ? 2 * 2 * BT * 4 : 0;
-  static constexpr uint32_t kSmem = 2 * kRTile + STAGES * 2 * kTTile + kNP * kPTile + kVecBytes + 1024 + 256;
-  static constexpr int kThreads = 256;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 softmax / epilogue
+  static constexpr uint32_t kFixed = 2 * kRTile + STAGES * 2 * kTTile + kVecBytes + 1024 + 256;
+  // P'/dS' tiles are double-buffered when shared memory allows it (then the softmax of tile i+1 never waits for the
+  // dV/dK/dQ MMAs of tile i)
+  static constexpr int kPB = (kFixed + 2 * kNP * kPTile <= 232448) ? 2 : 1;
+  static constexpr uint32_t kSmem = kFixed + kPB * kNP * kPTile;
+  static constexpr int kThreads = 128 + kSoftmaxThreads;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 softmax / epilogue
   static constexpr int kAcc0 = 2 * BT;                  // KV: dV ; Q: dQ
   static constexpr int kAcc1 = 2 * BT + (KV ? HD : 0);  // KV: dK
   static_assert(2 * BT + (KV ? 2 : 1) * HD <= 512, "TMEM budget");
@@ -57,7 +58,7 @@ struct BwdCfg {
 };
 
 template <int HD, int BT, int STAGES, bool KV>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(128 + kSoftmaxThreads, 1)
 attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant__ AttnBwdArgs p) {
   using Cfg = BwdCfg<HD, BT, STAGES, KV>;
   extern __shared__ uint8_t smem_raw[];
@@ -67,13 +68,14 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
   const uint32_t r2_smem = r1_smem + Cfg::kRTile;
   const uint32_t t_smem = r2_smem + Cfg::kRTile;                  // stage s: T1 at t_smem + s*2*kTTile, T2 right after
   const uint32_t p_smem = t_smem + STAGES * 2 * Cfg::kTTile;      // dS' first, then (KV) P'
-  const uint32_t vec_smem = p_smem + Cfg::kNP * Cfg::kPTile;
+  const uint32_t vec_smem = p_smem + Cfg::kPB * Cfg::kNP * Cfg::kPTile;
   const uint32_t bars = vec_smem + Cfg::kVecBytes;
   const uint32_t r_full = bars;
   auto t_full = [&](int s) { return bars + 8u * (1 + s); };
   auto t_empty = [&](int s) { return bars + 8u * (3 + s); };
-  const uint32_t s_full = bars + 8u * 5, p_full = bars + 8u * 6, acc_done = bars + 8u * 7;
-  const uint32_t tmem_slot = bars + 8u * 8;
+  const uint32_t s_full = bars + 8u * 5, p_full = bars + 8u * 6;
+  auto acc_done = [&](int b) { return bars + 8u * (7 + b); };
+  const uint32_t tmem_slot = bars + 8u * 9;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -88,8 +90,9 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
     mbar_init(r_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(acc_done, 1);
+    mbar_init(p_full, kSoftmaxThreads);
+    mbar_init(acc_done(0), 1);
+    mbar_init(acc_done(1), 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -155,6 +158,7 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
       };
       auto issue_acc = [&](int i) {
         const int s = i % STAGES;
+        const uint32_t p_lo = p_lo0 + (i % Cfg::kPB) * ((Cfg::kNP * Cfg::kPTile) >> 4);
         const uint32_t t1_mn = tmn_lo0 + s * ((2 * Cfg::kTTile) >> 4), t2_mn = t1_mn + (Cfg::kTTile >> 4);
         constexpr uint32_t kstep16 = (16 * Cfg::kRowBytes) >> 4;  // 16 rows of the T tile per MMA K step
         // dS' is the first P tile, P' (KV pass only) the second
@@ -164,12 +168,12 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
           for (int k = 0; k < 4; ++k) {
             const int kk = cb * 4 + k;
             if (KV)
-              umma_bf16(tmem_base + Cfg::kAcc0, umma_desc_join(p_lo0 + (Cfg::kPTile >> 4) + cb * ((128 * 128) >> 4) + 2u * k, hi_p),
+              umma_bf16(tmem_base + Cfg::kAcc0, umma_desc_join(p_lo + (Cfg::kPTile >> 4) + cb * ((128 * 128) >> 4) + 2u * k, hi_p),
                         umma_desc_join(t2_mn + kk * kstep16, hi_k), idesc_acc, (i | kk) != 0 ? 1u : 0u);
-            umma_bf16(tmem_base + Cfg::kAcc1, umma_desc_join(p_lo0 + cb * ((128 * 128) >> 4) + 2u * k, hi_p),
+            umma_bf16(tmem_base + Cfg::kAcc1, umma_desc_join(p_lo + cb * ((128 * 128) >> 4) + 2u * k, hi_p),
                       umma_desc_join(t1_mn + kk * kstep16, hi_k), idesc_acc, (i | kk) != 0 ? 1u : 0u);
           }
-        umma_commit(acc_done);
+        umma_commit(acc_done(i % Cfg::kPB));
         umma_commit(t_empty(s));
       };
       mbar_wait(r_full, 0);
@@ -196,16 +200,17 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
   } else if (warp >= 4) {
     // ===================== softmax-backward warps =====================
     const int quad = warp & 3;
+    const int grp = (warp - 4) >> 2;  // 0 or 1: which half of the interleaved 32-column chunks
     const int row = quad * 32 + lane;
     const int tid = threadIdx.x - 128;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t s_tmem = tmem_base + lane_off, dp_tmem = s_tmem + BT;
-    const uint32_t ds_row = p_smem + row * 128, pp_row = ds_row + Cfg::kPTile;
     float* vec = reinterpret_cast<float*>(smem_raw + (vec_smem - raw_u32));  // [buf][lse | D][BT]
     const float sl2 = p.scale_log2;
     const size_t voff = static_cast<size_t>(bh) * p.ntok;
     float my_lse = 0.f, my_D = 0.f;
     if (!KV && r0 + row < p.ntok) { my_lse = p.lse[voff + r0 + row]; my_D = p.D[voff + r0 + row]; }
+    constexpr int NCH = BT / 32;
     for (int i = 0; i < nt; ++i) {
       const int t0 = i * BT;
       float* vl = vec + (i & 1) * 2 * BT;
@@ -215,57 +220,78 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
           vl[tid] = t < p.ntok ? p.lse[voff + t] : INFINITY;
           vl[BT + tid] = t < p.ntok ? p.D[voff + t] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      const uint32_t ds_row = p_smem + (i % Cfg::kPB) * (Cfg::kNP * Cfg::kPTile) + row * 128, pp_row = ds_row + Cfg::kPTile;
       mbar_wait(s_full, i & 1u);
       tc_fence_after();
-      if (i > 0) mbar_wait(acc_done, (i - 1) & 1u);  // the MMAs reading the previous P'/dS' tiles have completed
       const bool tail = !KV && (t0 + BT > p.ntok);
+      bool p_free = (i < Cfg::kPB);  // first use of a P buffer needs no wait
 #pragma unroll
-      for (int c = 0; c < BT / 32; ++c) {
+      for (int cc = 0; cc < (NCH + 1) / 2; ++cc) {
+        const int c = 2 * cc + grp;
+        if (c >= NCH) break;
         uint32_t rs[32], rd[32];
         tmem_ld32(s_tmem + 32 * c, rs);
         tmem_ld32(dp_tmem + 32 * c, rd);
         tmem_wait_ld();
-        float pv[32], dv[32];
+        uint32_t wp[16], wd[16];
+        const float2 sl2v = make_float2(sl2, sl2);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float l2 = KV ? vl[32 * c + j] : my_lse;
-          const float Dc = KV ? vl[BT + 32 * c + j] : my_D;
-          float pe = ex2f(fmaf(__uint_as_float(rs[j]), sl2, -l2));
-          if (tail && t0 + 32 * c + j >= p.ntok) pe = 0.f;
-          pv[j] = pe;
-          dv[j] = pe * (__uint_as_float(rd[j]) - Dc);
+        for (int j = 0; j < 32; j += 2) {
+          float2 l2, Dc;
+          if (KV) {
+            l2 = *reinterpret_cast<const float2*>(vl + 32 * c + j);
+            Dc = *reinterpret_cast<const float2*>(vl + BT + 32 * c + j);
+          } else {
+            l2 = make_float2(my_lse, my_lse);
+            Dc = make_float2(my_D, my_D);
+          }
+          const float2 xs = ffma2(make_float2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), sl2v, make_float2(-l2.x, -l2.y));
+          float2 pe;
+          if (j < kPoly) {
+            pe = exp2_poly2(xs);
+          } else {
+            pe.x = ex2_approx(xs.x);
+            pe.y = ex2_approx(xs.y);
+          }
+          if (tail) {
+            if (t0 + 32 * c + j >= p.ntok) pe.x = 0.f;
+            if (t0 + 32 * c + j + 1 >= p.ntok) pe.y = 0.f;
+          }
+          const float2 dd = fadd2(make_float2(__uint_as_float(rd[j]), __uint_as_float(rd[j + 1])), make_float2(-Dc.x, -Dc.y));
+          wp[j >> 1] = pack_bf16(pe.x, pe.y);
+          wd[j >> 1] = pack_bf16(pe.x * dd.x, pe.y * dd.y);
+        }
+        if (!p_free) {  // the MMAs that read this P buffer (tile i - kPB) must have completed before it is overwritten
+          mbar_wait(acc_done(i % Cfg::kPB), ((i / Cfg::kPB) - 1) & 1u);
+          p_free = true;
         }
         const uint32_t blk_off = ((32 * c) >> 6) * (128 * 128);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int chunk = (((32 * c) & 63) >> 3) + ch;
           const uint32_t sw = static_cast<uint32_t>(chunk ^ (row & 7)) << 4;
-          {
-            const uint32_t w0 = pack_bf16(dv[8 * ch + 0], dv[8 * ch + 1]), w1 = pack_bf16(dv[8 * ch + 2], dv[8 * ch + 3]);
-            const uint32_t w2 = pack_bf16(dv[8 * ch + 4], dv[8 * ch + 5]), w3 = pack_bf16(dv[8 * ch + 6], dv[8 * ch + 7]);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ds_row + blk_off + sw), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-          }
-          if (KV) {
-            const uint32_t w0 = pack_bf16(pv[8 * ch + 0], pv[8 * ch + 1]), w1 = pack_bf16(pv[8 * ch + 2], pv[8 * ch + 3]);
-            const uint32_t w2 = pack_bf16(pv[8 * ch + 4], pv[8 * ch + 5]), w3 = pack_bf16(pv[8 * ch + 6], pv[8 * ch + 7]);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(pp_row + blk_off + sw), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-          }
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ds_row + blk_off + sw), "r"(wd[4 * ch]), "r"(wd[4 * ch + 1]),
+                       "r"(wd[4 * ch + 2]), "r"(wd[4 * ch + 3]) : "memory");
+          if (KV)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(pp_row + blk_off + sw), "r"(wp[4 * ch]), "r"(wp[4 * ch + 1]),
+                         "r"(wp[4 * ch + 2]), "r"(wp[4 * ch + 3]) : "memory");
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    // ---- epilogue: accumulators -> bf16 -> dqkv[b, tok, which*C + h*hd + d]
-    mbar_wait(acc_done, (nt - 1) & 1u);
+    // ---- epilogue: accumulators -> bf16 -> dqkv[b, tok, which*C + h*hd + d]; the two warp groups split the columns
+    mbar_wait(acc_done((nt - 1) % Cfg::kPB), ((nt - 1) / Cfg::kPB) & 1u);
     tc_fence_after();
     const int tok = r0 + row;
     __nv_bfloat16* orow = p.dqkv + (static_cast<size_t>(b) * p.ntok + tok) * p.ld3 + h * HD;
     auto store_acc = [&](uint32_t taddr, int which, float mul) {
 #pragma unroll
       for (int c0 = 0; c0 < HD; c0 += 16) {
+        if (((c0 >> 4) & 1) != grp) continue;
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
         tmem_wait_ld();
