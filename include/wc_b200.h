@@ -199,6 +199,22 @@ int wc_unet_train_backward(wc_unet_train* net, int op_begin, int op_end, void* s
 int wc_unet_train_grad_ready_op(const wc_unet_train* net, const char* name);
 double wc_unet_train_flops(const wc_unet_train* net, int backward);
 
+/* ---- model-level: legacy "old model" UNet (diffusion_model/models/old_modules.py:230-360, used by
+ * diffusion_model/sample_integrated.py:40-67).  names/ptrs/numels: the reference state_dict (fp32 device tensors, BN
+ * running statistics included); the attention in/out projections may be zero-padded per head to a supported head
+ * dimension (the padded size is read from numels; see weatherconverter_b200/diffusion_model/models/old_modules.py).
+ * forward: x nchw_f32 [B,3,128,128]; t f32 [B] = the noise variance 1 - alpha_bar_t the reference passes as
+ * scheduler.one_minus_cum_prod[t] (sample_integrated.py:60); out nchw_f32 [B,3,128,128]. */
+typedef struct wc_legacy_unet wc_legacy_unet;
+int wc_legacy_unet_create(wc_legacy_unet** out, int n_params, const char* const* names, const float* const* ptrs,
+                          const int64_t* numels);
+void wc_legacy_unet_destroy(wc_legacy_unet* net);
+size_t wc_legacy_unet_workspace_bytes(wc_legacy_unet* net, int batch, int size);
+int wc_legacy_unet_forward(wc_legacy_unet* net, const float* x, const float* t, float* out, int batch, int size, void* workspace,
+                           size_t workspace_bytes, void* stream);
+double wc_legacy_unet_flops(const wc_legacy_unet* net);
+int wc_legacy_unet_launches(const wc_legacy_unet* net);
+
 /* ---- model-level: DeepLabV3+ ResNet-50/101 os16 forward + CE + input gradient ------------------------------
  * (seg_model/network/*, seg_model/inference.py:118-152).  blocks_per_layer = {3,4,6,3} (R50) or {3,4,23,3} (R101).
  * names/ptrs: the reference state_dict (fp32 device tensors; num_batches_tracked entries may be omitted). */

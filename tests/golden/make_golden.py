@@ -266,10 +266,42 @@ def g_train():
     save("train_step.pt", out)
 
 
+def g_legacy():
+    """Legacy old_modules.UNet (eval) forward, B=2, and 3 steps of the sample_integrated loop (sample_integrated.py:52-65)
+    with recorded noise."""
+    from diffusion_model.models.old_modules import UNet as LegacyUNet
+    m = LegacyUNet().eval()
+    sd = synth_state_dict(m.state_dict(), 21)
+    m.load_state_dict(sd)
+    sched = LinearNoiseScheduler(1000, 1e-4, 0.02)
+    g = torch.Generator().manual_seed(91)
+    x = torch.randn(2, 3, 128, 128, generator=g)
+    t_idx = torch.tensor([40, 900])
+    out = dict(seed=21, x=x, t_idx=t_idx)
+    with torch.no_grad():
+        out["y"] = m(x, sched.one_minus_cum_prod[t_idx].view(-1, 1, 1, 1))
+        T = 3
+        xt = torch.randn(2, 3, 128, 128, generator=g)
+        zs = [torch.randn(2, 3, 128, 128, generator=g) for _ in range(T)]
+        out["xT"], out["zs"], traj = xt.clone(), torch.stack(zs), []
+        for i in reversed(range(T)):
+            t = torch.full((xt.size(0),), i, dtype=torch.long)
+            noise_pred = m(xt, sched.one_minus_cum_prod[t].view(-1, 1, 1, 1))
+            with InjectedRandn([zs[i]]):
+                mean, sigma, _ = sched.sample_prev_timestep2(xt, noise_pred, t)
+            xt = mean + sigma if i != 0 else mean
+            traj.append(xt.clone())
+        out["traj"] = torch.stack(traj)
+    save("legacy_unet.pt", out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     if only == ["train"]:
         g_train()
+        sys.exit(0)
+    if only == ["legacy"]:
+        g_legacy()
         sys.exit(0)
     g_scheduler()
     g_unet()
@@ -278,3 +310,4 @@ if __name__ == "__main__":
     G = g_srgan()
     g_gsg_and_driver(G)
     g_train()
+    g_legacy()

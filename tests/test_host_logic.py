@@ -116,3 +116,27 @@ def test_sharding_world_size_2_gloo(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                          env=env, capture_output=True, text=True, timeout=300)
     assert "GLOO_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_legacy_unet_state_dict_matches_reference_layout():
+    """The legacy UNet module exposes the reference's state_dict keys / shapes / dtypes in registration order."""
+    import torch
+    from oracle.legacy_unet import legacy_param_spec
+    from weatherconverter_b200.diffusion_model.models.old_modules import UNet, legacy_param_spec as spec2
+    m = UNet()
+    sd = m.state_dict()
+    ref = legacy_param_spec()
+    assert list(sd.keys()) == list(ref.keys()) == list(spec2().keys())
+    for k, (shape, dt) in ref.items():
+        assert tuple(sd[k].shape) == tuple(shape) and sd[k].dtype == dt, k
+    # head-dim padding helper: 24 -> 32 keeps q.k products and the projected output
+    w = {"a.mha.in_proj_weight": torch.randn(288, 96), "a.mha.in_proj_bias": torch.randn(288), "a.mha.out_proj.weight": torch.randn(96, 96)}
+    wp, bp, wop = UNet._pad_attention(w, "a", 96)
+    assert wp.shape == (384, 96) and bp.shape == (384,) and wop.shape == (96, 128)
+    x = torch.randn(5, 96)
+    qkv = (x @ w["a.mha.in_proj_weight"].T + w["a.mha.in_proj_bias"]).view(5, 3, 4, 24)
+    qkvp = (x @ wp.T + bp).view(5, 3, 4, 32)
+    assert torch.allclose(qkvp[..., :24], qkv, atol=1e-5) and float(qkvp[..., 24:].abs().max()) == 0.0
+    o = torch.randn(5, 4, 24)
+    op = torch.zeros(5, 4, 32); op[..., :24] = o
+    assert torch.allclose(op.reshape(5, 128) @ wop.T, o.reshape(5, 96) @ w["a.mha.out_proj.weight"].T, atol=1e-4)

@@ -113,3 +113,21 @@ def test_train_step(golden):
         assert (grads[k].flatten()[idx] - ref["grad_samples"]).abs().max() <= 2e-3 * gn / grads[k].numel() ** 0.5 * 8 + 1e-7, k
         # Adam's first step moves every weight by ~lr * sign(grad): compare the post-step values
         assert (new_sd[k].flatten()[idx] - ref["new_samples"]).abs().max() < 2.5e-5, k
+
+
+def test_legacy_unet(golden):
+    """oracle.legacy_unet vs the reference's old_modules.UNet (eval) and 3 steps of the sample_integrated loop."""
+    from oracle.legacy_unet import legacy_param_spec, legacy_unet_forward
+    d = golden("legacy_unet.pt")
+    sd = synth_state_dict(legacy_param_spec(), d["seed"])
+    s = OracleScheduler(1000, 1e-4, 0.02)
+    with torch.no_grad():
+        y = legacy_unet_forward(sd, d["x"], s.one_minus_cum_prod[d["t_idx"]].view(-1, 1, 1, 1))
+        assert (y - d["y"]).abs().max() < 2e-4 * d["y"].abs().max(), float((y - d["y"]).abs().max())
+        xt = d["xT"]
+        for k, i in enumerate(reversed(range(3))):
+            t = torch.full((xt.size(0),), i, dtype=torch.long)
+            eps = legacy_unet_forward(sd, xt, s.one_minus_cum_prod[t].view(-1, 1, 1, 1))
+            mean, sz, _ = s.sample_prev_timestep2(xt, eps, t, z=d["zs"][i])
+            xt = mean + sz if i != 0 else mean
+            assert (xt - d["traj"][k]).abs().max() < 1e-3 * d["traj"][k].abs().max(), k

@@ -87,6 +87,12 @@ _SIGS = {
     "wc_unet_train_backward": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr]),
     "wc_unet_train_grad_ready_op": (C.c_int, [c_ptr, C.c_char_p]),
     "wc_unet_train_flops": (C.c_double, [c_ptr, C.c_int]),
+    "wc_legacy_unet_create": (C.c_int, [C.POINTER(c_ptr), C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_ptr), C.POINTER(C.c_int64)]),
+    "wc_legacy_unet_destroy": (None, [c_ptr]),
+    "wc_legacy_unet_workspace_bytes": (C.c_size_t, [c_ptr, C.c_int, C.c_int]),
+    "wc_legacy_unet_forward": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, C.c_size_t, c_ptr]),
+    "wc_legacy_unet_flops": (C.c_double, [c_ptr]),
+    "wc_legacy_unet_launches": (C.c_int, [c_ptr]),
     "wc_seg_create": (C.c_int, [C.POINTER(c_ptr), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_char_p),
                                 C.POINTER(c_ptr), c_ptr]),
     "wc_seg_destroy": (None, [c_ptr]),

@@ -336,7 +336,7 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
 
 template <int HD, int BKV, int NQ, int POLY>
 int launch_attention_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
-                     int heads, int ntok, int ldo, cudaStream_t st, float* lse) {
+                     int heads, int ntok, int ldo, cudaStream_t st, float* lse, float scale) {
   using Cfg = AttnCfg<HD, BKV, NQ>;
   AttnMaps maps;
   const int BH = B * heads;
@@ -357,7 +357,7 @@ int launch_attention_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   }
   AttnArgs args;
   args.ntok = ntok; args.heads = heads; args.ldo = ldo; args.out = out; args.lse = lse;
-  args.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  args.scale_log2 = 1.4426950408889634f * (scale > 0.f ? scale : 1.f / sqrtf(static_cast<float>(HD)));
   static bool attr_set = false;
   if (!attr_set) {
     WC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD, BKV, NQ, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -373,17 +373,17 @@ int launch_attention_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
 
 template <int HD, int BKV, int NQ>
 int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
-                     int heads, int ntok, int ldo, cudaStream_t st, float* lse) {
+                     int heads, int ntok, int ldo, cudaStream_t st, float* lse, float scale) {
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("WC_ATTN_POLY");
     poly = e ? atoi(e) : 14;
   }
   switch (poly) {   // tuning knob; 14 is the shipped setting
-    case 0: return launch_attention_p<HD, BKV, NQ, 0>(q, k, vt, out, B, heads, ntok, ldo, st, lse);
-    case 8: return launch_attention_p<HD, BKV, NQ, 8>(q, k, vt, out, B, heads, ntok, ldo, st, lse);
-    case 20: return launch_attention_p<HD, BKV, NQ, 20>(q, k, vt, out, B, heads, ntok, ldo, st, lse);
-    default: return launch_attention_p<HD, BKV, NQ, 14>(q, k, vt, out, B, heads, ntok, ldo, st, lse);
+    case 0: return launch_attention_p<HD, BKV, NQ, 0>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 8: return launch_attention_p<HD, BKV, NQ, 8>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 20: return launch_attention_p<HD, BKV, NQ, 20>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    default: return launch_attention_p<HD, BKV, NQ, 14>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
   }
 }
 
@@ -391,15 +391,15 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
 
 // q,k [B,heads,ntok,hd]; vt [B,heads,hd,ntok]; out [B,ntok,ldo] (columns head*hd .. head*hd+hd).
 int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
-                      int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse) {
+                      int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse, float scale) {
   WC_REQUIRE(ntok % 8 == 0, "token count must be a multiple of 8");
   WC_REQUIRE(ldo % 8 == 0, "output row stride must be a multiple of 8");
   switch (hd) {
-    case 16: return launch_attention<16, 128, 3>(q, k, vt, out, B, heads, ntok, ldo, st, lse);
-    case 32: return launch_attention<32, 128, 3>(q, k, vt, out, B, heads, ntok, ldo, st, lse);
-    case 64: return launch_attention<64, 128, 2>(q, k, vt, out, B, heads, ntok, ldo, st, lse);
-    case 128: return launch_attention<128, 64, 2>(q, k, vt, out, B, heads, ntok, ldo, st, lse);
-    case 192: return launch_attention<192, 64, 1>(q, k, vt, out, B, heads, ntok, ldo, st, lse);
+    case 16: return launch_attention<16, 128, 3>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 32: return launch_attention<32, 128, 3>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 64: return launch_attention<64, 128, 2>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 128: return launch_attention<128, 64, 2>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 192: return launch_attention<192, 64, 1>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
     default: return fail("attention: unsupported head_dim " + std::to_string(hd) + " (supported: 16,32,64,128,192)");
   }
 }

@@ -123,6 +123,7 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
     a.mask = ep.mask->ptr; a.ldm = ep.mask->ld;
   }
   a.relu = ep.relu;
+  a.act = ep.act;
   a.prelu = ep.prelu;
   a.out_mode = out.mode;
   a.sy = sy; a.sx = sx; a.py = py; a.px = px;

@@ -47,6 +47,7 @@ struct Epilogue {
   const Act* res = nullptr;
   const Act* mask = nullptr;
   int relu = 0;
+  int act = 0;  // 2 SiLU, 3 GELU
   const float* prelu = nullptr;
 };
 

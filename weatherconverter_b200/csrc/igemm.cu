@@ -98,6 +98,13 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
 #pragma unroll
       for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.f);
     }
+    if (p.act == 2) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+    } else if (p.act == 3) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+    }
     if (p.prelu) {
 #pragma unroll
       for (int j = 0; j < NC; j += 4) {

@@ -51,6 +51,7 @@ struct IgemmArgs {
   const __nv_bfloat16* mask;  // ReLU-derivative mask on the output grid: result zeroed where mask <= 0, or nullptr
   int ldm;
   int relu;
+  int act;  // 0 none, 2 SiLU, 3 GELU (exact, erf): applied after bias / residual (legacy UNet, old_modules.py:84,148)
   const float* prelu;  // per-channel PReLU slopes [N] applied after bias/residual, or nullptr
   int out_mode;
   __nv_bfloat16* out;  // kOutNHWC: element (b, y*sy+py, x*sx+px, n) of a [B,Ho,Wo,ldc] buffer

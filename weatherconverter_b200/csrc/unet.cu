@@ -22,7 +22,7 @@ int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int 
                    const float* beta, float eps, int silu, void* workspace, cudaStream_t st);
 size_t groupnorm_workspace_bytes(int B);
 int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
-                      int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse = nullptr);
+                      int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse = nullptr, float scale = 0.f);
 double attention_flops(int B, int heads, int ntok, int hd);
 int conv_small_cin(const float* x, const float* w, const float* bias, const float* scale, const float* shift,
                    __nv_bfloat16* y, int B, int Cin, int H, int W, int Cout, int K, int stride, int pad, int ldy,

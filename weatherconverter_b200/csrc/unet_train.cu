@@ -28,7 +28,7 @@ size_t groupnorm_bwd_workspace_bytes(int B, int Cmax);
 int colsum(const __nv_bfloat16* x, int B, int HW, int C, int ld, float* out_rows, int ldo, float* out_total, void* workspace,
            cudaStream_t st);
 int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
-                      int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse = nullptr);
+                      int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse = nullptr, float scale = 0.f);
 double attention_flops(int B, int heads, int ntok, int hd);
 int attention_backward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const __nv_bfloat16* d_o, int ldd,
                        const float* lse, const float* D, __nv_bfloat16* dqkv, int ld3, int B, int heads, int ntok, int hd,

@@ -31,7 +31,7 @@ void prof_start();
 int prof_detail(int cap, int* cls, double* ms, double* work, int* info);
 int prof_stop(double* ms, long long* count, double* work);
 int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
-                      int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse = nullptr);
+                      int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse = nullptr, float scale = 0.f);
 int maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st);
 int maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16* x, __nv_bfloat16* dx, int B, int H,
                 int W, int C, cudaStream_t st);
