@@ -7,6 +7,8 @@ namespace wc {
 
 int pack_tap(__nv_bfloat16* dst, int ldk, int koff, const float* src, int Nn, int Cc, int Cpad, int KH, int KW, int ky,
              int kx, int transpose, const float* scale, int row_mul, int row_off, cudaStream_t st);
+int pack_taps(__nv_bfloat16* dst, int ldk, int ntaps, const float* const* src, const float* const* scale, const int* params,
+              cudaStream_t st);
 
 DeviceArena::~DeviceArena() {
   for (void* p : ptrs_) cudaFree(p);
@@ -86,6 +88,9 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
   if (!wp) return 1;
   int koff = 0;
   double macs_per_pixel = 0;
+  auto rec_src = std::make_shared<std::vector<const float*>>();
+  auto rec_scale = std::make_shared<std::vector<const float*>>();
+  auto rec_par = std::make_shared<std::vector<int>>();
   for (const TapDef& t : taps) {
     const WeightSrc& w = *t.w;
     const int n_src = out_channels_of(w);
@@ -93,15 +98,17 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
     const int cpad = (t.C + kIgemmBK - 1) / kIgemmBK * kIgemmBK;
     const int ky = w.flip ? w.KH - 1 - t.ky : t.ky, kx = w.flip ? w.KW - 1 - t.kx : t.kx;
     if (int e = pack_tap(wp, ktotal, koff, w.w, n_src, t.C, cpad, w.KH, w.KW, ky, kx, w.transpose, w.scale, w.row_mul, w.row_off, st)) return e;
-    if (g_pack_recorder) {
-      const WeightSrc wc = w;
-      const int tC = t.C, ko = koff;
-      g_pack_recorder->push_back([=](cudaStream_t s) {
-        return pack_tap(wp, ktotal, ko, wc.w, n_src, tC, cpad, wc.KH, wc.KW, ky, kx, wc.transpose, wc.scale, wc.row_mul, wc.row_off, s);
-      });
-    }
+    rec_src->push_back(w.w);
+    rec_scale->push_back(w.scale);
+    for (int v : {koff, n_src, t.C, cpad, w.KH, w.KW, ky, kx, w.transpose, w.row_mul, w.row_off}) rec_par->push_back(v);
     koff += cpad;
     macs_per_pixel += static_cast<double>(t.C) * n_src;
+  }
+  if (g_pack_recorder) {  // training: one launch re-packs every tap of this plan from the fp32 master weights
+    const int nt = static_cast<int>(taps.size());
+    g_pack_recorder->push_back([=](cudaStream_t s) {
+      return pack_taps(wp, ktotal, nt, rec_src->data(), rec_scale->data(), rec_par->data(), s);
+    });
   }
   if (int e = igemm_make_bmap(&plan->maps.b, wp, N, ktotal, a.BN)) return e;
   // zero rows [n_src, N) if any (arena memory is uninitialised)

@@ -3,6 +3,8 @@
 // time-embedding MLP, weight packing, and NCHW<->NHWC converters.
 // Reference ops: unet_base.py:7-30 (get_time_embedding), :395-397 (t_proj), :96-98 (t_emb_layers), :399 (conv_in),
 // :449 (conv_out); resnet.py:142-145 (conv1+bn1+relu).
+#include <algorithm>
+
 #include "wc_host.h"
 #include "wc_ptx.cuh"
 
@@ -254,6 +256,34 @@ __global__ void pack_tap_kernel(__nv_bfloat16* __restrict__ dst, int ldk, int ko
   }
 }
 
+// All taps of one plan in one launch (blockIdx.y = tap): the per-step re-packing of the training plans.
+struct PackTapDesc {
+  const float* src;
+  const float* scale;
+  int koff, Nn, Cc, Cpad, KH, KW, ky, kx, transpose, row_mul, row_off, D1;
+};
+constexpr int kPackMaxTaps = 20;
+struct PackTapsArgs {
+  __nv_bfloat16* dst;
+  int ldk, ntaps;
+  PackTapDesc t[kPackMaxTaps];
+};
+__global__ void pack_taps_kernel(const __grid_constant__ PackTapsArgs a) {
+  const PackTapDesc t = a.t[blockIdx.y];
+  const size_t total = static_cast<size_t>(t.Nn) * t.Cpad;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % t.Cpad), n = static_cast<int>(i / t.Cpad);
+    float v = 0.f;
+    if (c < t.Cc) {
+      const size_t d0 = t.transpose ? c : static_cast<size_t>(n) * t.row_mul + t.row_off, d1 = t.transpose ? n : c;
+      v = t.src[((d0 * t.D1 + d1) * t.KH + t.ky) * t.KW + t.kx];
+      if (t.scale) v *= t.scale[d0];
+    }
+    a.dst[static_cast<size_t>(n) * a.ldk + t.koff + c] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
                                              int HW, int ldy) {
   const size_t total = static_cast<size_t>(B) * HW * C;
@@ -351,6 +381,28 @@ int pack_tap(__nv_bfloat16* dst, int ldk, int koff, const float* src, int Nn, in
   pack_tap_kernel<<<grid_for(static_cast<size_t>(Nn) * Cpad), 256, 0, st>>>(dst, ldk, koff, src, Nn, Cc, Cpad, KH, KW,
                                                                            ky, kx, transpose, scale, row_mul, row_off, 0,
                                                                            transpose ? Nn : Cc);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+// One launch for up to 20 taps; taps[i] = {src, scale, koff, Nn, Cc, Cpad, KH, KW, ky, kx, transpose, row_mul, row_off}
+int pack_taps(__nv_bfloat16* dst, int ldk, int ntaps, const float* const* src, const float* const* scale, const int* params /*[ntaps][11]*/,
+              cudaStream_t st) {
+  WC_REQUIRE(ntaps >= 1 && ntaps <= kPackMaxTaps, "pack_taps: tap count out of range");
+  PackTapsArgs a;
+  a.dst = dst; a.ldk = ldk; a.ntaps = ntaps;
+  size_t max_total = 0;
+  for (int i = 0; i < ntaps; ++i) {
+    const int* p = params + i * 11;
+    PackTapDesc& t = a.t[i];
+    t.src = src[i]; t.scale = scale[i];
+    t.koff = p[0]; t.Nn = p[1]; t.Cc = p[2]; t.Cpad = p[3]; t.KH = p[4]; t.KW = p[5]; t.ky = p[6]; t.kx = p[7];
+    t.transpose = p[8]; t.row_mul = p[9]; t.row_off = p[10];
+    t.D1 = t.transpose ? t.Nn : t.Cc;
+    max_total = std::max(max_total, static_cast<size_t>(t.Nn) * t.Cpad);
+  }
+  const int gx = static_cast<int>(std::min<size_t>((max_total + 255) / 256, 256));
+  pack_taps_kernel<<<dim3(gx, ntaps), 256, 0, st>>>(a);
   WC_LAUNCH_CHECK();
   return 0;
 }

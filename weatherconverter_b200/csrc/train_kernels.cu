@@ -43,38 +43,70 @@ __global__ void mse_finish_kernel(const double* __restrict__ part, int nparts, s
 // the input image; result index [co=wc][ci=nc]); SIGN = -1: conv_out (wide = its input activation, narrow = dpred;
 // result index [co=nc][ci=wc]).  Also wsum[wc] = sum_p wide[p][wc] and nsum[nc] = sum_p narrow[nc][p].
 constexpr int kBwThreads = 256;
+constexpr int kBwTile = 64;  // pixels of one image row per tile
+// Tile-based: a block stages 64 pixels x 64 channels of `wide` (as fp32) and the 3 x 3 rows x 66 pixels halo of `narrow`
+// in shared memory, then thread (wc, q) accumulates its 16 pixels from shared memory (wide: conflict-free, narrow:
+// broadcast).  Partials per block are reduced in a fixed order by the finish kernel (deterministic).
 __global__ void __launch_bounds__(kBwThreads)
 boundary_wgrad_kernel(const __nv_bfloat16* __restrict__ wide, int ldw, const float* __restrict__ narrow, int B, int H, int W,
-                      int sign, float* __restrict__ part /*[blocks][64*27 + 64 + 3]*/) {
+                      int sign, float* __restrict__ part /*[blocks][64*28 + 4]*/) {
+  __shared__ float s_wide[kBwTile][65];
+  __shared__ float s_nar[3][3][kBwTile + 2];
   __shared__ float red[kBwThreads / 64][64 * 28 + 4];
   const int wc = threadIdx.x & 63, q = threadIdx.x >> 6;  // q in 0..3
-  const size_t npix = static_cast<size_t>(B) * H * W;
   const size_t plane = static_cast<size_t>(H) * W;
+  const int tiles_x = (W + kBwTile - 1) / kBwTile;
+  const long ntiles = static_cast<long>(B) * H * tiles_x;
   float acc[27];
 #pragma unroll
   for (int i = 0; i < 27; ++i) acc[i] = 0.f;
   float wsum = 0.f, ns0 = 0.f, ns1 = 0.f, ns2 = 0.f;
-  for (size_t p = blockIdx.x * 4ull + q; p < npix; p += static_cast<size_t>(gridDim.x) * 4ull) {
-    const int b = static_cast<int>(p / plane);
-    const int rem = static_cast<int>(p % plane), y = rem / W, x = rem % W;
-    const float wv = __bfloat162float(wide[p * ldw + wc]);
-    wsum += wv;
-    const float* nb = narrow + static_cast<size_t>(b) * 3 * plane;
+  for (long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int x0 = static_cast<int>(t % tiles_x) * kBwTile;
+    const int y = static_cast<int>((t / tiles_x) % H), b = static_cast<int>(t / (static_cast<long>(tiles_x) * H));
+    __syncthreads();
+    // wide tile: 64 pixels x 64 channels, 8 channels (16 bytes) per thread and step
+    for (int i = threadIdx.x; i < kBwTile * 8; i += kBwThreads) {
+      const int px = i >> 3, v = i & 7;
+      float f[8];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + sign * (ky - 1);
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + sign * (kx - 1);
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          const size_t o = static_cast<size_t>(yy) * W + xx;
-          const float n0 = __ldg(nb + o), n1 = __ldg(nb + plane + o), n2 = __ldg(nb + 2 * plane + o);
-          acc[0 * 9 + ky * 3 + kx] = fmaf(wv, n0, acc[0 * 9 + ky * 3 + kx]);
-          acc[1 * 9 + ky * 3 + kx] = fmaf(wv, n1, acc[1 * 9 + ky * 3 + kx]);
-          acc[2 * 9 + ky * 3 + kx] = fmaf(wv, n2, acc[2 * 9 + ky * 3 + kx]);
-          if (ky == 1 && kx == 1) { ns0 += n0; ns1 += n1; ns2 += n2; }
-        }
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      if (x0 + px < W) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(wide + ((static_cast<size_t>(b) * H + y) * W + x0 + px) * ldw + v * 8));
+        float2 tt;
+        tt = unpack_bf16(u.x); f[0] = tt.x; f[1] = tt.y;
+        tt = unpack_bf16(u.y); f[2] = tt.x; f[3] = tt.y;
+        tt = unpack_bf16(u.z); f[4] = tt.x; f[5] = tt.y;
+        tt = unpack_bf16(u.w); f[6] = tt.x; f[7] = tt.y;
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_wide[px][v * 8 + j] = f[j];
+    }
+    // narrow halo: rows y-1..y+1, columns x0-1..x0+64, 3 channels (zero outside the image)
+    for (int i = threadIdx.x; i < 9 * (kBwTile + 2); i += kBwThreads) {
+      const int cx = i % (kBwTile + 2), r = (i / (kBwTile + 2)) % 3, nc = i / (3 * (kBwTile + 2));
+      const int yy = y + r - 1, xx = x0 + cx - 1;
+      float v = 0.f;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(narrow + (static_cast<size_t>(b) * 3 + nc) * plane + static_cast<size_t>(yy) * W + xx);
+      s_nar[nc][r][cx] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int px = q; px < kBwTile; px += 4) {
+      if (x0 + px >= W) break;
+      const float wv = s_wide[px][wc];
+      wsum += wv;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          // narrow pixel of tap (ky,kx): p + sign*(k-1)  ->  halo index (1 + sign*(k-1))
+          const int r = 1 + sign * (ky - 1), c = px + 1 + sign * (kx - 1);
+          acc[0 * 9 + ky * 3 + kx] = fmaf(wv, s_nar[0][r][c], acc[0 * 9 + ky * 3 + kx]);
+          acc[1 * 9 + ky * 3 + kx] = fmaf(wv, s_nar[1][r][c], acc[1 * 9 + ky * 3 + kx]);
+          acc[2 * 9 + ky * 3 + kx] = fmaf(wv, s_nar[2][r][c], acc[2 * 9 + ky * 3 + kx]);
+        }
+      if (wc == 0) { ns0 += s_nar[0][1][px + 1]; ns1 += s_nar[1][1][px + 1]; ns2 += s_nar[2][1][px + 1]; }
     }
   }
 #pragma unroll
