@@ -13,6 +13,8 @@
 // D_i = rowsum(dO_i o O_i) is precomputed (attn_rowdot).  Accumulators (S, dP, dV/dK or dQ) live in TMEM.
 // Outputs are written as bf16 into one [B, N, 3C] buffer (dQ | dK | dV per token), which is exactly the dY operand
 // of the in-projection's data / weight gradients.
+#include <cstdlib>
+
 #include "wc_host.h"
 #include "wc_ptx.cuh"
 
@@ -32,10 +34,12 @@ struct AttnBwdMaps {
   CUtensorMap r1, r2, t1, t2;
 };
 
-constexpr int kSoftmaxThreads = 256;  // warps 4-11: two warps per TMEM lane quadrant, interleaving the 32-column chunks
 constexpr int kPoly = 12;             // of every 32 exponentials, this many run on the FMA pipe (exp2_poly2)
 
-template <int HD, int BT, int STAGES, bool KV>
+// NSW = number of softmax warpgroups.  NSW == 2: one CTA per SM, two warps per TMEM lane quadrant interleave the
+// 32-column chunks.  NSW == 1 (head_dim <= 64, BT = 64): the CTA needs <= 256 TMEM columns and <= 113 KB of shared
+// memory, so TWO CTAs share an SM and one CTA's exp / dS phase overlaps the other's MMA phase.
+template <int HD, int BT, int STAGES, bool KV, int NSW>
 struct BwdCfg {
   static constexpr int kKBlocks = HD >= 64 ? HD / 64 : 1;
   static constexpr int kRowBytes = HD >= 64 ? 128 : HD * 2;
@@ -48,19 +52,24 @@ struct BwdCfg {
   static constexpr uint32_t kFixed = 2 * kRTile + STAGES * 2 * kTTile + kVecBytes + 1024 + 256;
   // P'/dS' tiles are double-buffered when shared memory allows it (then the softmax of tile i+1 never waits for the
   // dV/dK/dQ MMAs of tile i)
-  static constexpr int kPB = (kFixed + 2 * kNP * kPTile <= 232448) ? 2 : 1;
+  static constexpr int kCtasPerSm = NSW == 1 ? 2 : 1;
+  static constexpr uint32_t kSmemLimit = NSW == 1 ? 115712 : 232448;
+  static constexpr int kPB = (kFixed + 2 * kNP * kPTile <= kSmemLimit) ? 2 : 1;
   static constexpr uint32_t kSmem = kFixed + kPB * kNP * kPTile;
-  static constexpr int kThreads = 128 + kSoftmaxThreads;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 softmax / epilogue
+  static constexpr int kSoftmaxThreads = 128 * NSW;
+  static constexpr int kThreads = 128 + kSoftmaxThreads;  // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. softmax / epilogue
+  static constexpr int kCols = 2 * BT + (KV ? 2 : 1) * HD;
+  static constexpr uint32_t kTmemCols = kCols <= 128 ? 128 : (kCols <= 256 ? 256 : 512);
   static constexpr int kAcc0 = 2 * BT;                  // KV: dV ; Q: dQ
   static constexpr int kAcc1 = 2 * BT + (KV ? HD : 0);  // KV: dK
-  static_assert(2 * BT + (KV ? 2 : 1) * HD <= 512, "TMEM budget");
-  static_assert(kSmem <= 232448, "shared memory budget");
+  static_assert(kCols <= 512 && kTmemCols * kCtasPerSm <= 512, "TMEM budget");
+  static_assert(kSmem <= kSmemLimit, "shared memory budget");
 };
 
-template <int HD, int BT, int STAGES, bool KV>
-__global__ void __launch_bounds__(128 + kSoftmaxThreads, 1)
+template <int HD, int BT, int STAGES, bool KV, int NSW>
+__global__ void __launch_bounds__(128 + 128 * NSW, NSW == 1 ? 2 : 1)
 attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_constant__ AttnBwdArgs p) {
-  using Cfg = BwdCfg<HD, BT, STAGES, KV>;
+  using Cfg = BwdCfg<HD, BT, STAGES, KV, NSW>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -90,13 +99,13 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
     mbar_init(r_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 1); }
     mbar_init(s_full, 1);
-    mbar_init(p_full, kSoftmaxThreads);
+    mbar_init(p_full, Cfg::kSoftmaxThreads);
     mbar_init(acc_done(0), 1);
     mbar_init(acc_done(1), 1);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -200,7 +209,7 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
   } else if (warp >= 4) {
     // ===================== softmax-backward warps =====================
     const int quad = warp & 3;
-    const int grp = (warp - 4) >> 2;  // 0 or 1: which half of the interleaved 32-column chunks
+    const int grp = NSW == 2 ? (warp - 4) >> 2 : 0;  // which share of the interleaved 32-column chunks
     const int row = quad * 32 + lane;
     const int tid = threadIdx.x - 128;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
@@ -220,7 +229,7 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
           vl[tid] = t < p.ntok ? p.lse[voff + t] : INFINITY;
           vl[BT + tid] = t < p.ntok ? p.D[voff + t] : 0.f;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(128 * NSW) : "memory");
       }
       const uint32_t ds_row = p_smem + (i % Cfg::kPB) * (Cfg::kNP * Cfg::kPTile) + row * 128, pp_row = ds_row + Cfg::kPTile;
       mbar_wait(s_full, i & 1u);
@@ -228,8 +237,8 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
       const bool tail = !KV && (t0 + BT > p.ntok);
       bool p_free = (i < Cfg::kPB);  // first use of a P buffer needs no wait
 #pragma unroll
-      for (int cc = 0; cc < (NCH + 1) / 2; ++cc) {
-        const int c = 2 * cc + grp;
+      for (int cc = 0; cc < (NCH + NSW - 1) / NSW; ++cc) {
+        const int c = NSW * cc + grp;
         if (c >= NCH) break;
         uint32_t rs[32], rd[32];
         tmem_ld32(s_tmem + 32 * c, rs);
@@ -291,7 +300,7 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
     auto store_acc = [&](uint32_t taddr, int which, float mul) {
 #pragma unroll
       for (int c0 = 0; c0 < HD; c0 += 16) {
-        if (((c0 >> 4) & 1) != grp) continue;
+        if (NSW == 2 && ((c0 >> 4) & 1) != grp) continue;
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
         tmem_wait_ld();
@@ -322,7 +331,7 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -340,10 +349,10 @@ int make_head_map(CUtensorMap* m, const __nv_bfloat16* ptr, int hd, int ntok, in
   return encode_tmap_bf16(m, ptr, 4, dims, strides, box, hd >= 64 ? 128 : hd * 2);
 }
 
-template <int HD, int BT, int STAGES, bool KV>
+template <int HD, int BT, int STAGES, bool KV, int NSW>
 int launch_bwd(const BwdTensors& t, const float* lse, const float* D, __nv_bfloat16* dqkv, int ld3, int B, int heads, int ntok,
                cudaStream_t st) {
-  using Cfg = BwdCfg<HD, BT, STAGES, KV>;
+  using Cfg = BwdCfg<HD, BT, STAGES, KV, NSW>;
   AttnBwdMaps maps;
   const uint64_t sh = static_cast<uint64_t>(ntok) * HD, sb = sh * heads;
   const uint64_t dsb = static_cast<uint64_t>(ntok) * t.ldd;
@@ -365,22 +374,31 @@ int launch_bwd(const BwdTensors& t, const float* lse, const float* D, __nv_bfloa
   a.lse = lse; a.D = D; a.dqkv = dqkv;
   static bool attr_set = false;
   if (!attr_set) {
-    WC_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<HD, BT, STAGES, KV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<HD, BT, STAGES, KV, NSW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;
   }
   dim3 grid((ntok + 127) / 128, B * heads);
   const double flops = (KV ? 8.0 : 6.0) * B * heads * static_cast<double>(ntok) * ntok * HD;
   ProfScope prof(kProfAttention, st, flops);
-  attention_bwd_kernel<HD, BT, STAGES, KV><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, a);
+  attention_bwd_kernel<HD, BT, STAGES, KV, NSW><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, a);
   WC_LAUNCH_CHECK();
   return 0;
 }
 
-template <int HD, int BT, int SKV, int SQ>
+template <int HD, int BT, int SKV, int SQ, int NSW>
 int launch_both(const BwdTensors& t, const float* lse, const float* D, __nv_bfloat16* dqkv, int ld3, int B, int heads, int ntok,
                 cudaStream_t st) {
-  if (int e = launch_bwd<HD, BT, SKV, true>(t, lse, D, dqkv, ld3, B, heads, ntok, st)) return e;
-  return launch_bwd<HD, BT, SQ, false>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
+  if (int e = launch_bwd<HD, BT, SKV, true, NSW>(t, lse, D, dqkv, ld3, B, heads, ntok, st)) return e;
+  return launch_bwd<HD, BT, SQ, false, NSW>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
+}
+
+bool two_cta() {  // WC_ATTN_BWD_2CTA=0 selects the one-CTA-per-SM variant for head_dim <= 64 (tuning knob)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WC_ATTN_BWD_2CTA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 }  // namespace
@@ -393,11 +411,14 @@ int attention_backward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   WC_REQUIRE(ntok % 8 == 0 && ldd % 8 == 0 && ld3 % 8 == 0, "attention backward: strides / token count must be multiples of 8");
   BwdTensors t{q, k, v, d_o, ldd};
   switch (hd) {
-    case 16: return launch_both<16, 128, 2, 2>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
-    case 32: return launch_both<32, 128, 2, 2>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
-    case 64: return launch_both<64, 128, 2, 2>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
-    case 128: return launch_both<128, 128, 1, 1>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
-    case 192: return launch_both<192, 64, 1, 2>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
+    case 16: return two_cta() ? launch_both<16, 64, 2, 2, 1>(t, lse, D, dqkv, ld3, B, heads, ntok, st)
+                              : launch_both<16, 128, 2, 2, 2>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
+    case 32: return two_cta() ? launch_both<32, 64, 2, 2, 1>(t, lse, D, dqkv, ld3, B, heads, ntok, st)
+                              : launch_both<32, 128, 2, 2, 2>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
+    case 64: return two_cta() ? launch_both<64, 64, 2, 2, 1>(t, lse, D, dqkv, ld3, B, heads, ntok, st)
+                              : launch_both<64, 128, 2, 2, 2>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
+    case 128: return launch_both<128, 128, 1, 1, 2>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
+    case 192: return launch_both<192, 64, 1, 2, 2>(t, lse, D, dqkv, ld3, B, heads, ntok, st);
     default: return fail("attention backward: unsupported head_dim " + std::to_string(hd));
   }
 }
