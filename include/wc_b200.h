@@ -117,6 +117,28 @@ int wc_nhwc_bf16_to_nchw_f32(const wc_bf16* x, float* y, int batch, int C, int h
 int wc_attention(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, int batch, int heads, int ntok,
                  int hd, int ldo, void* stream);
 
+/* ---- image / label edges of the loop: byte-exact replacements of the host-side PIL / numpy / torchvision
+ * steps right before and after the path.  *_host pointers are HOST memory (three floats). ------------------------------ */
+/* sample_ddpm.py:47-51: clamp(-1,1), (x+1)/2, make_grid(nrow, padding 2, pad_value 0), ToPILImage -> HWC uint8 grid
+ * [(H+pad)*ceil(B/nrow)+pad][(W+pad)*min(nrow,B)+pad][3] (a batch of one image is returned unpadded, as make_grid does). */
+int wc_ddpm_grid_u8(const float* x, uint8_t* out, int batch, int H, int W, int nrow, int padding, void* stream);
+/* sample_integrated.py:32-37 postprocess: (x*std + mean)*255 -> clamp(0,255) -> uint8, NCHW. */
+int wc_postprocess_u8(const float* x, uint8_t* out, int batch, int H, int W, const float* mean3_host, const float* std3_host, void* stream);
+/* seg_model/inference.py:75-78,103 + acdc.py:135-138: labelIds uint8 [Hs,Ws] -> NEAREST resize (source row / column index
+ * tables ytab[Hr], xtab[Wr], built on the host exactly as Pillow does) -> centre crop (top, left, Hc, Wc) -> id_to_train_id
+ * LUT -> int64 [Hc,Wc]. */
+int wc_label_encode(const uint8_t* label_ids, int Ws, const int* ytab, const int* xtab, int top, int left, int Hc, int Wc,
+                    const int64_t* lut, int nlut, int64_t* out, void* stream);
+/* Pillow's 8-bit two-pass resampling (Image.resize with BILINEAR/antialias; translation.py:140): HWC uint8 in -> HWC uint8
+ * out; bounds_* [2*n] and kk_* [n*ksize] are the per-output (first tap, tap count) pairs and the 22-bit fixed-point
+ * coefficients (weatherconverter_b200/image_io.py builds them as Resample.c does); tmp is [Hin,Wout,C]. */
+int wc_resample_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, int Hin, int Win, int Hout, int Wout, int channels, const int* bounds_h,
+                   const int* kk_h, int ksize_h, const int* bounds_v, const int* kk_v, int ksize_v, void* stream);
+/* centre crop + ToTensor (+ x*2-1 when mode == 0, translation.py:141-143; + ExtNormalize(mean, std) when mode == 1,
+ * seg_model/inference.py:79-80): HWC uint8 [.,Win,3] -> CHW f32 [3,Hc,Wc]. */
+int wc_u8_to_tensor(const uint8_t* in, int Win, int top, int left, int Hc, int Wc, int mode, const float* mean3_host, const float* std3_host,
+                    float* out, void* stream);
+
 /* ---- training-step building blocks (diffusion_model/train_ddpm.py:95-114: what loss.backward() and
  * optimizer.step() compute; the model-level wc_unet_train_* calls below use the same kernels) ------------------ */
 /* wc_attention that also writes lse [B*heads][ntok] (log2-domain log-sum-exp of every softmax row). */

@@ -295,8 +295,62 @@ def g_legacy():
     save("legacy_unet.pt", out)
 
 
+def g_io():
+    """Image / label edges, produced by the reference's own transforms (seg_model/utils/ext_transforms.py,
+    acdc.encode_target, sample_integrated.postprocess) and by the exact PIL / torchvision calls of translation.py:138-145
+    and sample_ddpm.py:47-51."""
+    import numpy as np
+    from PIL import Image
+    import torchvision
+    from torchvision import transforms
+    from torchvision.utils import make_grid
+    from seg_model.datasets.acdc import ACDCDataset
+    from seg_model.utils.ext_transforms import ExtCompose, ExtResize, ExtCenterCrop, ExtToTensor, ExtNormalize
+    from diffusion_model.sample_integrated import postprocess
+    rng = np.random.default_rng(2024)
+    out = {}
+    # --- seg preprocessing (inference.py:75-82,103-104): label ids 0..33 in 16x16 blocks + a small image
+    lab = np.kron(rng.integers(0, 34, (68, 120), dtype=np.uint8), np.ones((16, 16), dtype=np.uint8))[:1080, :1920]
+    lab = (lab + (rng.random(lab.shape) < 0.02) * 1).clip(0, 33).astype(np.uint8)
+    img_small = rng.integers(0, 256, (96, 160, 3), dtype=np.uint8)
+    val_transform = ExtCompose([ExtResize(size=(1080 // 2, 1920 // 2), interpolation=Image.BILINEAR, just_label=True),
+                                ExtCenterCrop(size=(512, 512), just_label=True), ExtToTensor(),
+                                ExtNormalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    input_tensor, lbl_tensor = val_transform(Image.fromarray(img_small), Image.fromarray(lab))
+    enc = torch.from_numpy(np.array(ACDCDataset.encode_target(lbl_tensor))).unsqueeze(0).long()
+    out["label_ids"] = torch.from_numpy(lab)
+    out["encoded_label"] = enc.to(torch.uint8)            # train ids 0..18 / 255 fit a byte (kept small)
+    out["image_small"] = torch.from_numpy(img_small)
+    out["normalized"] = input_tensor.unsqueeze(0)
+    # --- diffusion input (translation.py:138-145)
+    tf = transforms.Compose([transforms.Resize(128, transforms.InterpolationMode.BILINEAR), transforms.CenterCrop(128),
+                             transforms.ToTensor(), transforms.Lambda(lambd=lambda x: x * 2.0 - 1.0)])
+    out["diffusion_inputs"] = []
+    for (h, w) in ((405, 720), (333, 500), (200, 150)):
+        im = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        im = np.clip(im // 3 + np.linspace(0, 160, w, dtype=np.int64)[None, :, None], 0, 255).astype(np.uint8)   # gradients + noise
+        out["diffusion_inputs"].append(dict(image=torch.from_numpy(im), tensor=tf(Image.fromarray(im)).unsqueeze(0)))
+    # --- sample_ddpm.py:47-51
+    g = torch.Generator().manual_seed(8)
+    xt = torch.randn(5, 3, 24, 40, generator=g) * 0.8
+    ims = torch.clamp(xt, -1., 1.).detach().cpu()
+    ims = (ims + 1) / 2
+    grid = make_grid(ims, nrow=2)
+    img = torchvision.transforms.ToPILImage()(grid)
+    out["ddpm_xt"], out["ddpm_grid"] = xt, torch.from_numpy(np.array(img))
+    grid1 = make_grid(ims[:1], nrow=2)
+    out["ddpm_grid_single"] = torch.from_numpy(np.array(torchvision.transforms.ToPILImage()(grid1)))
+    # --- sample_integrated.postprocess
+    xl = torch.randn(2, 3, 16, 24, generator=g) * 2.0
+    out["legacy_xt"], out["legacy_u8"] = xl, postprocess(xl)
+    save("image_io.pt", out)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    if only == ["io"]:
+        g_io()
+        sys.exit(0)
     if only == ["train"]:
         g_train()
         sys.exit(0)
@@ -311,3 +365,4 @@ if __name__ == "__main__":
     g_gsg_and_driver(G)
     g_train()
     g_legacy()
+    g_io()

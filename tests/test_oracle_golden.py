@@ -131,3 +131,18 @@ def test_legacy_unet(golden):
             mean, sz, _ = s.sample_prev_timestep2(xt, eps, t, z=d["zs"][i])
             xt = mean + sz if i != 0 else mean
             assert (xt - d["traj"][k]).abs().max() < 1e-3 * d["traj"][k].abs().max(), k
+
+
+def test_image_io(golden):
+    """oracle.image_io (numpy restatement incl. Pillow's resampling) vs tensors produced by the reference's own transforms."""
+    import numpy as np
+    from oracle import image_io as io
+    d = golden("image_io.pt")
+    enc = io.encode_label(d["label_ids"].numpy())
+    assert np.array_equal(enc, d["encoded_label"].numpy().astype(np.int64))
+    assert np.array_equal(io.normalize_image(d["image_small"].numpy()), d["normalized"].numpy())
+    for e in d["diffusion_inputs"]:
+        assert np.array_equal(io.diffusion_input(e["image"].numpy()), e["tensor"].numpy())
+    assert np.array_equal(io.ddpm_grid_uint8(d["ddpm_xt"].numpy(), 2), d["ddpm_grid"].numpy())
+    assert np.array_equal(io.ddpm_grid_uint8(d["ddpm_xt"].numpy()[:1], 2), d["ddpm_grid_single"].numpy())
+    assert np.array_equal(io.postprocess_uint8(d["legacy_xt"].numpy()), d["legacy_u8"].numpy())

@@ -64,6 +64,14 @@ int boundary_wgrad(const __nv_bfloat16* wide, int ldw, const float* narrow, int 
                    float* dbias, void* scratch, cudaStream_t st);
 int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, int step,
               float grad_scale, cudaStream_t st);
+int ddpm_grid_u8(const float* x, uint8_t* out, int B, int H, int W, int nrow, int pad, cudaStream_t st);
+int postprocess_u8(const float* x, uint8_t* out, int B, int H, int W, const float* mean3, const float* std3, cudaStream_t st);
+int label_encode(const uint8_t* lab, int Ws, const int* ytab, const int* xtab, int top, int left, int Hc, int Wc, const long long* lut,
+                 int nlut, long long* out, cudaStream_t st);
+int resample_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, int Hin, int Win, int Hout, int Wout, int C, const int* bounds_h,
+                const int* kk_h, int ksize_h, const int* bounds_v, const int* kk_v, int ksize_v, cudaStream_t st);
+int u8_to_tensor(const uint8_t* in, int Win, int top, int left, int Hc, int Wc, int mode, const float* mean3, const float* std3, float* out,
+                 cudaStream_t st);
 }  // namespace wc
 
 using namespace wc;
@@ -279,6 +287,27 @@ int wc_boundary_wgrad(const wc_bf16* wide, const float* narrow, int batch, int H
 int wc_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, int step,
                  float grad_scale, void* stream) {
   return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, step, grad_scale, S(stream));
+}
+
+
+int wc_ddpm_grid_u8(const float* x, uint8_t* out, int batch, int H, int W, int nrow, int padding, void* stream) {
+  return ddpm_grid_u8(x, out, batch, H, W, nrow, padding, S(stream));
+}
+int wc_postprocess_u8(const float* x, uint8_t* out, int batch, int H, int W, const float* mean3_host, const float* std3_host, void* stream) {
+  return postprocess_u8(x, out, batch, H, W, mean3_host, std3_host, S(stream));
+}
+int wc_label_encode(const uint8_t* label_ids, int Ws, const int* ytab, const int* xtab, int top, int left, int Hc, int Wc,
+                    const int64_t* lut, int nlut, int64_t* out, void* stream) {
+  return label_encode(label_ids, Ws, ytab, xtab, top, left, Hc, Wc, reinterpret_cast<const long long*>(lut), nlut,
+                      reinterpret_cast<long long*>(out), S(stream));
+}
+int wc_resample_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, int Hin, int Win, int Hout, int Wout, int channels, const int* bounds_h,
+                   const int* kk_h, int ksize_h, const int* bounds_v, const int* kk_v, int ksize_v, void* stream) {
+  return resample_u8(in, tmp, out, Hin, Win, Hout, Wout, channels, bounds_h, kk_h, ksize_h, bounds_v, kk_v, ksize_v, S(stream));
+}
+int wc_u8_to_tensor(const uint8_t* in, int Win, int top, int left, int Hc, int Wc, int mode, const float* mean3_host, const float* std3_host,
+                    float* out, void* stream) {
+  return u8_to_tensor(in, Win, top, left, Hc, Wc, mode, mean3_host, std3_host, out, S(stream));
 }
 
 }  // extern "C"

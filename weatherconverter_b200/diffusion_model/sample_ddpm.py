@@ -57,12 +57,10 @@ def sample(model, scheduler: LinearNoiseScheduler, train_config: TrainingConfig,
     xt = sample_tensor(model, scheduler,
                        (train_config.sample_size, model_config.im_channels, model_config.im_size, model_config.im_size),
                        num_timesteps=diffusion_config.num_timesteps)
-    ims = torch.clamp(xt, -1., 1.).detach().cpu()
-    ims = (ims + 1) / 2
-    import torchvision
-    from torchvision.utils import make_grid
-    grid = make_grid(ims, nrow=train_config.num_grid_rows)
-    img = torchvision.transforms.ToPILImage()(grid)
+    # reference :47-51 (clamp, (x+1)/2, make_grid, ToPILImage) as one byte-exact kernel; only the uint8 grid crosses PCIe
+    from PIL import Image
+    from ..image_io import ddpm_grid_uint8
+    img = Image.fromarray(ddpm_grid_uint8(xt, train_config.num_grid_rows).cpu().numpy())
     os.makedirs(save_path, exist_ok=True)
     now = datetime.now()
     img.save(os.path.join(save_path, f'x_410{now.hour}{now.minute}{now.second}.png'))

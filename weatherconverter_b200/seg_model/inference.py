@@ -32,6 +32,24 @@ def load_model(model_path, model_config) -> torch.nn.Module:
     return model
 
 
+def preprocess(ori_img_path: str, img_path: str, gt_label_ids_path: str, gt_color_path: str, verbose=False):
+    """Reference :60-116 with the tensor work on the GPU (byte-exact, weatherconverter_b200/image_io.py): PNG decoding stays
+    on the host (PIL), then ExtToTensor + ExtNormalize of the image, NEAREST resize (540, 960) + centre crop 512 + labelIds ->
+    trainIds of the label run as kernels.  Returns (original_image PIL 512, input_tensor [1,3,H,W], encoded_label_tensor
+    [1,512,512] int64, lbl_colored_img PIL 512) like the reference."""
+    from PIL import Image
+    import torchvision.transforms as T
+    from .. import image_io
+    img = Image.open(img_path).convert("RGB")
+    ori_img = Image.open(ori_img_path).convert("RGB")
+    label = Image.open(gt_label_ids_path)
+    label_colored = Image.open(gt_color_path)
+    input_tensor = image_io.normalize_image(torch.from_numpy(np.array(img)).to(device))
+    encoded_label_tensor = image_io.encode_label(torch.from_numpy(np.array(label, dtype=np.uint8)).to(device))
+    host_tf = T.Compose([T.Resize(size=(1080 // 2, 1920 // 2), interpolation=Image.BILINEAR), T.CenterCrop(size=(512, 512))])
+    return host_tf(ori_img), input_tensor, encoded_label_tensor, host_tf(label_colored)   # the two PIL outputs are display-only
+
+
 def infer_batch(model, input_tensor, encoded_label_tensor, want_grad=True, grad_pool=1):
     """Batched, stream-ordered: returns dict(pred int64 [B,H,W], grad [B,3,H,W], loss [B]); image b's loss is the CE
     mean over its own valid pixels, i.e. a vmap of the reference's B = 1 call."""

@@ -19,6 +19,16 @@ LAMBDA = 60.0
 N_STEPS = 500
 
 
+def load_input_image(path: str, image_size: int = 128) -> torch.Tensor:
+    """translation.py:131,138-145: open the RGB image (host, PIL decode) and run Resize(BILINEAR) + CenterCrop + ToTensor +
+    x*2-1 on the GPU, bit-identical to the reference's torchvision/PIL transform (weatherconverter_b200/image_io.py)."""
+    import numpy as np
+    from PIL import Image
+    from . import image_io
+    img = torch.from_numpy(np.array(Image.open(path).convert("RGB"))).to(device)
+    return image_io.diffusion_input(img, image_size)
+
+
 @torch.no_grad()
 def sample_with_sgg(input_tensor, diff_model, diff_scheduler, seg_model, gt, srgan_model, *, n_steps=N_STEPS,
                     lam=LAMBDA, noise=None, t_forward=None, step_noise=None, device_noise=False, generator=None,
