@@ -18,14 +18,10 @@ device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
 
 
 def postprocess(xt, mean=[0.4865, 0.4998, 0.4323], std=[0.2326, 0.2276, 0.2659]):
-    """Reference :32-37: de-normalise, scale to 0..255, uint8 on the host (one byte-exact kernel when xt is on the GPU)."""
-    if xt.is_cuda:
-        from ..image_io import postprocess_uint8
-        return postprocess_uint8(xt, mean, std).cpu()
-    mean = torch.tensor(mean, device=xt.device).view(1, -1, 1, 1)
-    std = torch.tensor(std, device=xt.device).view(1, -1, 1, 1)
-    images = xt * std + mean
-    return (images * 255).clamp(0, 255).type(torch.uint8).detach().cpu()
+    """Reference :32-37: de-normalise, scale to 0..255, clamp, uint8, to the host — one byte-exact kernel on the GPU
+    (raises for CPU tensors: there is no CPU path)."""
+    from ..image_io import postprocess_uint8
+    return postprocess_uint8(xt, mean, std).cpu()
 
 
 @torch.no_grad()
