@@ -46,15 +46,6 @@ bool row3_enabled() {
   return v == 1;
 }
 
-bool wres_enabled() {  // WC_WRES=0 disables the resident-weights mode (tuning knob)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WC_WRES");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
 struct TapDef {
   int map, dy, dx;
   const WeightSrc* w;
@@ -212,8 +203,7 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   }
   if (int e = finish_plan(&plan, arena, taps, B, H, W, tb, th, tw, N, ep, out, out.up, out.up, out.py, out.px, st)) return e;
   plan.args.row3 = (want_row3 && plan.args.BN <= 128) ? row3_mode() : 0;
-  plan.args.wres = (wres_enabled() && igemm_weights_fit_resident(N, plan.args.BN, plan.args.total_kb, plan.args.row3)) ? 1 : 0;
-  plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3, plan.args.wres, plan.args.total_kb);
+  plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3);
   { const char* e = getenv("WC_IGEMM_DBG"); plan.args.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("WC_IGEMM_TRACE"); plan.args.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   op->flops = plan.flops;
@@ -240,8 +230,7 @@ int build_conv_transposed_s2(ConvOp* op, DeviceArena* arena, const Act& x, const
       if (int e = igemm_make_amap(&plan.maps.a[0], x, tb, th, tw)) return e;
       for (int i = 1; i < kMaxMaps; ++i) plan.maps.a[i] = plan.maps.a[0];
       if (int e = finish_plan(&plan, arena, taps, x.B, x.H, x.W, tb, th, tw, N, ep, out, 2, 2, qy, qx, st)) return e;
-      plan.args.wres = (wres_enabled() && igemm_weights_fit_resident(N, plan.args.BN, plan.args.total_kb, 0)) ? 1 : 0;
-      plan.args.nstages = igemm_stages_for(plan.args.BN, 0, plan.args.wres, plan.args.total_kb);
+      plan.args.nstages = igemm_stages_for(plan.args.BN, 0);
       op->flops += plan.flops;
     }
   return 0;

@@ -193,12 +193,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   // flight per SM (these layers are TMA-latency bound, not tensor bound).
   constexpr uint32_t kAOff = ROW3 ? kRowABytes : kABytes;   // offset of the B tile(s) inside a stage
   const int kStages = p.nstages;
-  const uint32_t kBTile = static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
-  const uint32_t kStageSz = p.wres ? kAOff : kAOff + (ROW3 ? 3u : 1u) * kBTile;
+  const uint32_t kStageSz = kAOff + (ROW3 ? 3u : 1u) * static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  // resident weights (wres): [total_kb] tiles of BN x 64 at the END of the ring area
-  const uint32_t wres_base = smem_base + kPipeBytes - static_cast<uint32_t>(p.total_kb) * kBTile;
-  const uint32_t wres_bar = smem_base + kPipeBytes + 8u * (2 * kMaxStages + 5);
   const uint32_t bar_base = smem_base + kPipeBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -241,7 +237,6 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 256);
       }
-      mbar_init(wres_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -275,11 +270,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kABytes + (p.wres ? 0u : kBTile);
-      if (p.wres && blockIdx.x < total_tiles) {   // one-time load of the whole weight matrix (n_tiles == 1)
-        mbar_arrive_expect_tx(wres_bar, static_cast<uint32_t>(p.total_kb) * kBTile);
-        for (int kb = 0; kb < p.total_kb; ++kb) tma_load_2d(wres_base + kb * kBTile, &maps.b, wres_bar, kb * kIgemmBK, 0);
-      }
+      const uint32_t tx_bytes = kABytes + static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n0, b0, y0, x0;
         decode(tile, n0, b0, y0, x0);
@@ -294,9 +285,9 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
               mbar_wait(empty_bar(stage), phase ^ 1u);
               trace(0, 1);
               const uint32_t sa = smem_base + stage * kStageSz;
-              mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0u : kRowSegPixels * 128u) + (((p.dbg & 4) || p.wres) ? 0u : 3u * b_bytes));
+              mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0u : kRowSegPixels * 128u) + ((p.dbg & 4) ? 0u : 3u * b_bytes));
               if (!(p.dbg & 8)) tma_load_4d(sa, &maps.a[2], full_bar(stage), kb * kIgemmBK, x0 - 1, y0 + ky - 1, b0);
-              for (int kx = 0; kx < 3 && !(p.dbg & 4) && !p.wres; ++kx)
+              for (int kx = 0; kx < 3 && !(p.dbg & 4); ++kx)
                 tma_load_2d(sa + kAOff + kx * b_bytes, &maps.b, full_bar(stage), ((ky * 3 + kx) * nkb + kb) * kIgemmBK, n0);
               trace(0, 2);
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -312,7 +303,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             const uint32_t sa = smem_base + stage * kStageSz;
             mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
             tma_load_4d(sa, amap, full_bar(stage), kb * kIgemmBK, x0 + tap.dx, y0 + tap.dy, b0);
-            if (!p.wres) tma_load_2d(sa + kAOff, &maps.b, full_bar(stage), kb_global * kIgemmBK, n0);
+            tma_load_2d(sa + kAOff, &maps.b, full_bar(stage), kb_global * kIgemmBK, n0);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -325,15 +316,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       // descriptor pieces (see umma_desc_join): constant high word, low words for stage 0, per-stage increment
       const uint64_t d0 = umma_smem_desc(smem_base, 128, 1024);
       const uint32_t dhi = umma_desc_hi(d0), a_lo0 = umma_desc_lo(d0), b_lo0 = a_lo0 + (kAOff >> 4);
-      const uint32_t stage16 = kStageSz >> 4, bt16 = kBTile >> 4;
-      const uint32_t wres_lo = a_lo0 + ((wres_base - smem_base) >> 4);
+      const uint32_t stage16 = kStageSz >> 4, bt16 = (static_cast<uint32_t>(p.BN) * kIgemmBK * 2) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      if (p.wres && blockIdx.x < total_tiles) {
-        mbar_wait(wres_bar, 0);
-        tc_fence_after();
-      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int a = it & 1;
         const uint32_t aphase = (it >> 1) & 1u;
@@ -348,18 +334,14 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             mbar_wait(full_bar(stage), phase);
             trace(1, 11);
             tc_fence_after();
-            const uint32_t a_lo = a_lo0 + stage * stage16;
-            // resident weights: tile index of tap (ky, kx), channel block kb is (ky*3 + kx)*nkb + kb with sg = ky*nkb + kb
-            const int nkb_ = p.taps[0].nkb;
-            const uint32_t b_lo = p.wres ? wres_lo + static_cast<uint32_t>((sg / nkb_) * 3 * nkb_ + (sg % nkb_)) * bt16 : b_lo0 + stage * stage16;
-            const uint32_t b_kx = p.wres ? static_cast<uint32_t>(nkb_) * bt16 : bt16;
+            const uint32_t a_lo = a_lo0 + stage * stage16, b_lo = b_lo0 + stage * stage16;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
               // window of 128 pixels starting kx pixels (kx*128 B = 8 descriptor units) into the 130-pixel segment; the
               // UMMA swizzle is a function of the absolute shared-memory address, so the shifted start needs no fix-up
 #pragma unroll
               for (int k = 0; k < kIgemmBK / 16; ++k)
-                umma_bf16(d_tmem, umma_desc_join(a_lo + 8u * kx + 2u * k, dhi), umma_desc_join(b_lo + kx * b_kx + 2u * k, dhi), idesc,
+                umma_bf16(d_tmem, umma_desc_join(a_lo + 8u * kx + 2u * k, dhi), umma_desc_join(b_lo + kx * bt16 + 2u * k, dhi), idesc,
                           (sg | kx | k) != 0 ? 1u : 0u);
             }
             umma_commit(empty_bar(stage));
@@ -371,8 +353,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         for (int ks = ks_first; ks < p.total_kb; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + stage * stage16;
-          const uint32_t b_lo = p.wres ? wres_lo + static_cast<uint32_t>(ks) * bt16 : b_lo0 + stage * stage16;
+          const uint32_t a_lo = a_lo0 + stage * stage16, b_lo = b_lo0 + stage * stage16;
 #pragma unroll
           for (int k = 0; k < kIgemmBK / 16; ++k)
             umma_bf16(d_tmem, umma_desc_join(a_lo + 2u * k, dhi), umma_desc_join(b_lo + 2u * k, dhi), idesc, (ks | k) != 0 ? 1u : 0u);
@@ -418,20 +399,11 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
 
 }  // namespace
 
-int igemm_stages_for(int BN, int row3, int wres, int total_kb) {
-  const uint32_t btile = static_cast<uint32_t>(BN) * kIgemmBK * 2;
-  const uint32_t stage = (row3 ? kRowABytes : kABytes) + (wres ? 0u : (row3 ? 3u : 1u) * btile);
+int igemm_stages_for(int BN, int row3) {
+  const uint32_t stage = (row3 ? kRowABytes : kABytes) + (row3 ? 3u : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2;
   // stages must stay 1024-byte aligned: BN is a multiple of 16 -> BN*128 is a multiple of 2048
-  const uint32_t avail = kPipeBytes - (wres ? static_cast<uint32_t>(total_kb) * btile : 0u);
-  int n = static_cast<int>(avail / stage);
+  int n = static_cast<int>(kPipeBytes / stage);
   return n > kMaxStages ? kMaxStages : n;
-}
-
-bool igemm_weights_fit_resident(int N, int BN, int total_kb, int row3) {
-  if (N > BN) return false;                                   // every tile must use the same weight rows
-  const uint32_t w = static_cast<uint32_t>(total_kb) * BN * kIgemmBK * 2;
-  const uint32_t stage = row3 ? kRowABytes : kABytes;
-  return w <= kPipeBytes && (kPipeBytes - w) / stage >= 4;    // keep at least 4 activation stages in flight
 }
 
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {

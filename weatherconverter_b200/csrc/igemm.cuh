@@ -41,9 +41,6 @@ struct IgemmArgs {
   int dbg;      // debug/experiment bits (WC_IGEMM_DBG): 1 skip epilogue global stores, 2 skip MMA issue, 4 skip B loads
   int nstages;  // depth of the TMA ring (set by igemm_stages_for)
   int row3;  // 1: taps 0..8 form a 3x3 stride-1 window executed in row-segment mode (see igemm.cu)
-  int wres;  // 1: the whole packed weight matrix (N <= BN, total_kb * BN * 128 bytes) is loaded ONCE per CTA and stays
-             // resident in shared memory; the TMA ring then carries only activation tiles (narrow layers are L2-bound on
-             // the per-tile weight re-load otherwise)
   IgemmTap taps[kMaxTaps];
   // epilogue
   const float* bias;     // [N] or nullptr
@@ -79,8 +76,7 @@ struct IgemmPlan {
 };
 
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
-int igemm_stages_for(int BN, int row3, int wres = 0, int total_kb = 0);
-bool igemm_weights_fit_resident(int N, int BN, int total_kb, int row3);
+int igemm_stages_for(int BN, int row3);
 
 // Choose the M-tile shape for a (B,H,W) grid: widest power-of-two span of x, then y, then b.
 void igemm_pick_tile(int B, int H, int W, int* tb, int* th, int* tw);
