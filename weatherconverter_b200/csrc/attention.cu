@@ -33,7 +33,9 @@ struct AttnMaps {
   CUtensorMap q, k, vt;
 };
 
-template <int HD, int BKV, int NQ>
+// TP: P lives in TENSOR MEMORY (written by the softmax threads with tcgen05.st, read by the PV tcgen05.mma as its A operand:
+// lane = query row, two bf16 per 32-bit column) instead of shared memory.
+template <int HD, int BKV, int NQ, bool TP = false>
 struct AttnCfg {
   static constexpr int kKBlocks = HD >= 64 ? HD / 64 : 1;          // 64-wide K blocks of the QK^T contraction
   static constexpr int kSwz = HD >= 64 ? 128 : HD * 2;             // swizzle span of Q/K rows (bytes)
@@ -44,24 +46,25 @@ struct AttnCfg {
   static constexpr uint32_t kVTile = HD * BKV * 2;
   static constexpr uint32_t kPTile = 128 * BKV * 2;
   static constexpr int kStages = 2;
-  static constexpr uint32_t kSmem = NQ * kQTile + kStages * (kKTile + kVTile) + NQ * kPTile + 1024 + 256;
+  static constexpr uint32_t kSmem = NQ * kQTile + kStages * (kKTile + kVTile) + (TP ? 0 : NQ * kPTile) + 1024 + 256;
   static constexpr int kThreads = 128 + 128 * NQ;
-  static constexpr int kColsPerQ = BKV + HD;
+  static constexpr int kColsPerQ = BKV + HD + (TP ? BKV / 2 : 0);
+  static_assert(NQ * kColsPerQ <= 512, "TMEM budget");
   static constexpr uint32_t kTmemCols = NQ * kColsPerQ <= 256 ? 256 : 512;
 };
 
 // POLY: of every 32 exponentials, this many run on the FMA pipe (even)
-template <int HD, int BKV, int NQ, int POLY>
-__global__ void __launch_bounds__(AttnCfg<HD, BKV, NQ>::kThreads, 1)
+template <int HD, int BKV, int NQ, int POLY, bool TP>
+__global__ void __launch_bounds__(AttnCfg<HD, BKV, NQ, TP>::kThreads, 1)
 attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ AttnArgs p) {
-  using Cfg = AttnCfg<HD, BKV, NQ>;
+  using Cfg = AttnCfg<HD, BKV, NQ, TP>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_smem = base;
   const uint32_t k_smem = q_smem + NQ * Cfg::kQTile;
   const uint32_t v_smem = k_smem + Cfg::kStages * Cfg::kKTile;
   const uint32_t p_smem = v_smem + Cfg::kStages * Cfg::kVTile;
-  const uint32_t bars = p_smem + NQ * Cfg::kPTile;
+  const uint32_t bars = p_smem + (TP ? 0u : NQ * Cfg::kPTile);
   // barrier map (8 bytes each)
   const uint32_t q_full = bars;
   auto k_full = [&](int s) { return bars + 8u * (1 + s); };
@@ -157,8 +160,12 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
         for (int vb = 0; vb < BKV / 64; ++vb) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(d, umma_desc_join(p_lo + vb * ((128 * 128) >> 4) + 2u * k, hi_pv),
-                      umma_desc_join(v_lo + vb * ((HD * 128) >> 4) + 2u * k, hi_pv), idesc_o, (j | vb | k) != 0 ? 1u : 0u);
+            if (TP)
+              umma_bf16_ts(d, d + HD + 8u * (vb * 4 + k), umma_desc_join(v_lo + vb * ((HD * 128) >> 4) + 2u * k, hi_pv), idesc_o,
+                           (j | vb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(d, umma_desc_join(p_lo + vb * ((128 * 128) >> 4) + 2u * k, hi_pv),
+                        umma_desc_join(v_lo + vb * ((HD * 128) >> 4) + 2u * k, hi_pv), idesc_o, (j | vb | k) != 0 ? 1u : 0u);
         }
         umma_commit(pv_done(q));
       };
@@ -277,6 +284,13 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
           pv[i] = v.x; pv[i + 1] = v.y;
           lsum[(i >> 1) & 1] = fadd2(lsum[(i >> 1) & 1], v);
         }
+        if (TP) {
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) w[i] = pack_bf16(pv[2 * i], pv[2 * i + 1]);
+          tmem_st16(o_tmem + HD + 16 * c, w);
+          continue;
+        }
         const uint32_t blk = p_row + ((32 * c) >> 6) * (128 * 128);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -287,7 +301,8 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
         }
       }
-      fence_proxy_async_smem();
+      if (TP) tmem_wait_st();
+      else fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full(q));
     };
@@ -334,10 +349,10 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
   }
 }
 
-template <int HD, int BKV, int NQ, int POLY>
+template <int HD, int BKV, int NQ, int POLY, bool TP>
 int launch_attention_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                      int heads, int ntok, int ldo, cudaStream_t st, float* lse, float scale) {
-  using Cfg = AttnCfg<HD, BKV, NQ>;
+  using Cfg = AttnCfg<HD, BKV, NQ, TP>;
   AttnMaps maps;
   const int BH = B * heads;
   const uint32_t inner = HD >= 64 ? 64 : HD;
@@ -360,18 +375,18 @@ int launch_attention_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   args.scale_log2 = 1.4426950408889634f * (scale > 0.f ? scale : 1.f / sqrtf(static_cast<float>(HD)));
   static bool attr_set = false;
   if (!attr_set) {
-    WC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD, BKV, NQ, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    WC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD, BKV, NQ, POLY, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmem));
     attr_set = true;
   }
   dim3 grid((ntok + 128 * NQ - 1) / (128 * NQ), BH);
   ProfScope prof(kProfAttention, st, 4.0 * BH * static_cast<double>(ntok) * ntok * HD);
-  attention_kernel<HD, BKV, NQ, POLY><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
+  attention_kernel<HD, BKV, NQ, POLY, TP><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
   WC_LAUNCH_CHECK();
   return 0;
 }
 
-template <int HD, int BKV, int NQ>
+template <int HD, int BKV, int NQ, bool TP = false>
 int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                      int heads, int ntok, int ldo, cudaStream_t st, float* lse, float scale) {
   static int poly = -1;
@@ -380,10 +395,10 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     poly = e ? atoi(e) : 14;
   }
   switch (poly) {   // tuning knob; 14 is the shipped setting
-    case 0: return launch_attention_p<HD, BKV, NQ, 0>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
-    case 8: return launch_attention_p<HD, BKV, NQ, 8>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
-    case 20: return launch_attention_p<HD, BKV, NQ, 20>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
-    default: return launch_attention_p<HD, BKV, NQ, 14>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 0: return launch_attention_p<HD, BKV, NQ, 0, TP>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 8: return launch_attention_p<HD, BKV, NQ, 8, TP>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 20: return launch_attention_p<HD, BKV, NQ, 20, TP>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    default: return launch_attention_p<HD, BKV, NQ, 14, TP>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
   }
 }
 
@@ -394,6 +409,21 @@ int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv
                       int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse, float scale) {
   WC_REQUIRE(ntok % 8 == 0, "token count must be a multiple of 8");
   WC_REQUIRE(ldo % 8 == 0, "output row stride must be a multiple of 8");
+  static int tp = -1;   // WC_ATTN_TP=0: P through shared memory (previous design); default: P in tensor memory
+  if (tp < 0) {
+    const char* e = getenv("WC_ATTN_TP");
+    tp = e ? atoi(e) : 1;
+  }
+  if (tp) {
+    switch (hd) {
+      // head_dim <= 32 keeps P in shared memory: three query tiles per CTA (which no longer fit in TMEM with P there)
+      // matter more than the saved stores (measured: 3.15 vs 2.84 T exp/s at head_dim 16)
+      case 64: return launch_attention<64, 128, 2, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+      case 128: return launch_attention<128, 64, 2, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+      case 192: return launch_attention<192, 64, 1, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+      default: break;
+    }
+  }
   switch (hd) {
     case 16: return launch_attention<16, 128, 3>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
     case 32: return launch_attention<32, 128, 3>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
