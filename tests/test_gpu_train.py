@@ -101,3 +101,38 @@ def test_two_steps_deterministic_and_loss_decreases():
     with torch.no_grad():
         y = model(images, t.to(dev))
     assert torch.isfinite(y).all()
+
+
+def test_train_step_ragged_shapes_vs_oracle():
+    """Odd batch (3), non-square 32x64 input with im_size 64: token counts 2048 / 512 / 128 / 32 (attention tiles larger than
+    the sequence, pixel tiles spanning several samples in the weight-gradient GEMMs).  Full gradients vs the fp32 oracle."""
+    from oracle.scheduler import OracleScheduler
+    from oracle.train import train_step
+    from oracle.unet import DEFAULT_MODEL_CONFIG
+    from weatherconverter_b200.diffusion_model.train_ddpm import DenoisingTrainer
+    dev = _dev()
+    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = 64
+    sd, model, sched = _build(cfg, 99, dev)
+    g = torch.Generator().manual_seed(12)
+    images = torch.rand(3, 3, 32, 64, generator=g) * 2 - 1
+    noise = torch.randn(3, 3, 32, 64, generator=g)
+    t = torch.tensor([5, 420, 999])
+    trainer = DenoisingTrainer(model, sched, lr=1e-4)
+    loss = trainer.forward_backward(sched.add_noise(images.to(dev), noise.to(dev), t.to(dev)), t, noise.to(dev))
+    torch.cuda.synchronize()
+    loss_ref, grads, _ = train_step(sd, cfg, images, noise, t, OracleScheduler(1000, 1e-4, 0.02))
+    assert abs(float(loss) - float(loss_ref)) < 3e-3 * abs(float(loss_ref)), (float(loss), float(loss_ref))
+    params = dict(model.named_parameters())
+    num = den = 0.0
+    worst, worst_name = 0.0, ""
+    for k, g_ref in grads.items():
+        gg = params[k].grad.detach().cpu()
+        assert torch.isfinite(gg).all(), k
+        a, b = float((gg - g_ref).norm()), float(g_ref.norm())
+        num += a * a
+        den += b * b
+        if a / (b + 1e-12) > worst:
+            worst, worst_name = a / (b + 1e-12), k
+    print(f"ragged step: loss {float(loss):.5f} vs {float(loss_ref):.5f}, gradient rms-rel {(num / den) ** 0.5:.3e}, worst {worst_name} {worst:.3e}")
+    assert (num / den) ** 0.5 < 3e-2
+    assert worst < 1.5e-1, (worst_name, worst)
