@@ -23,12 +23,20 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int
   const int p1 = static_cast<int>(static_cast<long long>(HW) * (split + 1) / nsplit);
   const __nv_bfloat16* xb = x + static_cast<size_t>(b) * HW * ld + v * 8;
   float s = 0.f, ss = 0.f;
-  for (int p = p0 + r; p < p1; p += rows) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld));
+  auto acc = [&](const uint4& u) {
     const float2 a = unpack_bf16(u.x), bq = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
     s += (a.x + a.y) + (bq.x + bq.y) + (c.x + c.y) + (d.x + d.y);
     ss += (a.x * a.x + a.y * a.y) + (bq.x * bq.x + bq.y * bq.y) + (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
+  };
+  int p = p0 + r;
+  for (; p + 3 * rows < p1; p += 4 * rows) {   // four independent 16-byte loads in flight per thread
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld));
+    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p + rows) * ld));
+    const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p + 2 * rows) * ld));
+    const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p + 3 * rows) * ld));
+    acc(u0); acc(u1); acc(u2); acc(u3);
   }
+  for (; p < p1; p += rows) acc(__ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld)));
   stash[threadIdx.x] = make_float2(s, ss);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,8 +92,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
   const int p1 = static_cast<int>(static_cast<long long>(HW) * (split + 1) / nsplit);
   const __nv_bfloat16* xb = x + static_cast<size_t>(b) * HW * ld + v * 8;
   __nv_bfloat16* yb = y + static_cast<size_t>(b) * HW * ldy + v * 8;
-  for (int p = p0 + r; p < p1; p += rows) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld));
+  auto one = [&](const uint4& u, int p) {
     float f[8];
     float2 t;
     t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
@@ -101,7 +108,16 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
     uint4 w;
     w.x = pack_bf16(f[0], f[1]); w.y = pack_bf16(f[2], f[3]); w.z = pack_bf16(f[4], f[5]); w.w = pack_bf16(f[6], f[7]);
     *reinterpret_cast<uint4*>(yb + static_cast<size_t>(p) * ldy) = w;
+  };
+  int p = p0 + r;
+  for (; p + 3 * rows < p1; p += 4 * rows) {   // four independent 16-byte loads in flight per thread
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld));
+    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p + rows) * ld));
+    const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p + 2 * rows) * ld));
+    const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p + 3 * rows) * ld));
+    one(u0, p); one(u1, p + rows); one(u2, p + 2 * rows); one(u3, p + 3 * rows);
   }
+  for (; p < p1; p += rows) one(__ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * ld)), p);
 }
 
 
@@ -164,10 +180,7 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
   const int p1 = static_cast<int>(static_cast<long long>(HW) * (split + 1) / nsplit);
   const __nv_bfloat16* xb = x + static_cast<size_t>(b) * HW * ld + v * 8;
   const __nv_bfloat16* db = dy + static_cast<size_t>(b) * HW * ldd + v * 8;
-  for (int p = p0 + r; p < p1; p += rows) {
-    float f[8], d[8];
-    load8(xb + static_cast<size_t>(p) * ld, f);
-    load8(db + static_cast<size_t>(p) * ldd, d);
+  auto accum = [&](const float (&f)[8], const float (&d)[8]) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xh = (f[j] - mean) * rstd;
@@ -175,6 +188,22 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
       a0[j] += dz;
       a1[j] = fmaf(dz, xh, a1[j]);
     }
+  };
+  int p = p0 + r;
+  for (; p + rows < p1; p += 2 * rows) {   // four independent 16-byte loads in flight per thread
+    float f0[8], d0[8], f1[8], d1[8];
+    load8(xb + static_cast<size_t>(p) * ld, f0);
+    load8(db + static_cast<size_t>(p) * ldd, d0);
+    load8(xb + static_cast<size_t>(p + rows) * ld, f1);
+    load8(db + static_cast<size_t>(p + rows) * ldd, d1);
+    accum(f0, d0);
+    accum(f1, d1);
+  }
+  for (; p < p1; p += rows) {
+    float f[8], d[8];
+    load8(xb + static_cast<size_t>(p) * ld, f);
+    load8(db + static_cast<size_t>(p) * ldd, d);
+    accum(f, d);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) stash[static_cast<size_t>(r) * C + v * 8 + j] = make_float2(a0[j], a1[j]);
@@ -283,7 +312,17 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C
   const int p1 = static_cast<int>(static_cast<long long>(HW) * (split + 1) / nsplit);
   const __nv_bfloat16* xb = x + static_cast<size_t>(b) * HW * ld + v * 8;
   if (r < rows) {
-    for (int p = p0 + r; p < p1; p += rows) {
+    int p = p0 + r;
+    for (; p + 3 * rows < p1; p += 4 * rows) {   // four independent 16-byte loads in flight per thread
+      float f0[8], f1[8], f2[8], f3[8];
+      load8(xb + static_cast<size_t>(p) * ld, f0);
+      load8(xb + static_cast<size_t>(p + rows) * ld, f1);
+      load8(xb + static_cast<size_t>(p + 2 * rows) * ld, f2);
+      load8(xb + static_cast<size_t>(p + 3 * rows) * ld, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+    }
+    for (; p < p1; p += rows) {
       float f[8];
       load8(xb + static_cast<size_t>(p) * ld, f);
 #pragma unroll
@@ -358,7 +397,7 @@ namespace wc {
 
 namespace {
 int bwd_splits(int B, int HW) {
-  int n = (2 * num_sms() + B - 1) / B;
+  int n = (4 * num_sms() + B - 1) / B;
   const int max_split = (HW + 31) / 32;
   if (n > max_split) n = max_split;
   if (n > 32) n = 32;
