@@ -339,19 +339,30 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C
   }
 }
 
-// out_rows[b*ldo + c] = sum_split part (optional), out_total[c] = sum_b sum_split part (optional); one block, fixed order
+// out_rows[b*ldo + c] = sum_split part (optional), out_total[c] = sum_b sum_split part (optional).  Block = 64 channels x 8
+// sample lanes; every sum runs in a fixed order (deterministic).
 __global__ void colsum_finish_kernel(const float* __restrict__ part, int B, int C, int nsplit, float* __restrict__ out_rows,
                                      int ldo, float* __restrict__ out_total) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float tot = 0.f;
-  for (int b = 0; b < B; ++b) {
-    float s = 0.f;
-    for (int i = 0; i < nsplit; ++i) s += part[(static_cast<size_t>(b) * nsplit + i) * C + c];
-    if (out_rows) out_rows[static_cast<size_t>(b) * ldo + c] = s;
-    tot += s;
+  __shared__ float tot[8][64];
+  const int cl = threadIdx.x & 63, bl = threadIdx.x >> 6;   // 512 threads
+  const int c = blockIdx.x * 64 + cl;
+  float t = 0.f;
+  if (c < C) {
+    for (int b = bl; b < B; b += 8) {
+      float s = 0.f;
+      for (int i = 0; i < nsplit; ++i) s += part[(static_cast<size_t>(b) * nsplit + i) * C + c];
+      if (out_rows) out_rows[static_cast<size_t>(b) * ldo + c] = s;
+      t += s;
+    }
   }
-  if (out_total) out_total[c] = tot;
+  tot[bl][cl] = t;
+  __syncthreads();
+  if (bl == 0 && c < C && out_total) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += tot[k][cl];
+    out_total[c] = s;
+  }
 }
 
 }  // namespace
@@ -397,7 +408,7 @@ namespace wc {
 
 namespace {
 int bwd_splits(int B, int HW) {
-  int n = (4 * num_sms() + B - 1) / B;
+  int n = (8 * num_sms() + B - 1) / B;
   const int max_split = (HW + 31) / 32;
   if (n > max_split) n = max_split;
   if (n > 32) n = 32;
@@ -462,7 +473,7 @@ int colsum(const __nv_bfloat16* x, int B, int HW, int C, int ld, float* out_rows
   ProfScope prof(kProfOther, st, 2.0 * B * static_cast<double>(HW) * C);
   colsum_kernel<<<dim3(nsplit, B), threads, static_cast<size_t>(rows) * C * sizeof(float), st>>>(x, HW, C, ld, nsplit, part);
   WC_LAUNCH_CHECK();
-  colsum_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, B, C, nsplit, out_rows, ldo, out_total);
+  colsum_finish_kernel<<<(C + 63) / 64, 512, 0, st>>>(part, B, C, nsplit, out_rows, ldo, out_total);
   WC_LAUNCH_CHECK();
   return 0;
 }
