@@ -170,3 +170,39 @@ def test_attention(hd, N, B):
     ref = (att @ _bf(v)).transpose(1, 2).reshape(B, N, heads * hd)
     err = _rel(o, ref)
     assert err < 1e-2, err
+
+
+@pytest.mark.parametrize("hd,N,B,mode", [(16, 1024, 1, "grow"), (32, 1024, 1, "grow"), (16, 520, 2, "grow"), (32, 136, 1, "grow"),
+                                          (16, 1024, 1, "big"), (32, 512, 1, "big"), (16, 384, 1, "shrink"),
+                                          (16, 8192, 1, "plain"), (32, 8192, 1, "plain")])
+def test_attention_small_heads_stale_max(hd, N, B, mode):
+    """head_dim 16/32 kernel (csrc/attention_small.cu): the row maximum is tracked lazily (stale offset folded into the S
+    accumulator, overflow detection on the packed P words).  Inputs whose row maximum keeps growing from one KV tile to the
+    next by far more than the 2^9 slack, very large logits, maxima that only occur in the first tile, and ragged N must all
+    match softmax(QK^T/sqrt(hd))V; the log-sum-exp rows saved for the backward are checked too."""
+    from weatherconverter_b200 import ops
+    dev = _dev()
+    heads = 4
+    g = torch.Generator(device="cpu").manual_seed(7 * hd + N)
+    q = torch.randn(B, heads, N, hd, generator=g)
+    k = torch.randn(B, heads, N, hd, generator=g)
+    v = torch.randn(B, heads, N, hd, generator=g)
+    if mode == "grow":      # key norms grow with the index: every later tile raises the row maximum
+        k = k * torch.linspace(0.25, 14.0, N)[None, None, :, None]
+    elif mode == "big":     # logits of several hundred (log2 units)
+        q, k = q * 6.0, k * 6.0
+    elif mode == "shrink":  # the largest logits are all in the first tile, later ones are far below
+        k = k * torch.linspace(14.0, 0.05, N)[None, None, :, None]
+    q, k, v = q.to(dev), k.to(dev), v.to(dev)
+    o, lse = ops.attention_lse(q.bfloat16(), k.bfloat16(), v.transpose(2, 3).contiguous().bfloat16())
+    o2 = ops.attention(q.bfloat16(), k.bfloat16(), v.transpose(2, 3).contiguous().bfloat16())
+    assert torch.equal(o, o2)
+    s = (_bf(q).double() @ _bf(k).double().transpose(-2, -1)) / math.sqrt(hd)
+    att = torch.softmax(s, dim=-1)
+    ref = (att @ _bf(v).double()).transpose(1, 2).reshape(B, N, heads * hd).float()
+    err = _rel(o.float(), ref)
+    assert torch.isfinite(o.float()).all()
+    assert err < 1e-2, err
+    lse_ref = (torch.logsumexp(s, dim=-1) * math.log2(math.e)).reshape(B * heads, N).float()
+    # l is summed from bf16-rounded P: relative error <= 2^-9 per term -> absolute log2 error of a few 1e-3
+    assert (lse - lse_ref).abs().max() < 2e-2 + 1e-5 * lse_ref.abs().max(), float((lse - lse_ref).abs().max())

@@ -404,11 +404,20 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
 
 }  // namespace
 
+int attention_small_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
+                            int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse, float scale);
+
 // q,k [B,heads,ntok,hd]; vt [B,heads,hd,ntok]; out [B,ntok,ldo] (columns head*hd .. head*hd+hd).
 int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                       int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse, float scale) {
   WC_REQUIRE(ntok % 8 == 0, "token count must be a multiple of 8");
   WC_REQUIRE(ldo % 8 == 0, "output row stride must be a multiple of 8");
+  static int small = -1;   // WC_ATTN_SMALL=0: general kernel for head_dim 16 / 32 too (previous design)
+  if (small < 0) {
+    const char* e = getenv("WC_ATTN_SMALL");
+    small = e ? atoi(e) : 1;
+  }
+  if (small && (hd == 16 || hd == 32)) return attention_small_forward(q, k, vt, out, B, heads, ntok, hd, ldo, st, lse, scale);
   static int tp = -1;   // WC_ATTN_TP=0: P through shared memory (previous design); default: P in tensor memory
   if (tp < 0) {
     const char* e = getenv("WC_ATTN_TP");

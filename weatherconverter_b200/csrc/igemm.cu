@@ -204,7 +204,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (role dispatch below)
   const int lane = threadIdx.x & 31;
   // bias / PReLU vectors -> shared memory (read once per CTA instead of once per tile from L2)
   float* s_vec = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
@@ -265,8 +265,12 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     b0 = (mt / (tiles_x * tiles_y)) * p.tb;
   };
 
+  // Producer and MMA warps run their loops in warp-uniform control flow and ONE ELECTED lane issues (elect.sync): the
+  // compiler then keeps stage counters / descriptors in uniform registers and emits bare UTCHMMA / UTMALDG sequences.
+  // Issuing from inside `if (lane == 0)` wraps every such instruction in an ELECT / PLOP3 / BRA.U.ANY loop plus R2UR moves
+  // (~10 SASS instructions per MMA); for the narrow layers (N <= 64) that made the issuing thread the limiter.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
@@ -283,13 +287,16 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           for (int ky = 0; ky < 3; ++ky)
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
-              trace(0, 1);
-              const uint32_t sa = smem_base + stage * kStageSz;
-              mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0u : kRowSegPixels * 128u) + ((p.dbg & 4) ? 0u : 3u * b_bytes));
-              if (!(p.dbg & 8)) tma_load_4d(sa, &maps.a[2], full_bar(stage), kb * kIgemmBK, x0 - 1, y0 + ky - 1, b0);
-              for (int kx = 0; kx < 3 && !(p.dbg & 4); ++kx)
-                tma_load_2d(sa + kAOff + kx * b_bytes, &maps.b, full_bar(stage), ((ky * 3 + kx) * nkb + kb) * kIgemmBK, n0);
-              trace(0, 2);
+              if (elect_one_sync()) {
+                trace(0, 1);
+                const uint32_t sa = smem_base + stage * kStageSz;
+                mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0u : kRowSegPixels * 128u) + ((p.dbg & 4) ? 0u : 3u * b_bytes));
+                if (!(p.dbg & 8)) tma_load_4d(sa, &maps.a[2], full_bar(stage), kb * kIgemmBK, x0 - 1, y0 + ky - 1, b0);
+                for (int kx = 0; kx < 3 && !(p.dbg & 4); ++kx)
+                  tma_load_2d(sa + kAOff + kx * b_bytes, &maps.b, full_bar(stage), ((ky * 3 + kx) * nkb + kb) * kIgemmBK, n0);
+                trace(0, 2);
+              }
+              __syncwarp();
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
           t_first = 9;
@@ -300,18 +307,22 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           const CUtensorMap* amap = &maps.a[tap.map];
           for (int kb = 0; kb < tap.nkb; ++kb, ++kb_global) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage * kStageSz;
-            mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-            tma_load_4d(sa, amap, full_bar(stage), kb * kIgemmBK, x0 + tap.dx, y0 + tap.dy, b0);
-            tma_load_2d(sa + kAOff, &maps.b, full_bar(stage), kb_global * kIgemmBK, n0);
+            if (elect_one_sync()) {
+              const uint32_t sa = smem_base + stage * kStageSz;
+              mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+              tma_load_4d(sa, amap, full_bar(stage), kb * kIgemmBK, x0 + tap.dx, y0 + tap.dy, b0);
+              tma_load_2d(sa + kAOff, &maps.b, full_bar(stage), kb_global * kIgemmBK, n0);
+            }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===================== MMA issuer =====================
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = umma_idesc_bf16(kIgemmBM, static_cast<uint32_t>(p.BN));
       // descriptor pieces (see umma_desc_join): constant high word, low words for stage 0, per-stage increment
       const uint64_t d0 = umma_smem_desc(smem_base, 128, 1024);
@@ -324,28 +335,30 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         const int a = it & 1;
         const uint32_t aphase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(a), aphase ^ 1u);
-        trace(1, 10);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(a) * 256u;
+        const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(a) * 256u;
         int ks_first = 0;
         if (ROW3) {
           const int nseg = 3 * p.taps[0].nkb;
           for (int sg = 0; sg < nseg; ++sg) {
             mbar_wait(full_bar(stage), phase);
-            trace(1, 11);
             tc_fence_after();
-            const uint32_t a_lo = a_lo0 + stage * stage16, b_lo = b_lo0 + stage * stage16;
+            if (elect_one_sync()) {
+              trace(1, 11);
+              const uint32_t a_lo = a_lo0 + stage * stage16, b_lo = b_lo0 + stage * stage16;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              // window of 128 pixels starting kx pixels (kx*128 B = 8 descriptor units) into the 130-pixel segment; the
-              // UMMA swizzle is a function of the absolute shared-memory address, so the shifted start needs no fix-up
+              for (int kx = 0; kx < 3; ++kx) {
+                // window of 128 pixels starting kx pixels (kx*128 B = 8 descriptor units) into the 130-pixel segment; the
+                // UMMA swizzle is a function of the absolute shared-memory address, so the shifted start needs no fix-up
 #pragma unroll
-              for (int k = 0; k < kIgemmBK / 16; ++k)
-                umma_bf16(d_tmem, umma_desc_join(a_lo + 8u * kx + 2u * k, dhi), umma_desc_join(b_lo + kx * bt16 + 2u * k, dhi), idesc,
-                          (sg | kx | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < kIgemmBK / 16; ++k)
+                  umma_bf16(d_tmem, umma_desc_join(a_lo + 8u * kx + 2u * k, dhi), umma_desc_join(b_lo + kx * bt16 + 2u * k, dhi), idesc,
+                            (sg | kx | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(empty_bar(stage));
+              trace(1, 12);
             }
-            umma_commit(empty_bar(stage));
-            trace(1, 12);
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
           ks_first = 9 * p.taps[0].nkb;
@@ -353,15 +366,21 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         for (int ks = ks_first; ks < p.total_kb; ++ks) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + stage * stage16, b_lo = b_lo0 + stage * stage16;
+          if (elect_one_sync()) {
+            const uint32_t a_lo = a_lo0 + stage * stage16, b_lo = b_lo0 + stage * stage16;
 #pragma unroll
-          for (int k = 0; k < kIgemmBK / 16; ++k)
-            umma_bf16(d_tmem, umma_desc_join(a_lo + 2u * k, dhi), umma_desc_join(b_lo + 2u * k, dhi), idesc, (ks | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+            for (int k = 0; k < kIgemmBK / 16; ++k)
+              umma_bf16(d_tmem, umma_desc_join(a_lo + 2u * k, dhi), umma_desc_join(b_lo + 2u * k, dhi), idesc, (ks | k) != 0 ? 1u : 0u);
+            umma_commit(empty_bar(stage));
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(a));
-        trace(1, 13);
+        if (elect_one_sync()) {
+          umma_commit(tfull_bar(a));
+          trace(1, 13);
+        }
+        __syncwarp();
       }
     }
   } else {
