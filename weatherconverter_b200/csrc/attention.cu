@@ -77,7 +77,7 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
   const uint32_t tmem_slot = bars + 8u * 18;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index, provably uniform
   const int bh = blockIdx.y;
   const int q0 = blockIdx.x * (128 * NQ);
   const int nkv = (p.ntok + BKV - 1) / BKV;
@@ -130,8 +130,11 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===================== MMA issuer =====================
+      // Warp-uniform control flow, one elected lane issues (see igemm.cu): descriptors stay in uniform registers and the
+      // UTCHMMA sequences carry no per-instruction ELECT / BRA.U.ANY wrappers.
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
       const uint32_t idesc_s = umma_idesc_bf16(128, BKV);
       const uint32_t idesc_o = umma_idesc_bf16(128, HD);
       // Descriptors: constant high words, low words advanced with 32-bit adds (the issuing lane's integer work is
@@ -172,22 +175,32 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
       mbar_wait(q_full, 0);
       mbar_wait(k_full(0), 0);
       tc_fence_after();
-      for (int q = 0; q < NQ; ++q) issue_s(q, 0);
-      umma_commit(k_empty(0));
+      if (elect_one_sync()) {
+        for (int q = 0; q < NQ; ++q) issue_s(q, 0);
+        umma_commit(k_empty(0));
+      }
+      __syncwarp();
       for (int j = 0; j < nkv; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1u;
         mbar_wait(v_full(s), ph);
         const bool more = (j + 1 < nkv);
         if (more) mbar_wait(k_full((j + 1) & 1), ((j + 1) >> 1) & 1u);
+#pragma unroll
         for (int q = 0; q < NQ; ++q) {
           mbar_wait(p_full(q), j & 1u);
           tc_fence_after();
-          issue_pv(q, j);
-          if (more) issue_s(q, j + 1);
+          if (elect_one_sync()) {
+            issue_pv(q, j);
+            if (more) issue_s(q, j + 1);
+          }
+          __syncwarp();
         }
-        umma_commit(v_empty(s));
-        if (more) umma_commit(k_empty((j + 1) & 1));
+        if (elect_one_sync()) {
+          umma_commit(v_empty(s));
+          if (more) umma_commit(k_empty((j + 1) & 1));
+        }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

@@ -93,7 +93,7 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
   const uint32_t tmem_slot = bars + 8u * 9;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_u32));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index, provably uniform
   const int bh = blockIdx.y, b = bh / p.heads, h = bh % p.heads;
   const int r0 = blockIdx.x * 128;
   const int nt = (p.ntok + BT - 1) / BT;
@@ -140,8 +140,10 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===================== MMA issuer =====================
+      // Warp-uniform control flow, one elected lane issues (see igemm.cu).
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
       const uint32_t idesc_s = umma_idesc_bf16(128, BT);
       const uint32_t idesc_acc = umma_idesc_bf16(128, HD, 0, 1);  // B operand MN-major
       // K-major descriptors of the hd-contraction operands (R1, R2, T1, T2) and of the P'/dS' tiles
@@ -201,7 +203,8 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
       mbar_wait(r_full, 0);
       mbar_wait(t_full(0), 0);
       tc_fence_after();
-      issue_s(0);
+      if (elect_one_sync()) issue_s(0);
+      __syncwarp();
       for (int i = 0; i < nt; ++i) {
         mbar_wait(p_full, i & 1u);
         tc_fence_after();
@@ -209,13 +212,17 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
         if (STAGES >= 2 && more) {
           mbar_wait(t_full((i + 1) % STAGES), ((i + 1) / STAGES) & 1u);
           tc_fence_after();
-          issue_s(i + 1);
         }
-        issue_acc(i);
+        if (elect_one_sync()) {
+          if (STAGES >= 2 && more) issue_s(i + 1);
+          issue_acc(i);
+        }
+        __syncwarp();
         if (STAGES == 1 && more) {
           mbar_wait(t_full(0), (i + 1) & 1u);
           tc_fence_after();
-          issue_s(i + 1);
+          if (elect_one_sync()) issue_s(i + 1);
+          __syncwarp();
         }
       }
     }

@@ -55,6 +55,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
   prefetch(n0 + grp * NC);            // issued BEFORE waiting for the accumulator: overlaps the main loop's tail
   mbar_wait(tfull_addr, tfull_parity);
   tc_fence_after();
+  if (p.dbg & 16) return;   // experiment: no TMEM reads / math / stores
   for (int c0 = grp * NC; c0 < p.BN; c0 += 2 * NC) {
     const int nb = n0 + c0;
     if (nb >= p.N) break;  // warp-uniform
@@ -352,8 +353,9 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
                 // UMMA swizzle is a function of the absolute shared-memory address, so the shifted start needs no fix-up
 #pragma unroll
                 for (int k = 0; k < kIgemmBK / 16; ++k)
-                  umma_bf16(d_tmem, umma_desc_join(a_lo + 8u * kx + 2u * k, dhi), umma_desc_join(b_lo + kx * bt16 + 2u * k, dhi), idesc,
-                            (sg | kx | k) != 0 ? 1u : 0u);
+                  if (!(p.dbg & 32))
+                    umma_bf16(d_tmem, umma_desc_join(a_lo + 8u * kx + 2u * k, dhi), umma_desc_join(b_lo + kx * bt16 + 2u * k, dhi), idesc,
+                              (sg | kx | k) != 0 ? 1u : 0u);
               }
               umma_commit(empty_bar(stage));
               trace(1, 12);

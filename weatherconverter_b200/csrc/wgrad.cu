@@ -61,7 +61,7 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ Wgr
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index, provably uniform
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.dy);
     for (int i = 0; i < kWgMaxMaps; ++i) tma_prefetch_desc(&maps.x[i]);
@@ -122,8 +122,10 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ Wgr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ===================== MMA issuer =====================
+      // Warp-uniform control flow, one elected lane issues (see igemm.cu).
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
       const uint64_t d0 = umma_smem_desc_mn(smem_base, kAtomBytes, 1024);
       const uint32_t dhi = umma_desc_hi(d0), a_lo0 = umma_desc_lo(d0), b_lo0 = a_lo0 + (kAStage >> 4);
       int stage = 0;
@@ -144,15 +146,19 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ Wgr
         for (int pt = pb; pt < pe; ++pt) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + stage * (kStageBytes >> 4), b_lo = b_lo0 + stage * (kStageBytes >> 4);
+          if (elect_one_sync()) {
+            const uint32_t a_lo = a_lo0 + stage * (kStageBytes >> 4), b_lo = b_lo0 + stage * (kStageBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kWgPixels / 16; ++k)  // 16 pixels = two 8-row groups = 2048 bytes
-            umma_bf16(d_tmem, umma_desc_join(a_lo + 128u * k, dhi), umma_desc_join(b_lo + 128u * k, dhi), idesc,
-                      (pt > pb || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+            for (int k = 0; k < kWgPixels / 16; ++k)  // 16 pixels = two 8-row groups = 2048 bytes
+              umma_bf16(d_tmem, umma_desc_join(a_lo + 128u * k, dhi), umma_desc_join(b_lo + 128u * k, dhi), idesc,
+                        (pt > pb || k > 0) ? 1u : 0u);
+            umma_commit(empty_bar(stage));
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(a));
+        if (elect_one_sync()) umma_commit(tfull_bar(a));
+        __syncwarp();
       }
     }
   } else {

@@ -99,7 +99,7 @@ class DenoisingTrainer:
         n_mids = len(model.mid_channels) - 1
         order = sorted(range(len(named)), key=lambda i: (_backward_group(named[i][0], n_levels, n_mids, n_levels), i))
         total = sum((p.numel() + 3) & ~3 for _, p in named)   # every tensor starts 16-byte aligned
-        self.flat_params = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_params = torch.zeros(total, device=dev, dtype=torch.float32)   # zeros: the alignment gaps are stepped by Adam too
         self.flat_grads = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
