@@ -422,6 +422,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def _dram_traffic_per_launch(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per igemm launch (bytes), averaged over the launches of one step, from the
+    committed ncu capture of the same command (profiles/r1_dram_traffic_<workload>.json); None when no capture exists."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", f"r1_dram_traffic_{workload}.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -543,7 +554,8 @@ def main():
         dom = "igemm_tcgen05"
         achieved = classes[dom]["tflops"]
         roofline = {"bound": "tensor", "kernel": "igemm_kernel (csrc/igemm.cu)", "achieved": achieved,
-                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
+                    "traffic": _dram_traffic_per_launch(args.workload),
                     "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                     "share_of_step": classes[dom]["share_of_step"],
                     "flops_per_launch": classes[dom]["work_per_step"] / classes[dom]["launches_per_step"],
