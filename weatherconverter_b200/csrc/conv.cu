@@ -139,6 +139,21 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
     WC_REQUIRE(out.out.ptr && out.out.B == B && out.out.H == a.Ho && out.out.W == a.Wo, "output grid mismatch");
     WC_REQUIRE(out.out.ld % 8 == 0, "output pixel stride must be a multiple of 8");
     a.out = out.out.ptr; a.ldc = out.out.ld;
+    static int tma_store = -1;   // WC_IGEMM_TMA_STORE=0: row-per-lane global stores (previous epilogue)
+    if (tma_store < 0) {
+      const char* e = getenv("WC_IGEMM_TMA_STORE");
+      tma_store = e ? atoi(e) : 1;
+    }
+    if (tma_store && sy == 1 && sx == 1) {
+      const int nc = (a.BN % 32 == 0 && N % 32 == 0) ? 32 : 16;   // the epilogue's chunk width (see igemm_kernel)
+      a.qw = tw < 32 ? tw : 32;
+      a.qh = th < 32 / a.qw ? th : 32 / a.qw;
+      a.qb = 32 / (a.qw * a.qh);
+      if (a.qb <= tb) {
+        if (int e = igemm_make_cmap(&plan->maps.c, out.out, N, nc, a.qw, a.qh, a.qb)) return e;
+        a.tma_store = 1;
+      }
+    }
   } else if (out.mode == kOutNCHWf32) {
     a.out_f32 = out.out_f32; a.n_store = out.n_store;
   } else {

@@ -13,7 +13,11 @@ constexpr uint32_t kPipeBytes = 204800;  // shared-memory budget of the TMA ring
 constexpr int kMaxStages = 8;
 constexpr int kVecMaxN = 1024;  // bias / PReLU vectors up to this many channels are staged in shared memory
 constexpr uint32_t kVecBytes = 2 * kVecMaxN * 4;
-constexpr uint32_t kSmemBytes = kPipeBytes + 1024 /*align*/ + 256 /*barriers*/ + kVecBytes;
+// Output staging of the TMA-store epilogue: 2 KiB per epilogue warp (32 rows x 32 channels bf16, 64-byte swizzle).  The
+// row-per-lane global stores it replaces touch 32 different 128-byte lines per request (16 bytes each) and keep the L1TEX
+// tag stage busy (profiles/r1_ncu_igemm_1x1_64_256.txt); a TMA store reads shared memory directly.
+constexpr uint32_t kOutStageBytes = 8 * 2048;
+constexpr uint32_t kSmemBytes = kPipeBytes + kOutStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kVecBytes;   // + 1 KiB static
 constexpr uint32_t kTmemCols = 512;
 // Row-segment mode (3x3, stride 1, dilation 1, tiles of 128 pixels of ONE image row): per (channel block, ky) one TMA
 // box of 130 pixels [x0-1, x0+129) is loaded once and the three kx taps read it through UMMA descriptors whose start is
@@ -31,11 +35,14 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NC]) {
 // Epilogue of one accumulator tile for one thread (= one output pixel row of the tile).  `grp` in {0,1}: the two
 // epilogue warpgroups interleave the N chunks.  Residual / ReLU-mask rows are prefetched one chunk ahead so their global
 // latency overlaps the TMEM load and the math of the current chunk.
-template <int NC>
+template <int NC, bool TMA_OUT>
 __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc, int n0, int b, int y, int x,
                                               bool valid, int grp, const float* s_bias, const float* s_prelu,
-                                              uint32_t tfull_addr, uint32_t tfull_parity) {
+                                              uint32_t tfull_addr, uint32_t tfull_parity, const CUtensorMap* cmap,
+                                              uint32_t out_stage, int qx, int qy, int qb0) {
   constexpr int NV = NC / 8;
+  const int lane = threadIdx.x & 31;
+  constexpr bool tma_out = TMA_OUT;
   const int oy = y * p.sy + p.py, ox = x * p.sx + p.px;
   const size_t opix = (static_cast<size_t>(b) * p.Ho + oy) * p.Wo + ox;
   const uint4* res_row = p.res ? reinterpret_cast<const uint4*>(p.res + opix * p.ldr) : nullptr;
@@ -66,7 +73,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
     for (int j = 0; j < NV; ++j) { res_cur[j] = res_nxt[j]; mask_cur[j] = mask_nxt[j]; }
     if (c0 + 2 * NC < p.BN) prefetch(nb + 2 * NC);
     tmem_wait_ld();
-    if (!valid) continue;
+    if (!valid && !tma_out) continue;   // TMA store: all lanes stage their row, rows outside the tensor are clipped by the TMA
     float v[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
@@ -79,7 +86,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
       }
     }
     if (p.rowbias) {
-      const float* rb = p.rowbias + static_cast<size_t>(b) * p.ldrb + nb;
+      const float* rb = p.rowbias + static_cast<size_t>(b < p.B ? b : p.B - 1) * p.ldrb + nb;
 #pragma unroll
       for (int j = 0; j < NC; j += 4) {
         float4 bv = __ldg(reinterpret_cast<const float4*>(rb + j));
@@ -131,7 +138,26 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
       }
     }
     if (p.dbg & 1) continue;
-    if (p.out_mode == kOutNHWC) {
+    if constexpr (tma_out) {
+      // the previous chunk's store must have finished READING the staging buffer
+      if (lane == 0) tma_store_wait_read0();
+      __syncwarp();
+      // row `lane` of the box, 16-byte chunk j at j ^ swizzle(row): 64-byte rows -> XOR with bits 1..2 of the row (SWIZZLE_64B),
+      // 32-byte rows -> XOR with bit 2 (SWIZZLE_32B); conflict-free per quarter warp
+      const uint32_t mine = out_stage + lane * (NC * 2);
+      const uint32_t sw = NC == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(mine + ((static_cast<uint32_t>(j) ^ sw) << 4)),
+                     "r"(pack_bf16(v[8 * j + 0], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
+                     "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7])) : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(cmap, out_stage, nb, qx, qy, qb0);
+        tma_store_commit();
+      }
+    } else if (p.out_mode == kOutNHWC) {
       uint4* op = reinterpret_cast<uint4*>(p.out + opix * p.ldc + nb);
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
@@ -186,7 +212,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
   }
 }
 
-template <bool ROW3>
+template <bool ROW3, bool TMA_OUT>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -196,7 +222,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   const int kStages = p.nstages;
   const uint32_t kStageSz = kAOff + (ROW3 ? 3u : 1u) * static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kPipeBytes;
+  const uint32_t bar_base = smem_base + kPipeBytes + kOutStageBytes;   // [ring | output staging | barriers | bias / PReLU]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
@@ -390,6 +416,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int grp = (warp - 2) >> 2;  // 0 or 1: which half of the interleaved N chunks
     const int row = quad * 32 + lane;
+    // TMA-store epilogue: this warp's staging buffer (1024-byte aligned) and the origin of its 32-pixel box inside the tile
+    const uint32_t out_stage = smem_base + kPipeBytes + static_cast<uint32_t>(warp - 2) * 2048u;
+    const int q_pix = quad * 32;
+    const int qx0 = q_pix % p.tw, qy0 = (q_pix / p.tw) % p.th, qb0 = q_pix / (p.tw * p.th);
     const int bb = row / (p.th * p.tw), rem = row % (p.th * p.tw), yy = rem / p.tw, xx = rem % p.tw;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -402,13 +432,16 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       const uint32_t tacc = tmem_base + static_cast<uint32_t>(a) * 256u + (static_cast<uint32_t>(quad * 32) << 16);
       if (warp == 2 && lane == 0) trace(2, 20);
       if (p.out_mode != kOutQKV && (p.BN % 32 == 0) && (p.N % 32 == 0))
-        epilogue_tile<32>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase);
+        epilogue_tile<32, TMA_OUT>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, out_stage, x0 + qx0,
+                          y0 + qy0, b0 + qb0);
       else
-        epilogue_tile<16>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase);
+        epilogue_tile<16, TMA_OUT>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, out_stage, x0 + qx0,
+                          y0 + qy0, b0 + qb0);
       tc_fence_before();
       mbar_arrive(tempty_bar(a));
       if (warp == 2 && lane == 0) trace(2, 22);
     }
+    if (TMA_OUT && lane == 0) tma_store_wait_read0();   // shared memory must outlive the last bulk store's read
   }
   tc_fence_before();
   __syncthreads();
@@ -430,16 +463,21 @@ int igemm_stages_for(int BN, int row3) {
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
     attr_set = true;
   }
   ProfScope prof(kProfIgemm, stream, plan.flops);
   prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.total_kb * kIgemmBK, plan.args.BN, plan.args.ntaps + 100 * plan.args.row3, plan.grid);
-  if (plan.args.row3)
-    igemm_kernel<true><<<plan.grid, kThreads, kRowSmemBytes, stream>>>(plan.maps, plan.args);
-  else
-    igemm_kernel<false><<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
+  if (plan.args.row3) {
+    if (plan.args.tma_store) igemm_kernel<true, true><<<plan.grid, kThreads, kRowSmemBytes, stream>>>(plan.maps, plan.args);
+    else igemm_kernel<true, false><<<plan.grid, kThreads, kRowSmemBytes, stream>>>(plan.maps, plan.args);
+  } else {
+    if (plan.args.tma_store) igemm_kernel<false, true><<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
+    else igemm_kernel<false, false><<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
+  }
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -501,6 +539,15 @@ int igemm_make_rowseg_map(CUtensorMap* out, const Act& act) {
                          static_cast<uint64_t>(act.ld) * act.W * act.H};
   uint32_t box[4] = {static_cast<uint32_t>(kIgemmBK), kRowSegPixels, 1, 1};
   return encode_tmap_bf16(out, act.ptr, 4, dims, strides, box, 128);
+}
+
+int igemm_make_cmap(CUtensorMap* out, const Act& act, int N, int nc, int qw, int qh, int qb) {
+  uint64_t dims[4] = {static_cast<uint64_t>(N), static_cast<uint64_t>(act.W), static_cast<uint64_t>(act.H),
+                      static_cast<uint64_t>(act.B)};
+  uint64_t strides[4] = {1, static_cast<uint64_t>(act.ld), static_cast<uint64_t>(act.ld) * act.W,
+                         static_cast<uint64_t>(act.ld) * act.W * act.H};
+  uint32_t box[4] = {static_cast<uint32_t>(nc), static_cast<uint32_t>(qw), static_cast<uint32_t>(qh), static_cast<uint32_t>(qb)};
+  return encode_tmap_bf16(out, act.ptr, 4, dims, strides, box, static_cast<uint32_t>(nc * 2));
 }
 
 int igemm_make_bmap(CUtensorMap* out, const __nv_bfloat16* wpacked, int n_rows, int ktotal, int BN) {

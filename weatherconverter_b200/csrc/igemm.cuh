@@ -61,11 +61,15 @@ struct IgemmArgs {
   __nv_bfloat16 *q, *k, *vt;  // kOutQKV: Q,K [B,heads,ntok,hd]; V^T [B,heads,hd,ntok]
   __nv_bfloat16* v;           // kOutQKV, optional: V [B,heads,ntok,hd] as well (the attention backward reads it)
   int heads, hd, C;
+  // kOutNHWC through TMA (tma_store == 1; unit-stride outputs only): every epilogue warp stages its 32 rows x NC channels in
+  // shared memory and one lane stores the box (NC, qw, qh, qb) = its TMEM lane quadrant of the tile with IgemmMaps::c
+  int tma_store, qw, qh, qb;
 };
 
 struct IgemmMaps {
   CUtensorMap a[kMaxMaps];
   CUtensorMap b;
+  CUtensorMap c;   // output (tma_store)
 };
 
 struct IgemmPlan {
@@ -89,5 +93,7 @@ int igemm_make_amap(CUtensorMap* out, const Act& act, int tb, int th, int tw, in
 // Row-segment A map (box 64 ch x 130 pixels of one image row) for the row3 mode.
 int igemm_make_rowseg_map(CUtensorMap* out, const Act& act);
 int igemm_make_bmap(CUtensorMap* out, const __nv_bfloat16* wpacked, int n_rows, int ktotal, int BN);
+// Output map for the TMA-store epilogue: channels [0, N) of an NHWC view, box (nc, qw, qh, qb), swizzle = nc*2 bytes.
+int igemm_make_cmap(CUtensorMap* out, const Act& act, int N, int nc, int qw, int qh, int qb);
 
 }  // namespace wc
