@@ -152,6 +152,15 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
       if (a.qb <= tb) {
         if (int e = igemm_make_cmap(&plan->maps.c, out.out, N, nc, a.qw, a.qh, a.qb)) return e;
         a.tma_store = 1;
+        static int tma_res = -1;   // WC_IGEMM_TMA_RES=0: residual rows through per-lane global loads
+        if (tma_res < 0) {
+          const char* e2 = getenv("WC_IGEMM_TMA_RES");
+          tma_res = e2 ? atoi(e2) : 1;
+        }
+        if (tma_res && ep.res && ep.res->ld % 8 == 0) {
+          if (int e = igemm_make_cmap(&plan->maps.r, *ep.res, N, nc, a.qw, a.qh, a.qb)) return e;
+          a.tma_res = 2;   // candidate: confirmed by the caller once the ring depth is known
+        }
       }
     }
   } else if (out.mode == kOutNCHWf32) {
@@ -219,6 +228,7 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   if (int e = finish_plan(&plan, arena, taps, B, H, W, tb, th, tw, N, ep, out, out.up, out.up, out.py, out.px, st)) return e;
   plan.args.row3 = (want_row3 && plan.args.BN <= 128) ? row3_mode() : 0;
   plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3);
+  plan.args.tma_res = (plan.args.tma_res == 2 && igemm_res_staging_fits(plan.args.BN, plan.args.row3, plan.args.nstages)) ? 1 : 0;
   { const char* e = getenv("WC_IGEMM_DBG"); plan.args.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("WC_IGEMM_TRACE"); plan.args.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   op->flops = plan.flops;

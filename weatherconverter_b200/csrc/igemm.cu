@@ -9,9 +9,10 @@ namespace {
 
 constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two groups of 4, one per TMEM lane quadrant)
 constexpr uint32_t kABytes = kIgemmBM * kIgemmBK * 2;  // 16 KiB
-constexpr uint32_t kPipeBytes = 204800;  // shared-memory budget of the TMA ring (both modes), multiple of 1024
+constexpr uint32_t kPipeBytes = 212992;  // shared-memory budget of the TMA ring (both modes), multiple of 1024; its last 16 KiB double as
+                                         // the residual staging of the TMA epilogue when the ring leaves them free (igemm_res_staging_fits)
 constexpr int kMaxStages = 8;
-constexpr int kVecMaxN = 1024;  // bias / PReLU vectors up to this many channels are staged in shared memory
+constexpr int kVecMaxN = 128;   // bias / PReLU vectors up to this many channels are staged in shared memory (wider: L1-cached loads)
 constexpr uint32_t kVecBytes = 2 * kVecMaxN * 4;
 // Output staging of the TMA-store epilogue: 2 KiB per epilogue warp (32 rows x 32 channels bf16, 64-byte swizzle).  The
 // row-per-lane global stores it replaces touch 32 different 128-byte lines per request (16 bytes each) and keep the L1TEX
@@ -24,7 +25,6 @@ constexpr uint32_t kTmemCols = 512;
 // shifted by kx*128 bytes (base_offset = kx keeps the 128-byte swizzle phase right) -> A traffic / 3.
 constexpr uint32_t kRowSegPixels = 130;
 constexpr uint32_t kRowABytes = 18432;                       // 130*128 = 16640, padded to a multiple of 1024
-constexpr uint32_t kRowSmemBytes = kSmemBytes;
 
 template <int NC>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NC]) {
@@ -35,22 +35,28 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NC]) {
 // Epilogue of one accumulator tile for one thread (= one output pixel row of the tile).  `grp` in {0,1}: the two
 // epilogue warpgroups interleave the N chunks.  Residual / ReLU-mask rows are prefetched one chunk ahead so their global
 // latency overlaps the TMEM load and the math of the current chunk.
-template <int NC, bool TMA_OUT>
+template <int NC, bool TMA_OUT, bool TMA_RES>
 __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc, int n0, int b, int y, int x,
                                               bool valid, int grp, const float* s_bias, const float* s_prelu,
                                               uint32_t tfull_addr, uint32_t tfull_parity, const CUtensorMap* cmap,
-                                              uint32_t out_stage, int qx, int qy, int qb0) {
+                                              uint32_t out_stage, int qx, int qy, int qb0, const CUtensorMap* rmap,
+                                              uint32_t res_stage, uint32_t res_bar, uint32_t& res_phase) {
   constexpr int NV = NC / 8;
   const int lane = threadIdx.x & 31;
   constexpr bool tma_out = TMA_OUT;
+  constexpr bool tma_res = TMA_OUT && TMA_RES;   // the residual box arrives in shared memory through TMA
   const int oy = y * p.sy + p.py, ox = x * p.sx + p.px;
   const size_t opix = (static_cast<size_t>(b) * p.Ho + oy) * p.Wo + ox;
   const uint4* res_row = p.res ? reinterpret_cast<const uint4*>(p.res + opix * p.ldr) : nullptr;
   const uint4* mask_row = p.mask ? reinterpret_cast<const uint4*>(p.mask + opix * p.ldm) : nullptr;
   uint4 res_nxt[NV], mask_nxt[NV];
   auto prefetch = [&](int nb) {
+    if (tma_res && nb < p.N && lane == 0) {   // one box (NC channels x this warp's 32 pixels); rows outside the tensor are zero-filled
+      mbar_arrive_expect_tx(res_bar, NC * 2 * 32);
+      tma_load_4d(res_stage, rmap, res_bar, nb, qx, qy, qb0);
+    }
     if (!valid || nb >= p.N) return;
-    if (res_row) {
+    if (res_row && !tma_res) {
 #pragma unroll
       for (int j = 0; j < NV; ++j) res_nxt[j] = __ldg(res_row + (nb >> 3) + j);
     }
@@ -59,7 +65,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
       for (int j = 0; j < NV; ++j) mask_nxt[j] = __ldg(mask_row + (nb >> 3) + j);
     }
   };
-  prefetch(n0 + grp * NC);            // issued BEFORE waiting for the accumulator: overlaps the main loop's tail
+  if (grp * NC < p.BN) prefetch(n0 + grp * NC);   // issued BEFORE waiting for the accumulator: overlaps the main loop's tail
   mbar_wait(tfull_addr, tfull_parity);
   tc_fence_after();
   if (p.dbg & 16) return;   // experiment: no TMEM reads / math / stores
@@ -71,6 +77,17 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
     uint4 res_cur[NV], mask_cur[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) { res_cur[j] = res_nxt[j]; mask_cur[j] = mask_nxt[j]; }
+    if (tma_res) {
+      mbar_wait(res_bar, res_phase);
+      res_phase ^= 1u;
+      const uint32_t mine = res_stage + lane * (NC * 2);
+      const uint32_t sw = NC == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(res_cur[j].x), "=r"(res_cur[j].y), "=r"(res_cur[j].z), "=r"(res_cur[j].w)
+                     : "r"(mine + ((static_cast<uint32_t>(j) ^ sw) << 4)) : "memory");
+      __syncwarp();   // every lane has read its row before the next box may land
+    }
     if (c0 + 2 * NC < p.BN) prefetch(nb + 2 * NC);
     tmem_wait_ld();
     if (!valid && !tma_out) continue;   // TMA store: all lanes stage their row, rows outside the tensor are clipped by the TMA
@@ -212,7 +229,7 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
   }
 }
 
-template <bool ROW3, bool TMA_OUT>
+template <bool ROW3, bool TMA_OUT, bool TMA_RES>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -264,6 +281,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 256);
       }
+      for (int w = 0; w < 8; ++w) mbar_init(bar_base + 8u * (2 * kMaxStages + 5 + w), 1);   // residual boxes (tma_res)
       fence_barrier_init();
     }
     __syncwarp();
@@ -418,6 +436,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const int row = quad * 32 + lane;
     // TMA-store epilogue: this warp's staging buffer (1024-byte aligned) and the origin of its 32-pixel box inside the tile
     const uint32_t out_stage = smem_base + kPipeBytes + static_cast<uint32_t>(warp - 2) * 2048u;
+    // residual staging (tma_res): the last 16 KiB of the ring area (free by construction), one mbarrier per warp
+    const uint32_t res_stage = smem_base + kPipeBytes - kOutStageBytes + static_cast<uint32_t>(warp - 2) * 2048u;
+    const uint32_t res_bar = bar_base + 8u * (2 * kMaxStages + 5 + (warp - 2));
+    uint32_t res_phase = 0;
     const int q_pix = quad * 32;
     const int qx0 = q_pix % p.tw, qy0 = (q_pix / p.tw) % p.th, qb0 = q_pix / (p.tw * p.th);
     const int bb = row / (p.th * p.tw), rem = row % (p.th * p.tw), yy = rem / p.tw, xx = rem % p.tw;
@@ -432,11 +454,11 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       const uint32_t tacc = tmem_base + static_cast<uint32_t>(a) * 256u + (static_cast<uint32_t>(quad * 32) << 16);
       if (warp == 2 && lane == 0) trace(2, 20);
       if (p.out_mode != kOutQKV && (p.BN % 32 == 0) && (p.N % 32 == 0))
-        epilogue_tile<32, TMA_OUT>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, out_stage, x0 + qx0,
-                          y0 + qy0, b0 + qb0);
+        epilogue_tile<32, TMA_OUT, TMA_RES>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, out_stage, x0 + qx0,
+                          y0 + qy0, b0 + qb0, &maps.r, res_stage, res_bar, res_phase);
       else
-        epilogue_tile<16, TMA_OUT>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, out_stage, x0 + qx0,
-                          y0 + qy0, b0 + qb0);
+        epilogue_tile<16, TMA_OUT, TMA_RES>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, out_stage, x0 + qx0,
+                          y0 + qy0, b0 + qb0, &maps.r, res_stage, res_bar, res_phase);
       tc_fence_before();
       mbar_arrive(tempty_bar(a));
       if (warp == 2 && lane == 0) trace(2, 22);
@@ -460,24 +482,30 @@ int igemm_stages_for(int BN, int row3) {
   return n > kMaxStages ? kMaxStages : n;
 }
 
-int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
+bool igemm_res_staging_fits(int BN, int row3, int nstages) {
+  const uint32_t stage = (row3 ? kRowABytes : kABytes) + (row3 ? 3u : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2;
+  return static_cast<uint32_t>(nstages) * stage + kOutStageBytes <= kPipeBytes;
+}
+
+template <bool ROW3, bool TMA_OUT, bool TMA_RES>
+static int launch_variant(const IgemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
-    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<ROW3, TMA_OUT, TMA_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
+  igemm_kernel<ROW3, TMA_OUT, TMA_RES><<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
+  return 0;
+}
+
+int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
   ProfScope prof(kProfIgemm, stream, plan.flops);
   prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.total_kb * kIgemmBK, plan.args.BN, plan.args.ntaps + 100 * plan.args.row3, plan.grid);
-  if (plan.args.row3) {
-    if (plan.args.tma_store) igemm_kernel<true, true><<<plan.grid, kThreads, kRowSmemBytes, stream>>>(plan.maps, plan.args);
-    else igemm_kernel<true, false><<<plan.grid, kThreads, kRowSmemBytes, stream>>>(plan.maps, plan.args);
-  } else {
-    if (plan.args.tma_store) igemm_kernel<false, true><<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
-    else igemm_kernel<false, false><<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
-  }
+  const int variant = plan.args.tma_store ? (plan.args.tma_res ? 2 : 1) : 0;   // epilogue: per-lane stores / TMA store / TMA store + TMA residual
+  int e = 0;
+  if (plan.args.row3) e = variant == 2 ? launch_variant<true, true, true>(plan, stream) : variant == 1 ? launch_variant<true, true, false>(plan, stream) : launch_variant<true, false, false>(plan, stream);
+  else e = variant == 2 ? launch_variant<false, true, true>(plan, stream) : variant == 1 ? launch_variant<false, true, false>(plan, stream) : launch_variant<false, false, false>(plan, stream);
+  if (e) return e;
   WC_LAUNCH_CHECK();
   return 0;
 }

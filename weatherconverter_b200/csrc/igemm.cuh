@@ -64,12 +64,16 @@ struct IgemmArgs {
   // kOutNHWC through TMA (tma_store == 1; unit-stride outputs only): every epilogue warp stages its 32 rows x NC channels in
   // shared memory and one lane stores the box (NC, qw, qh, qb) = its TMEM lane quadrant of the tile with IgemmMaps::c
   int tma_store, qw, qh, qb;
+  // residual through TMA as well (tma_res == 1): needs tma_store and 16 KiB of the ring area free behind the last stage; every
+  // epilogue warp loads the (NC, qw, qh, qb) box of its next chunk with IgemmMaps::r and reads its own row from shared memory
+  int tma_res;
 };
 
 struct IgemmMaps {
   CUtensorMap a[kMaxMaps];
   CUtensorMap b;
   CUtensorMap c;   // output (tma_store)
+  CUtensorMap r;   // residual (tma_res)
 };
 
 struct IgemmPlan {
@@ -81,6 +85,8 @@ struct IgemmPlan {
 
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
 int igemm_stages_for(int BN, int row3);
+// true if 16 KiB stay free behind `nstages` stages of the TMA ring (room for the residual staging of the TMA epilogue)
+bool igemm_res_staging_fits(int BN, int row3, int nstages);
 
 // Choose the M-tile shape for a (B,H,W) grid: widest power-of-two span of x, then y, then b.
 void igemm_pick_tile(int B, int H, int W, int* tb, int* th, int* tw);
