@@ -12,8 +12,10 @@ constexpr uint32_t kABytes = kIgemmBM * kIgemmBK * 2;  // 16 KiB
 constexpr uint32_t kPipeBytes = 212992;  // shared-memory budget of the TMA ring (both modes), multiple of 1024; its last 16 KiB double as
                                          // the residual staging of the TMA epilogue when the ring leaves them free (igemm_res_staging_fits)
 constexpr int kMaxStages = 8;
-constexpr int kVecMaxN = 128;   // bias / PReLU vectors up to this many channels are staged in shared memory (wider: L1-cached loads)
-constexpr uint32_t kVecBytes = 2 * kVecMaxN * 4;
+// bias / PReLU vectors up to this many channels are staged in shared memory (wider layers: L1-cached broadcast loads); the two
+// limits are what is left of the 227 KiB after the ring, the output staging, the barriers and the alignment slack
+constexpr int kBiasMaxN = 256, kPreluMaxN = 192;
+constexpr uint32_t kVecBytes = (kBiasMaxN + kPreluMaxN) * 4;
 // Output staging of the TMA-store epilogue: 2 KiB per epilogue warp (32 rows x 32 channels bf16, 64-byte swizzle).  The
 // row-per-lane global stores it replaces touch 32 different 128-byte lines per request (16 bytes each) and keep the L1TEX
 // tag stage busy (profiles/r1_ncu_igemm_1x1_64_256.txt); a TMA store reads shared memory directly.
@@ -252,15 +254,15 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   const int lane = threadIdx.x & 31;
   // bias / PReLU vectors -> shared memory (read once per CTA instead of once per tile from L2)
   float* s_vec = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
-  const bool vec_in_smem = p.N <= kVecMaxN;
-  if (vec_in_smem) {
+  const bool bias_in_smem = p.bias && p.N <= kBiasMaxN, prelu_in_smem = p.prelu && p.N <= kPreluMaxN;
+  {
     for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
-      if (p.bias) s_vec[i] = p.bias[i];
-      if (p.prelu) s_vec[kVecMaxN + i] = p.prelu[i];
+      if (bias_in_smem) s_vec[i] = p.bias[i];
+      if (prelu_in_smem) s_vec[kBiasMaxN + i] = p.prelu[i];
     }
   }
-  const float* s_bias = (vec_in_smem && p.bias) ? s_vec : nullptr;
-  const float* s_prelu = (vec_in_smem && p.prelu) ? s_vec + kVecMaxN : nullptr;
+  const float* s_bias = bias_in_smem ? s_vec : nullptr;
+  const float* s_prelu = prelu_in_smem ? s_vec + kBiasMaxN : nullptr;
 
   const int tiles_x = (p.W + p.tw - 1) / p.tw, tiles_y = (p.H + p.th - 1) / p.th, tiles_b = (p.B + p.tb - 1) / p.tb;
   const int m_tiles = tiles_x * tiles_y * tiles_b;
