@@ -15,6 +15,8 @@ int bn_fold(const float* g, const float* b, const float* mean, const float* var,
             int n, int n_pad, cudaStream_t st);
 int compose_sep(const float* dw, const float* pw, const float* dwb, const float* pwb, float* w, float* bias, int Co, int Ci,
                 int KK, cudaStream_t st);
+int srgan_initial(const float* x, const float* dw, const float* dwb, const float* pw, const float* pwb, const float* slope,
+                  __nv_bfloat16* y, int B, int H, int W, int ldy, cudaStream_t st);
 int srgan_final(const __nv_bfloat16* x, const float* dw, const float* dwb, const float* pw, const float* pwb, float* y, int B,
                 int H, int W, int ldx, cudaStream_t st);
 int gather_stride(const float* src, float* dst, int n, int mul, int off, cudaStream_t st);
@@ -88,14 +90,14 @@ int build(wc_srgan* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
   // ---- initial: SeperableConv2d(3->64, k9) + PReLU, NCHW fp32 in
   Act initial = make_act(bump, B, H, W, NCH);
   if (!dry) {
-    Composed c = compose("initial.cnn", 3, NCH, 9, "");
+    const float *dw = P("initial.cnn.depthwise.weight"), *dwb = Popt("initial.cnn.depthwise.bias");
+    const float *pw = P("initial.cnn.pointwise.weight"), *pwb = Popt("initial.cnn.pointwise.bias");
     const float* slope = P("initial.act.weight");
     if (err) return err;
+    WC_REQUIRE(NCH == 64, "srgan_initial is written for 64 hidden channels");
     wc_srgan* n = net;
-    push([=](cudaStream_t s) {
-      return conv_small_cin(n->x_in, c.w, c.bias, nullptr, nullptr, initial.ptr, B, 3, H, W, NCH, 9, 1, 4, initial.ld, 0, s, slope);
-    });
-    net->flops += 2.0 * B * H * W * 243.0 * NCH;
+    push([=](cudaStream_t s) { return srgan_initial(n->x_in, dw, dwb, pw, pwb, slope, initial.ptr, B, H, W, initial.ld, s); });
+    net->flops += 2.0 * B * H * W * (243.0 + 3.0 * NCH);   // separable, as the reference runs it
   }
   // ---- residual trunk
   Act cur = initial;
