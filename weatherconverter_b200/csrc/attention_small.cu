@@ -138,9 +138,15 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index, provably uniform
-  const int bh = blockIdx.y;
-  const int q0 = blockIdx.x * (128 * kNQ);
+  // head_dim 16: grid = (batch*heads, query blocks), i.e. CTAs are dispatched head-fastest and the short last query block of
+  // every head (see nq_valid) fills the tail of the last wave (+2 %).  head_dim 32 keeps query-block-fastest order: K and V of
+  // 128 heads (128 MB at N = 8192) would not stay in L2 otherwise (-4 %).
+  const int bh = HD == 16 ? blockIdx.x : blockIdx.y;
+  const int q0 = (HD == 16 ? blockIdx.y : blockIdx.x) * (128 * kNQ);
   const int nkv = (p.ntok + kBKV - 1) / kBKV;
+  // query tiles of this CTA that hold at least one token (8192 = 21 x 384 + 128: the last CTA of every (batch, head) has one);
+  // the other softmax groups and their MMAs are skipped, such a CTA finishes in well under half the time
+  const int nq_valid = min(kNQ, (p.ntok - q0 + 127) / 128);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.q);
@@ -228,12 +234,14 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
     for (int j = 0; j < npro; ++j) mbar_wait(k_full(j), 0);
 #pragma unroll
     for (int q = 0; q < kNQ; ++q) {
-      mbar_wait(q_ready(q), 0);
+      mbar_wait(q_ready(q), 0);   // every group (also one without tokens) has written its share of the constant rows
       tc_fence_after();
-      if (elect_one_sync()) {
-        for (int j = 0; j < npro; ++j) issue_s(q, j);
+      if (q < nq_valid) {
+        if (elect_one_sync()) {
+          for (int j = 0; j < npro; ++j) issue_s(q, j);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     if (elect_one_sync()) {
       for (int j = 0; j < npro; ++j) umma_commit(k_empty(j));
@@ -246,13 +254,15 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
       if (more) mbar_wait(k_full((j + 2) % kKStages), ((j + 2) / kKStages) & 1u);
 #pragma unroll
       for (int q = 0; q < kNQ; ++q) {
-        mbar_wait(p_full(q, j & 1), (j >> 1) & 1u);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          issue_pv(q, j);
-          if (more) issue_s(q, j + 2);
+        if (q < nq_valid) {
+          mbar_wait(p_full(q, j & 1), (j >> 1) & 1u);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            issue_pv(q, j);
+            if (more) issue_s(q, j + 2);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (elect_one_sync()) {
         umma_commit(v_empty(s));
@@ -449,7 +459,7 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
       return redo;
     };
 
-    for (int j = 0; j < nkv; ++j) {
+    for (int j = 0; j < (q < nq_valid ? nkv : 0); ++j) {
       const int b = j & 1;
       mbar_wait(s_full(q, b), (j >> 1) & 1u);
       if (j >= 2) mbar_wait(pv_done(q, b), ((j - 2) >> 1) & 1u);   // P buffer b free (PV of tile j-2 has read it)
@@ -466,7 +476,7 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
     }
 
     // ---- finalize: O / l -> bf16 -> out[b, tok, head*hd + d]
-    mbar_wait(pv_done(q, (nkv - 1) & 1), ((nkv - 1) >> 1) & 1u);
+    if (q < nq_valid) mbar_wait(pv_done(q, (nkv - 1) & 1), ((nkv - 1) >> 1) & 1u);
     tc_fence_after();
     const int tok = q0 + q * 128 + row;
     const int b = bh / p.heads, head = bh % p.heads;
@@ -537,7 +547,8 @@ int launch_small_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
     WC_CHECK_CUDA(cudaFuncSetAttribute(attention_small_kernel<HD, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;
   }
-  dim3 grid((ntok + 128 * kNQ - 1) / (128 * kNQ), BH);
+  const int nqb = (ntok + 128 * kNQ - 1) / (128 * kNQ);
+  dim3 grid(HD == 16 ? BH : nqb, HD == 16 ? nqb : BH);
   ProfScope prof(kProfAttention, st, 4.0 * BH * static_cast<double>(ntok) * ntok * HD);
   attention_small_kernel<HD, POLY><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
   WC_LAUNCH_CHECK();
