@@ -17,6 +17,9 @@
 //     O accumulator is l = sum_j P'_j (of the bf16-rounded P' that the PV product really uses); no FADD per element.
 //     head_dim 32 has no TMEM columns left for that at three query tiles per CTA and keeps packed fp32 row sums (which also
 //     serve as the overflow detector).
+//   * head_dim 32: P' in tensor memory too (TP): the tile is read into registers, P' is written over the first 32 columns of the
+//     S buffer it came from (tcgen05.st, two bf16 per column) and the PV MMA takes its A operand from there; a tile that needs
+//     the slow path is redone from the registers.
 //   * S double-buffered in tensor memory (KV tiles of 64 keys: 3 x (2 x 64 + 32) = 480 columns): S(q, j+2) is issued as soon
 //     as the softmax group has consumed S(q, j), so the exponentials never wait for the QK^T / PV round trip (in the general
 //     kernel the softmax warps spent 36 % of their time waiting for s_full).  A tile that moves the offset leaves the
@@ -51,7 +54,7 @@ constexpr int kKStages = 4;       // K / V^T TMA ring depth
 constexpr float kShift = 8.0f;    // P' = P * 2^-8: the "needs a new maximum" test becomes "exponent bit 7 set"
 constexpr float kLazy = 6.0f;
 
-template <int HD>
+template <int HD, bool TP = false>
 struct SmallCfg {
   static constexpr bool kLT = (HD == 16);                       // row sums on the tensor core
   static constexpr int kRowBytes = HD * 2;                      // Q / K rows (one swizzle span)
@@ -65,7 +68,8 @@ struct SmallCfg {
   static constexpr uint32_t kVBlock = kVRows * 128;             // 64 keys x kVRows
   static constexpr uint32_t kVLoad = HD * 128;                  // bytes the TMA writes per stage
   static constexpr uint32_t kPTile = 128 * kBKV * 2;
-  static constexpr uint32_t kSmem = kNQ * kQTile + kNQ * kXTile + kKxTile + kKStages * (kKTile + kVBlock) + 2 * kNQ * kPTile + 1024 + 512;
+  // TP: P lives in TENSOR MEMORY, written over the first 32 columns of the S buffer it was computed from (two bf16 per column)
+  static constexpr uint32_t kSmem = kNQ * kQTile + kNQ * kXTile + kKxTile + kKStages * (kKTile + kVBlock) + (TP ? 0u : 2 * kNQ * kPTile) + 1024 + 512;
   static constexpr int kThreads = 128 + 128 * kNQ;
   static constexpr int kColsPerQ = 2 * kBKV + kVRows;           // S0 | S1 | O (+ l)
   static_assert(kNQ * kColsPerQ <= 512, "TMEM budget");
@@ -111,10 +115,10 @@ __device__ __forceinline__ float2 exp2_poly2_scaled(float2 x, float2 c, float lo
   return o;
 }
 
-template <int HD, int POLY>
-__global__ void __launch_bounds__(SmallCfg<HD>::kThreads, 1)
+template <int HD, int POLY, bool TP>
+__global__ void __launch_bounds__(SmallCfg<HD, TP>::kThreads, 1)
 attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_constant__ SmallArgs p) {
-  using Cfg = SmallCfg<HD>;
+  using Cfg = SmallCfg<HD, TP>;
   constexpr bool LT = Cfg::kLT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -124,7 +128,7 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
   const uint32_t k_smem = kx_smem + Cfg::kKxTile;
   const uint32_t v_smem = k_smem + kKStages * Cfg::kKTile;
   const uint32_t p_smem = v_smem + kKStages * Cfg::kVBlock;
-  const uint32_t bars = p_smem + 2 * kNQ * Cfg::kPTile;
+  const uint32_t bars = p_smem + (TP ? 0u : 2 * kNQ * Cfg::kPTile);
   const uint32_t q_full = bars;
   auto k_full = [&](int s) { return bars + 8u * (1 + s); };
   auto k_empty = [&](int s) { return bars + 8u * (5 + s); };
@@ -226,8 +230,13 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
       const uint32_t d = tmem_u + q * Cfg::kColsPerQ + 2 * kBKV;
       const uint32_t p_lo = p_lo0 + (2 * q + (j & 1)) * (Cfg::kPTile >> 4), v_lo = v_lo0 + (j % kKStages) * (Cfg::kVBlock >> 4);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(d, umma_desc_join(p_lo + 2u * k, hi_pv), umma_desc_join(v_lo + 2u * k, hi_pv), idesc_o, (j | k) != 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k) {
+        if (TP)   // A = P from tensor memory: 8 columns (16 keys) per K step, in the S buffer the tile came from
+          umma_bf16_ts(d, tmem_u + q * Cfg::kColsPerQ + (j & 1) * kBKV + 8u * k, umma_desc_join(v_lo + 2u * k, hi_pv), idesc_o,
+                       (j | k) != 0 ? 1u : 0u);
+        else
+          umma_bf16(d, umma_desc_join(p_lo + 2u * k, hi_pv), umma_desc_join(v_lo + 2u * k, hi_pv), idesc_o, (j | k) != 0 ? 1u : 0u);
+      }
       umma_commit(pv_done(q, j & 1));
     };
     const int npro = nkv < 2 ? nkv : 2;
@@ -459,18 +468,133 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
       return redo;
     };
 
+    // ---- TP: the whole S tile is read into registers first, P' is written back over its first 32 columns (tcgen05.st) and
+    // the PV MMA reads it from there: no shared-memory stores, no fence.proxy.async, no A-operand fetch from shared memory.
+    // A tile that has to take the slow path is redone from the registers.
+    auto tp_tile = [&](int j, bool force_slow, auto tail_tag) {
+      constexpr bool TAIL = decltype(tail_tag)::value;
+      const int kv0 = j * kBKV;
+      const int b = j & 1;
+      uint32_t ra[32], rb[32], w0[16], w1[16];
+      tmem_ld32(s_tmem + b * kBKV, ra);
+      tmem_ld32(s_tmem + b * kBKV + 32, rb);
+      tmem_wait_ld();
+      bool slow = force_slow;
+      if (!slow) {
+        uint32_t orw = 0u;
+        float2 ts[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        const float2 cv = make_float2(cs, cs);
+        const float lo = -125.f / cs;
+        auto half = [&](const uint32_t (&cur)[32], uint32_t (&w)[16]) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 xs = make_float2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+            float2 v;
+            if (i < POLY) {
+              v = exp2_poly2_scaled(xs, cv, lo);
+            } else {
+              const float2 y = fmul2(xs, cv);
+              v.x = ex2_approx(y.x);
+              v.y = ex2_approx(y.y);
+            }
+            if (!LT) ts[(i >> 1) & 1] = fadd2(ts[(i >> 1) & 1], v);
+            w[i >> 1] = pack_bf16(v.x, v.y);
+          }
+          if (LT) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) orw |= w[i] | w[i + 1];
+          }
+        };
+        half(ra, w0);
+        half(rb, w1);
+        bool redo;
+        if (LT) {
+          redo = (orw & 0xC000C000u) != 0u;
+        } else {
+          const float tsum = (ts[0].x + ts[0].y) + (ts[1].x + ts[1].y);
+          redo = !(tsum < 32.f);
+        }
+        slow = __any_sync(0xffffffffu, redo);
+        if (!LT && !slow) { lsum[0] = fadd2(lsum[0], ts[0]); lsum[1] = fadd2(lsum[1], ts[1]); }
+      }
+      if (slow) {
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float a0 = __uint_as_float(ra[i]), a1 = __uint_as_float(rb[i]);
+          if (TAIL && kv0 + i >= p.ntok) a0 = -INFINITY;
+          if (TAIL && kv0 + 32 + i >= p.ntok) a1 = -INFINITY;
+          tmax = fmaxf(tmax, fmaxf(a0, a1));
+        }
+        tmax -= carry;
+        float delta = 0.f;
+        const bool upd = (j == 0) || (tmax > -shift + kLazy / cs);
+        if (upd) {
+          if (j + 1 < nkv) mbar_wait(s_full(q, b ^ 1), ((j + 1) >> 1) & 1u);
+          const float e_new = bf16_round(E + tmax + shift);
+          delta = e_new - E;
+          E = e_new;
+          sts16(qx_row, bf16_bits(-e_new));
+        }
+        if (j > 0 && __any_sync(0xffffffffu, upd)) {
+          mbar_wait(pv_done(q, (j - 1) & 1), ((j - 1) >> 1) & 1u);
+          tc_fence_after();
+          const float alpha = ex2_approx(-delta * cs);
+          if (!LT) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { lsum[i].x *= alpha; lsum[i].y *= alpha; }
+          }
+#pragma unroll
+          for (int c0 = 0; c0 < Cfg::kVRows; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(o_tmem + c0, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st16(o_tmem + c0, r);
+          }
+          tmem_wait_st();
+        }
+        const float dneg = -(carry + delta) * cs;
+        carry = delta;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float v0 = ex2_approx(fmaf(__uint_as_float(ra[i]), cs, dneg)), v1 = ex2_approx(fmaf(__uint_as_float(ra[i + 1]), cs, dneg));
+          float v2 = ex2_approx(fmaf(__uint_as_float(rb[i]), cs, dneg)), v3 = ex2_approx(fmaf(__uint_as_float(rb[i + 1]), cs, dneg));
+          if (TAIL) {
+            if (kv0 + i >= p.ntok) v0 = 0.f;
+            if (kv0 + i + 1 >= p.ntok) v1 = 0.f;
+            if (kv0 + 32 + i >= p.ntok) v2 = 0.f;
+            if (kv0 + 32 + i + 1 >= p.ntok) v3 = 0.f;
+          }
+          if (!LT) { lsum[0].x += v0; lsum[0].y += v1; lsum[1].x += v2; lsum[1].y += v3; }
+          w0[i >> 1] = pack_bf16(v0, v1);
+          w1[i >> 1] = pack_bf16(v2, v3);
+        }
+        fence_proxy_async_smem();   // Qx may have changed (generic-proxy store read by the next S MMA)
+      }
+      tmem_st16(s_tmem + b * kBKV, w0);
+      tmem_st16(s_tmem + b * kBKV + 16, w1);
+      tmem_wait_st();
+    };
+
     for (int j = 0; j < (q < nq_valid ? nkv : 0); ++j) {
       const int b = j & 1;
       mbar_wait(s_full(q, b), (j >> 1) & 1u);
       if (j >= 2) mbar_wait(pv_done(q, b), ((j - 2) >> 1) & 1u);   // P buffer b free (PV of tile j-2 has read it)
       tc_fence_after();
       const bool tail = (j * kBKV + kBKV > p.ntok);
-      if (tail) {
-        slow_tile(j, std::true_type{});
-      } else if (j == 0 || __any_sync(0xffffffffu, carry != 0.f) || hot_tile(b)) {
-        slow_tile(j, std::false_type{});
+      if (TP) {
+        if (tail) tp_tile(j, true, std::true_type{});
+        else tp_tile(j, j == 0 || __any_sync(0xffffffffu, carry != 0.f), std::false_type{});
+      } else {
+        if (tail) {
+          slow_tile(j, std::true_type{});
+        } else if (j == 0 || __any_sync(0xffffffffu, carry != 0.f) || hot_tile(b)) {
+          slow_tile(j, std::false_type{});
+        }
+        fence_proxy_async_smem();
       }
-      fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full(q, b));
     }
@@ -513,10 +637,10 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
   }
 }
 
-template <int HD, int POLY>
+template <int HD, int POLY, bool TP>
 int launch_small_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int heads,
                    int ntok, int ldo, cudaStream_t st, float* lse, float scale) {
-  using Cfg = SmallCfg<HD>;
+  using Cfg = SmallCfg<HD, TP>;
   SmallMaps maps;
   const int BH = B * heads;
   {
@@ -544,13 +668,13 @@ int launch_small_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
   }
   static bool attr_set = false;
   if (!attr_set) {
-    WC_CHECK_CUDA(cudaFuncSetAttribute(attention_small_kernel<HD, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(attention_small_kernel<HD, POLY, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;
   }
   const int nqb = (ntok + 128 * kNQ - 1) / (128 * kNQ);
   dim3 grid(HD == 16 ? BH : nqb, HD == 16 ? nqb : BH);
   ProfScope prof(kProfAttention, st, 4.0 * BH * static_cast<double>(ntok) * ntok * HD);
-  attention_small_kernel<HD, POLY><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
+  attention_small_kernel<HD, POLY, TP><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -563,12 +687,28 @@ int launch_small(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bflo
     const char* e = getenv("WC_ATTN_SMALL_POLY");
     poly = e ? atoi(e) : (HD == 16 ? 12 : 8);   // measured best on B200 (N 8192, batch 32): 2.46 ms (hd 16), 2.55 ms (hd 32)
   }
+  // P in tensor memory (aliased on the consumed S buffer) instead of shared memory.  Measured on B200 (batch 32, N 8192):
+  // head_dim 32: 2.52 -> 2.40 ms; head_dim 16: 2.43 -> 2.48 ms (the whole S tile held in registers spills at 128 registers,
+  // which costs more than the saved stores when there are no row-sum FADDs to begin with) -> default on for head_dim 32 only.
+  static int tp = -1;
+  if (tp < 0) {
+    const char* e = getenv("WC_ATTN_SMALL_TP");
+    tp = e ? atoi(e) : (HD == 32 ? 1 : 0);
+  }
+  if (tp) {
+    switch (poly) {
+      case 0: return launch_small_p<HD, 0, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+      case 12: return launch_small_p<HD, 12, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+      case 16: return launch_small_p<HD, 16, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+      default: return launch_small_p<HD, 8, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    }
+  }
   switch (poly) {   // tuning knob: how many of every 32 exponentials run on the FMA pipe
-    case 0: return launch_small_p<HD, 0>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
-    case 4: return launch_small_p<HD, 4>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
-    case 12: return launch_small_p<HD, 12>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
-    case 16: return launch_small_p<HD, 16>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
-    default: return launch_small_p<HD, 8>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 0: return launch_small_p<HD, 0, false>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 4: return launch_small_p<HD, 4, false>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 12: return launch_small_p<HD, 12, false>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 16: return launch_small_p<HD, 16, false>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    default: return launch_small_p<HD, 8, false>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
   }
 }
 
