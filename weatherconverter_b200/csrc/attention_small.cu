@@ -475,7 +475,10 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
       constexpr bool TAIL = decltype(tail_tag)::value;
       const int kv0 = j * kBKV;
       const int b = j & 1;
-      uint32_t ra[32], rb[32], w0[16], w1[16];
+      // P' is stored 16 words at a time as soon as it is computed (the stores are idempotent: a slow-path redo simply writes the
+      // columns again before the PV MMA is released), so only the raw tile (64 registers) and 16 packed words are live at once
+      uint32_t ra[32], rb[32], w[16];
+      const uint32_t p_tmem = s_tmem + b * kBKV;
       tmem_ld32(s_tmem + b * kBKV, ra);
       tmem_ld32(s_tmem + b * kBKV + 32, rb);
       tmem_wait_ld();
@@ -505,8 +508,10 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
             for (int i = 0; i < 16; i += 2) orw |= w[i] | w[i + 1];
           }
         };
-        half(ra, w0);
-        half(rb, w1);
+        half(ra, w);
+        tmem_st16(p_tmem, w);
+        half(rb, w);
+        tmem_st16(p_tmem + 16, w);
         bool redo;
         if (LT) {
           redo = (orw & 0xC000C000u) != 0u;
@@ -557,24 +562,25 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
         }
         const float dneg = -(carry + delta) * cs;
         carry = delta;
+        auto redo_half = [&](const uint32_t (&cur)[32], int k0, float2& acc) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float v0 = ex2_approx(fmaf(__uint_as_float(ra[i]), cs, dneg)), v1 = ex2_approx(fmaf(__uint_as_float(ra[i + 1]), cs, dneg));
-          float v2 = ex2_approx(fmaf(__uint_as_float(rb[i]), cs, dneg)), v3 = ex2_approx(fmaf(__uint_as_float(rb[i + 1]), cs, dneg));
-          if (TAIL) {
-            if (kv0 + i >= p.ntok) v0 = 0.f;
-            if (kv0 + i + 1 >= p.ntok) v1 = 0.f;
-            if (kv0 + 32 + i >= p.ntok) v2 = 0.f;
-            if (kv0 + 32 + i + 1 >= p.ntok) v3 = 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            float v0 = ex2_approx(fmaf(__uint_as_float(cur[i]), cs, dneg)), v1 = ex2_approx(fmaf(__uint_as_float(cur[i + 1]), cs, dneg));
+            if (TAIL) {
+              if (k0 + i >= p.ntok) v0 = 0.f;
+              if (k0 + i + 1 >= p.ntok) v1 = 0.f;
+            }
+            if (!LT) { acc.x += v0; acc.y += v1; }
+            w[i >> 1] = pack_bf16(v0, v1);
           }
-          if (!LT) { lsum[0].x += v0; lsum[0].y += v1; lsum[1].x += v2; lsum[1].y += v3; }
-          w0[i >> 1] = pack_bf16(v0, v1);
-          w1[i >> 1] = pack_bf16(v2, v3);
-        }
+        };
+        tmem_wait_st();
+        redo_half(ra, kv0, lsum[0]);
+        tmem_st16(p_tmem, w);
+        redo_half(rb, kv0 + 32, lsum[1]);
+        tmem_st16(p_tmem + 16, w);
         fence_proxy_async_smem();   // Qx may have changed (generic-proxy store read by the next S MMA)
       }
-      tmem_st16(s_tmem + b * kBKV, w0);
-      tmem_st16(s_tmem + b * kBKV + 16, w1);
       tmem_wait_st();
     };
 
