@@ -140,3 +140,43 @@ def test_legacy_unet_state_dict_matches_reference_layout():
     o = torch.randn(5, 4, 24)
     op = torch.zeros(5, 4, 32); op[..., :24] = o
     assert torch.allclose(op.reshape(5, 128) @ wop.T, o.reshape(5, 96) @ w["a.mha.out_proj.weight"].T, atol=1e-4)
+
+
+def test_bench_roofline_traffic_comes_from_the_committed_ncu_capture():
+    """bench.py's roofline.traffic is the DRAM bytes per igemm launch of the committed ncu launch list of the same command."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    t = bench._dram_traffic_per_launch("c3")
+    meta = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic_c3.json")))
+    assert t == pytest.approx(meta["dram_bytes_per_launch"]) and t > 1e6
+    assert os.path.exists(os.path.join(ROOT, meta["source"]))
+    assert bench._dram_traffic_per_launch("no_such_workload") is None
+
+
+def test_launch_traffic_tool_parses_an_ncu_log(tmp_path, monkeypatch):
+    """tools/launch_traffic.py: keeps the last N launches of an ncu metric log, sums time / DRAM bytes per kernel."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import launch_traffic
+    hdr = '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"'
+    rows = [hdr]
+    def add(i, name, ns, rd_mb, wr_kb):
+        base = f'"{i}","1","python","h","{name}","1","7","(320, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics"'
+        rows.append(base + f',"dram__bytes_read.sum","Mbyte","{rd_mb}"')
+        rows.append(base + f',"dram__bytes_write.sum","Kbyte","{wr_kb}"')
+        rows.append(base + f',"gpu__time_duration.sum","us","{ns}"')
+    add(0, "void wc::<unnamed>::pack_kernel(int)", "5.0", "1.0", "1.0")                       # setup launch: dropped
+    add(1, "void wc::<unnamed>::igemm_kernel<(bool)0, (bool)1, (bool)0>(wc::IgemmMaps, wc::IgemmArgs)", "40.0", "10.0", "500.0")
+    add(2, "void wc::<unnamed>::igemm_kernel<(bool)0, (bool)1, (bool)0>(wc::IgemmMaps, wc::IgemmArgs)", "60.0", "30.0", "1,500.0")
+    add(3, "void wc::<unnamed>::gn_apply_kernel(const __nv_bfloat16 *, int)", "10.0", "2.0", "0.0")
+    log = tmp_path / "ncu.csv"
+    log.write_text("==PROF== Connected\n" + "\n".join(rows) + "\n")
+    (tmp_path / "profiles").mkdir()
+    monkeypatch.chdir(tmp_path)
+    launch_traffic.main(str(log), 3, str(tmp_path / "profiles" / "x"), "zz")
+    import json
+    meta = json.load(open(tmp_path / "profiles" / "r1_dram_traffic_zz.json"))
+    assert meta["launches_per_step"] == 2
+    assert meta["dram_bytes_per_launch"] == pytest.approx((10e6 + 30e6 + 0.5e6 + 1.5e6) / 2)
+    summary = (tmp_path / "profiles" / "x_summary.txt").read_text()
+    assert "igemm_kernel<0, 1, 0>" in summary and "pack_kernel" not in summary
