@@ -180,3 +180,23 @@ def test_launch_traffic_tool_parses_an_ncu_log(tmp_path, monkeypatch):
     assert meta["dram_bytes_per_launch"] == pytest.approx((10e6 + 30e6 + 0.5e6 + 1.5e6) / 2)
     summary = (tmp_path / "profiles" / "x_summary.txt").read_text()
     assert "igemm_kernel<0, 1, 0>" in summary and "pack_kernel" not in summary
+
+
+def test_mma_issue_is_warp_uniform_in_sass():
+    """The tcgen05.mma issue loops must stay in warp-uniform control flow with one elected lane: inside
+    `if (lane == 0)` the compiler wraps every UTCHMMA in an ELECT / PLOP3 / BRA.U.ANY loop plus R2UR moves (~13 SASS
+    instructions per MMA), which made the issuing thread the limiter of the narrow layers.  Checked on the built objects."""
+    import shutil
+    import __graft_entry__ as ge
+    ge.build()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    build = os.path.join(ROOT, "weatherconverter_b200", "csrc", "build")
+    for obj in ("igemm.o", "attention.o", "attention_small.o", "attention_bwd.o", "wgrad.o"):
+        sass = subprocess.run([cuobjdump, "-sass", os.path.join(build, obj)], capture_output=True, text=True, check=True).stdout
+        lines = [l for l in sass.splitlines() if re.search(r"/\*[0-9a-f]{4,5}\*/\s+\S", l)]
+        n_mma = sum("UTCHMMA" in l for l in lines)
+        assert n_mma > 0, obj
+        wrapped = sum(1 for i, l in enumerate(lines) if "BRA.U.ANY" in l and any("UTCHMMA" in p for p in lines[max(0, i - 4):i]))
+        assert wrapped == 0, f"{obj}: {wrapped} of {n_mma} UTCHMMA are issued from divergent code (ELECT/BRA.U.ANY wrapper)"
