@@ -25,7 +25,15 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int it
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = slot;
+  // Warp 0 runs the loop in uniform control flow and one elected lane issues (as the library kernels do since the end of
+  // round 1).  The table in profiles/r1_mma_issue_rate.txt was measured with the issue inside `if (threadIdx.x == 0)`: there the
+  // compiler wraps every UTCHMMA in an ELECT / BRA.U.ANY loop, and the "45-clk floor" for N <= 64 is that wrapper, not the tensor
+  // pipe (the igemm trace shows 37 clk per 128x64x16 MMA with the elected issue).  Define MMA_RATE_DIVERGENT to reproduce it.
+#ifdef MMA_RATE_DIVERGENT
   if (threadIdx.x == 0) {
+#else
+  if (__shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0 && elect_one_sync()) {
+#endif
     const uint32_t idesc = umma_idesc_bf16(128, N);
     const uint64_t da = umma_smem_desc(base, 128, 1024), db = umma_smem_desc(base + 16384, 128, 1024);
     const uint32_t hi = umma_desc_hi(da), alo = umma_desc_lo(da), blo = umma_desc_lo(db);
