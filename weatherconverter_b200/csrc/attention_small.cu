@@ -99,6 +99,10 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&ud);
 }
 // 2^(c*x), c in [1, 2): x is clamped at lo = -125/c; n = round(c*x) and f = c*x - n come out of two FMAs.
+// Large positive arguments (a row maximum that outgrew the stale one) wrap the exponent field: for c*x < 511.5 the result is
+// >= 4, negative or NaN and the caller's "any P' >= 2 / sign bit" test sends the tile to the slow path.  Stated domain limit:
+// a logit that exceeds the row's stale maximum by more than 2^511 (354 in natural-log units of the scaled logits - out of
+// reach for bf16 q, k of any normalised network) on a polynomial lane would alias to a plausible value undetected.
 __device__ __forceinline__ float2 exp2_poly2_scaled(float2 x, float2 c, float lo) {
   const float kMagic = 12582912.f;
   x.x = fmaxf(x.x, lo);
