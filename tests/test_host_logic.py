@@ -200,3 +200,28 @@ def test_mma_issue_is_warp_uniform_in_sass():
         assert n_mma > 0, obj
         wrapped = sum(1 for i, l in enumerate(lines) if "BRA.U.ANY" in l and any("UTCHMMA" in p for p in lines[max(0, i - 4):i]))
         assert wrapped == 0, f"{obj}: {wrapped} of {n_mma} UTCHMMA are issued from divergent code (ELECT/BRA.U.ANY wrapper)"
+
+
+def test_tma_epilogue_quadrant_boxes_cover_the_tile_in_lane_order():
+    """igemm TMA epilogue (csrc/igemm.cu, conv.cu): the 32 pixels of a TMEM lane quadrant (tile pixels 32q .. 32q+31 in x-fastest
+    order) must be exactly the TMA box (qw, qh, qb) at (qx0, qy0, qb0), enumerated in the box's own x-fastest order - that is
+    what lets lane i stage row i of the box.  Checked for every power-of-two tile shape with tb*th*tw == 128."""
+    shapes = [(tb, th, tw) for tb in (1, 2, 4, 8, 16, 32, 64, 128) for th in (1, 2, 4, 8, 16, 32, 64, 128)
+              for tw in (1, 2, 4, 8, 16, 32, 64, 128) if tb * th * tw == 128]
+    assert len(shapes) == 36
+    for tb, th, tw in shapes:
+        qw = min(tw, 32)                      # conv.cu: finish_plan
+        qh = min(th, 32 // qw)
+        qb = 32 // (qw * qh)
+        if qb > tb:                           # such a plan keeps the per-lane stores
+            continue
+        for quad in range(4):
+            q_pix = quad * 32                 # igemm_kernel: epilogue warps
+            qx0, qy0, qb0 = q_pix % tw, (q_pix // tw) % th, q_pix // (tw * th)
+            for lane in range(32):
+                row = q_pix + lane
+                bb, rem = divmod(row, th * tw)
+                yy, xx = divmod(rem, tw)
+                # position of box row `lane`: x fastest, then y, then b
+                bx, by, bz = lane % qw, (lane // qw) % qh, lane // (qw * qh)
+                assert (xx, yy, bb) == (qx0 + bx, qy0 + by, qb0 + bz), (tb, th, tw, quad, lane)
