@@ -45,13 +45,30 @@ int wc_profile_detail(int cap, int* cls, double* ms, double* work, int* info);
 int wc_ddpm_step(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
                  size_t n_per_sample, int batch, float beta, float sqrt_one_minus_acp, float sqrt_alpha, float sigma,
                  void* stream);
-/* :63-77 sample_prev_timestep2 (batched t [B] int64, sigma^2 = beta_t), tables are the scheduler's fp32 [T] arrays. */
+/* :63-77 sample_prev_timestep2 (batched t [B] int64, sigma^2 = beta_t), tables are the scheduler's fp32 [T] arrays of
+ * num_timesteps entries; a t outside [0, num_timesteps) (IndexError in the reference) is clamped to the table. */
 int wc_ddpm_step_batched(const float* xt, const float* eps, const float* z, float* out, float* mean_out,
                          float* sigz_out, size_t n_per_sample, int batch, const float* betas, const float* alphas,
-                         const float* sqrt_one_minus_acp, const int64_t* t, void* stream);
+                         const float* sqrt_one_minus_acp, const int64_t* t, int num_timesteps, void* stream);
+/* The same update as wc_ddpm_step with the scalar timestep READ FROM DEVICE MEMORY (t_dev: one int64) and the four per-step
+ * coefficients gathered from coef_tables [4, num_timesteps] fp32 = rows {beta_t, sqrt(1 - acp_t), sqrt(alpha_t), sigma_t}
+ * built on the host exactly as the scalar path builds them (bit-identical results).  The launch parameters do not depend on
+ * the step, so ONE captured CUDA graph of a reverse step serves every t > 0 (t == 0: z ignored, sigz_out = 0). */
+int wc_ddpm_step_indexed(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
+                         size_t n_per_sample, int batch, const float* coef_tables, const int64_t* t_dev, int num_timesteps,
+                         void* stream);
 /* :30-35 add_noise2 / :37-61 add_noise. */
 int wc_add_noise(const float* x0, const float* noise, float* out, size_t n_per_sample, int batch,
-                 const float* sqrt_acp, const float* sqrt_one_minus_acp, const int64_t* t, void* stream);
+                 const float* sqrt_acp, const float* sqrt_one_minus_acp, const int64_t* t, int num_timesteps, void* stream);
+
+/* ---- time embedding (diffusion_model/models/unet_base.py:7-30 get_time_embedding) ------------------------ */
+/* factor_host [half] fp32 = the reference's `10000 ** (arange(half) / half)` evaluated by torch on the HOST (:22-24); the
+ * library keeps a device copy for the current device and every time-embedding kernel (also inside wc_unet_forward /
+ * wc_unet_train_forward) divides by it, so t / factor is bit-identical to the reference's.  Not set -> powf on the device.
+ * Synchronous (one small cudaMemcpy); call it at model-load time, not inside a captured region. */
+int wc_set_time_factor_table(const float* factor_host, int half);
+/* out [n, dim] f32 = cat[sin(t/factor), cos(t/factor)] for t int64 [n] (:27-30). */
+int wc_time_embedding(const int64_t* t, int n, int dim, float* out, void* stream);
 
 /* ---- guidance update (sgg/sgg.py:18-22, seg_model/inference.py:36-53) ------------------------------------ */
 /* grad [B,3,pool*h,pool*w] f32 ; mu, sigz, out [B,3,h,w] f32 ; mag_out [B,h,w] f32 or NULL. */

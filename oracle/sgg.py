@@ -61,10 +61,11 @@ def apply_lcg(seg_sd, mu, sigma, sr_xt, gt, lam, backbone="resnet50", pool=4, nu
 
 
 def sample_with_sgg(unet_sd, unet_cfg, sched, seg_sd, srgan_sd, x0, gt, noise, t_fwd, zs,
-                    lam=60.0, n_steps=500, backbone="resnet50", guidance=True, record=None):
+                    lam=60.0, n_steps=500, backbone="resnet50", guidance=True, record=None, mode="gsg"):
     """Repaired translation driver (translation.py:46-97 + SURVEY.md 8c repairs).
     x0 [B,3,h,w] in [-1,1]; gt [B,4h,4w] int64; noise like x0; t_fwd [B] int64 (translation.py:63);
     zs: list of n_steps tensors like x0, zs[i] is the z drawn at reverse step i (scheduler.py:110).
+    mode: "gsg" = GSG on every step (repaired default); "alternate" = the shipped schedule :84-87 (LCG on even, GSG on odd i).
     Returns sr_x0 [B,3,4h,4w] in [0,1]."""
     with torch.no_grad():
         xt = sched.add_noise2(x0, noise, t_fwd)                                   # :65
@@ -76,7 +77,10 @@ def sample_with_sgg(unet_sd, unet_cfg, sched, seg_sd, srgan_sd, x0, gt, noise, t
             elif guidance:
                 sr_xt = srgan.generator_forward(srgan_sd, xt)                     # :81
                 with torch.enable_grad():
-                    xt, _, _ = apply_gsg(seg_sd, mu, sigma, sr_xt, gt, lam, backbone)   # :87 (every step)
+                    if mode == "lcg" or (mode == "alternate" and i % 2 == 0):
+                        xt = apply_lcg(seg_sd, mu, sigma, sr_xt, gt, lam, backbone)     # :84-85 (even steps)
+                    else:
+                        xt, _, _ = apply_gsg(seg_sd, mu, sigma, sr_xt, gt, lam, backbone)   # :86-87
             else:
                 xt = mu + sigma                                                   # :90 (reference quirk D1)
             if record is not None:

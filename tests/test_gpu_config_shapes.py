@@ -1,0 +1,188 @@
+"""Parity AT THE BENCHMARKED CONFIGURATIONS (BASELINE.json configs 2, 3, 5): the golden fixtures are small, so these tests run
+the CPU oracle (pinned to the reference by tests/test_oracle_golden.py) on the GPU box's host cores at the real geometries:
+
+  C2  UNet forward 1 x 3 x 128 x 256, im_size 128                         (sample_ddpm.py:37-44)
+  C3  two guided reverse steps at geometry A: latent 64 x 128 (im_size 64) -> SRGAN x4 -> DeepLabV3+-R50 at 256 x 512 ->
+      avg-pool 4 -> guidance, B = 2 distinct images / label maps           (translation.py:70-97)
+      + batch invariance: image b of a batch-32 step == the B = 1 result (chains are independent)
+  C5  training step 128 x 256, im_size 128, B = 2: loss and sampled gradients (train_ddpm.py:95-114)
+
+Tolerances are bf16-storage / fp32-accumulation against the fp32 oracle and are printed next to the measured values."""
+import math
+import time
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA")
+    return torch.device("cuda")
+
+
+def _psnr(y, ref, peak=None):
+    peak = float(ref.abs().max()) if peak is None else peak
+    return 10 * math.log10(peak ** 2 / max(float(((y - ref) ** 2).mean()), 1e-30))
+
+
+def _block_labels(gen, B, H, W, blk=8):
+    lab = torch.randint(0, 19, (B, H // blk, W // blk), generator=gen)
+    lab[torch.rand(B, H // blk, W // blk, generator=gen) < 0.05] = 255
+    return lab.repeat_interleave(blk, 1).repeat_interleave(blk, 2)
+
+
+def _unet(cfg, seed, dev):
+    from oracle.weights import synth_state_dict
+    from weatherconverter_b200.diffusion_model.models.unet_base import Unet, param_spec
+    sd = synth_state_dict({k: (v, torch.float32) for k, v in param_spec(cfg).items()}, seed)
+    m = Unet(cfg).to(dev).eval()
+    m.load_state_dict(sd)
+    return m, sd
+
+
+def test_c2_unet_forward_128x256():
+    from oracle.unet import DEFAULT_MODEL_CONFIG, unet_forward
+    dev = _dev()
+    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = 128
+    m, sd = _unet(cfg, 3455, dev)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(1, 3, 128, 256, generator=g)
+    t = torch.tensor([637])
+    t0 = time.time()
+    with torch.no_grad():
+        ref = unet_forward(sd, cfg, x, t)
+    y = m(x.to(dev), t.to(dev)).cpu()
+    rel = float((y - ref).norm() / ref.norm())
+    print(f"C2 shape: rms-rel {rel:.3e} psnr {_psnr(y, ref):.1f} dB max-abs {float((y - ref).abs().max()):.3e} "
+          f"(oracle {time.time() - t0:.1f} s on {torch.get_num_threads()} threads)")
+    assert rel < 1.6e-2 and _psnr(y, ref) > 48
+    # the same image inside a batch of 16 (the C2 batch): independent samples
+    xb = torch.randn(16, 3, 128, 256, generator=g)
+    xb[5] = x[0]
+    yb = m(xb.to(dev), t.to(dev))[5].cpu()
+    rel_b = float((yb - y[0]).norm() / y[0].norm())
+    print(f"C2 batch invariance (image 5 of 16 vs B = 1): rms-rel {rel_b:.3e}")
+    assert rel_b < 2e-3
+
+
+def _c3_models(dev):
+    from oracle import deeplab, srgan
+    from oracle.unet import DEFAULT_MODEL_CONFIG
+    from oracle.weights import synth_state_dict
+    from weatherconverter_b200.seg_model.network import modeling
+    from weatherconverter_b200.srgan_model.models import Generator
+    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = 64
+    unet, unet_sd = _unet(cfg, 3455, dev)
+    seg_sd = synth_state_dict(deeplab.deeplab_param_spec("resnet50"), 42)
+    seg = modeling.deeplabv3plus_resnet50(num_classes=19, output_stride=16, pretrained_backbone=False)
+    seg.load_state_dict(seg_sd)
+    seg = seg.to(dev).eval()
+    gan_sd = synth_state_dict(srgan.srgan_param_spec(), 0)
+    G = Generator(upscale_factor=4)
+    G.load_state_dict(synth_state_dict(G.state_dict(), 0))      # same pure function of (name, shape, seed) as gan_sd
+    G = G.to(dev).eval()
+    return cfg, unet, unet_sd, seg, seg_sd, G, gan_sd
+
+
+def test_c3_geometry_a_two_guided_steps_and_batch_invariance():
+    from oracle import sgg as osgg
+    from oracle.scheduler import OracleScheduler
+    from weatherconverter_b200.diffusion_model.scheduler.linear_noise_scheduler import LinearNoiseScheduler
+    from weatherconverter_b200.translation import sample_with_sgg
+    dev = _dev()
+    cfg, unet, unet_sd, seg, seg_sd, G, gan_sd = _c3_models(dev)
+    gen = torch.Generator().manual_seed(1234)
+    B, h, w, N = 2, 64, 128, 3           # reverse steps i = 2, 1 are guided, i = 0 is x_0 = mu
+    x0 = torch.rand(B, 3, h, w, generator=gen) * 2 - 1
+    gt = _block_labels(gen, B, 4 * h, 4 * w)
+    noise = torch.randn(B, 3, h, w, generator=gen)
+    t_fwd = torch.tensor([N - 1] * B)
+    zs = [torch.randn(B, 3, h, w, generator=gen) for _ in range(N)]
+    t0 = time.time()
+    rec_ref = []
+    sr_ref = osgg.sample_with_sgg(unet_sd, cfg, OracleScheduler(1000, 1e-4, 0.02), seg_sd, gan_sd, x0, gt, noise, t_fwd, zs,
+                                  n_steps=N, record=rec_ref)
+    t_oracle = time.time() - t0
+    sched = LinearNoiseScheduler(1000, 1e-4, 0.02)
+    rec, base = [], []
+    sr = sample_with_sgg(x0, unet, sched, seg, gt, G, n_steps=N, noise=noise, t_forward=t_fwd, step_noise=torch.stack(zs),
+                         record=rec, record_base=base).cpu()
+    print(f"C3 geometry A, B = {B}: oracle {t_oracle:.1f} s")
+    for k in range(N):
+        for b in range(B):
+            y, ref = rec[k][b].cpu(), rec_ref[k][b]
+            print(f"  step {k} image {b}: psnr {_psnr(y, ref):.1f} dB max-abs {float((y - ref).abs().max()):.3e}")
+            assert _psnr(y, ref) > 60, (k, b)
+    for b in range(B):
+        p = _psnr(sr[b], sr_ref[b], 1.0)
+        print(f"  sr_x0 image {b}: psnr {p:.1f} dB")
+        assert sr.shape == (B, 3, 4 * h, 4 * w) and p > 35
+    # the two images really are independent chains with their own labels: swapping the label maps changes the guided x_t
+    rec_sw = []
+    sample_with_sgg(x0, unet, sched, seg, gt.flip(0), G, n_steps=N, noise=noise, t_forward=t_fwd, step_noise=torch.stack(zs),
+                    record=rec_sw)
+    assert not torch.equal(rec_sw[0], rec[0])
+    # ---- batch invariance at the benchmarked batch: image b of a batch-32 guided step vs the same image alone
+    from weatherconverter_b200.sgg.sgg import apply_gsg_batch
+    Bb = 32
+    xt = torch.randn(Bb, 3, h, w, generator=gen).to(dev)
+    gtb = _block_labels(gen, Bb, 4 * h, 4 * w).to(dev)
+    z = torch.randn(Bb, 3, h, w, generator=gen).to(dev)
+
+    def guided_step(xx, gg, zz):
+        eps = unet(xx, torch.tensor([400], device=dev))
+        mu, sigma, _ = sched.sample_prev_timestep(xx, eps, 400, z=zz)
+        out, aux = apply_gsg_batch(seg, mu, sigma, G(xx), gg, 60.0, return_aux=True)
+        return out, mu + sigma, aux["pred"]
+
+    full, full_base, full_pred = guided_step(xt, gtb, z)
+    for b in (0, 17, 31):
+        one, one_base, one_pred = guided_step(xt[b:b + 1].clone(), gtb[b:b + 1].clone(), z[b:b + 1].clone())
+        rel = float((full[b] - one[0]).norm() / one[0].norm())
+        d_full, d_one = (full[b].double() - full_base[b].double()), (one[0].double() - one_base[0].double())
+        rel_g = float((d_full - d_one).norm() / d_one.norm())
+        agree = float((full_pred[b] == one_pred[0]).float().mean())
+        print(f"  batch-32 image {b} vs B = 1: x_t rms-rel {rel:.3e}, guidance term rms-rel {rel_g:.3e}, argmax agreement {agree:.5f}")
+        assert rel < 2e-3 and agree > 0.995
+        assert rel_g < 0.2
+
+
+def test_c5_training_step_128x256():
+    """Loss and gradients of the training step at the C5 geometry (batch 2 instead of 64: same kernels and tile shapes per
+    image; the fp32 oracle's autograd pass over 2 images takes tens of seconds on the host)."""
+    from oracle.scheduler import OracleScheduler
+    from oracle.train import train_step
+    from oracle.unet import DEFAULT_MODEL_CONFIG
+    from weatherconverter_b200.diffusion_model.scheduler.linear_noise_scheduler import LinearNoiseScheduler
+    from weatherconverter_b200.diffusion_model.train_ddpm import DenoisingTrainer
+    dev = _dev()
+    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = 128
+    model, sd = _unet(cfg, 3455, dev)
+    model.train()
+    g = torch.Generator().manual_seed(77)
+    images = torch.rand(2, 3, 128, 256, generator=g) * 2 - 1
+    noise = torch.randn(2, 3, 128, 256, generator=g)
+    t = torch.tensor([37, 811])
+    trainer = DenoisingTrainer(model, LinearNoiseScheduler(1000, 1e-4, 0.02), lr=1e-4)
+    loss = trainer.step(images.to(dev), noise=noise.to(dev), t=t)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    loss_ref, grads, _ = train_step(sd, cfg, images, noise, t, OracleScheduler(1000, 1e-4, 0.02), lr=1e-4)
+    params = dict(model.named_parameters())
+    num = den = 0.0
+    cos_min, worst = 1.0, ("", 0.0)
+    for k, g_ref in grads.items():
+        gg = params[k].grad.detach().cpu()
+        n_, d_ = float((gg - g_ref).norm()), float(g_ref.norm())
+        num += n_ * n_; den += d_ * d_
+        cos_min = min(cos_min, float((gg * g_ref).sum() / (gg.norm() * g_ref.norm() + 1e-20)))
+        if n_ / (d_ + 1e-12) > worst[1]:
+            worst = (k, n_ / (d_ + 1e-12))
+    rel = (num / den) ** 0.5
+    print(f"C5 shape: loss {float(loss):.6f} vs oracle {float(loss_ref):.6f}; gradients global rms-rel {rel:.3e}, worst {worst[0]} "
+          f"{worst[1]:.3e}, min cosine {cos_min:.5f} (oracle {time.time() - t0:.1f} s)")
+    assert abs(float(loss) - float(loss_ref)) < 2e-3 * abs(float(loss_ref))
+    assert rel < 2e-2 and worst[1] < 1e-1 and cos_min > 0.995

@@ -64,6 +64,44 @@ def test_seg_infer_vs_golden(golden):
         assert cos_e > 0.975 and rel_e < 0.25, (tag, cos_e, rel_e)
 
 
+def test_seg_gradient_on_conditioned_fixture(golden):
+    """Input gradient on a WELL-CONDITIONED fixture (tests/golden/seg_conditioned.pt, made by the reference's infer): the last
+    BatchNorm scale of every bottleneck x 0.2, i.e. residual branches are small corrections of the identity path as in a
+    trained ResNet.  There bf16 storage (oracle, EMULATE="bf16") moves the reference's own gradient only to cosine 0.994 /
+    rms-rel 0.11, against 0.974 / 0.23 on the plain random-init fixture and 0.12 / 1.27 with BatchNorm statistics calibrated
+    on a forward pass (random weights + normalisation = exploding backward gains; numbers in DESIGN.md section 4).  The CUDA
+    gradient must reach the same level: cosine >= 0.99, rms-rel <= 0.15, batch of two distinct images."""
+    from oracle import deeplab
+    from oracle.weights import synth_state_dict
+    from weatherconverter_b200.seg_model.network import modeling
+    dev = _dev()
+    d = golden("seg_conditioned.pt")
+    m = modeling.deeplabv3plus_resnet50(num_classes=19, output_stride=16, pretrained_backbone=False)
+    sd = synth_state_dict(m.state_dict(), d["seed"])
+    for k in sd:
+        if k.endswith("bn3.weight"):
+            sd[k] = sd[k] * d["bn3_gain"]
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    out = m.infer(d["x"].to(dev), d["gt"].to(dev), want_grad=True)
+    for b in range(d["x"].shape[0]):
+        grad, ref = out["grad"][b].cpu(), d["grad"][b]
+        cos = float(torch.nn.functional.cosine_similarity(grad.flatten(), ref.flatten(), dim=0))
+        rel = float((grad - ref).norm() / ref.norm())
+        agree = float((out["pred"][b].cpu().to(torch.uint8) == d["pred"][b]).float().mean())
+        deeplab.EMULATE = "bf16"
+        try:
+            _, grad_emu, _ = deeplab.infer(sd, d["x"][b:b + 1], d["gt"][b:b + 1], "resnet50")
+        finally:
+            deeplab.EMULATE = None
+        cos_o = float(torch.nn.functional.cosine_similarity(grad_emu.flatten(), ref.flatten(), dim=0))
+        rel_o = float((grad_emu[0] - ref).norm() / ref.norm())
+        print(f"conditioned image {b}: CUDA vs fp32 reference cosine {cos:.5f} rms-rel {rel:.3e} argmax {agree:.4f} | "
+              f"bf16-storage oracle vs fp32 reference cosine {cos_o:.5f} rms-rel {rel_o:.3e}")
+        assert cos > 0.99 and rel < 0.15, (b, cos, rel)
+        assert agree > 0.99, (b, agree)
+
+
 def test_seg_gradient_has_every_branch(golden):
     """Wiring check: cutting any one gradient branch in the oracle moves its gradient further from the CUDA
     gradient than the full oracle gradient is."""
@@ -148,8 +186,9 @@ def test_apply_gsg_end_to_end(golden):
     guid = ref - (d["mu"] + d["sigma"])          # the guidance term alone
     got = xt - (d["mu"] + d["sigma"])
     rel = float((got - guid).norm() / guid.norm())
-    print(f"apply_gsg: guidance-term rms-rel {rel:.3e}, total max-abs {float((xt - ref).abs().max()):.3e}")
-    assert rel < 0.25
+    cos = float(torch.nn.functional.cosine_similarity(got.flatten(), guid.flatten(), dim=0))
+    print(f"apply_gsg: guidance-term rms-rel {rel:.3e} cosine {cos:.4f}, total max-abs {float((xt - ref).abs().max()):.3e}")
+    assert rel < 0.25 and cos > 0.97
     assert (xt - ref).abs().max() < 1e-3
 
 

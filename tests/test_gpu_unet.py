@@ -1,8 +1,10 @@
 """GPU parity of the UNet forward and the sampling loop against golden vectors from the reference and against
 the CPU oracle (pytest -m gpu on the B200 box).
 
-Tolerances (bf16 storage / fp32 accumulation vs the fp32 reference): single forward
-RMS-relative error <= 2e-2 and PSNR >= 34 dB (peak = max |reference|); both are printed."""
+Tolerances (bf16 storage / fp32 accumulation vs the fp32 reference), asserted at <= 1.25x what was measured
+on B200 (round 1: single forward RMS-relative error 1.05e-2 .. 1.35e-2, PSNR 50.3 .. 52.8 dB; 12-step trajectory PSNR 78 dB
+at step 1 -> 64 dB at step 12): single forward rms-rel <= 1.6e-2 and PSNR >= 48 dB (peak = max |reference|), trajectory
+PSNR >= 62 dB at every step; all are printed."""
 import math
 
 import pytest
@@ -41,7 +43,7 @@ def test_unet_forward_vs_golden(golden):
         y = m(d["x"].to(dev), d["t"].to(dev)).cpu()
         rel, psnr, mx = _metrics(y, d["y"])
         print(f"{tag}: rms-rel {rel:.3e} psnr {psnr:.1f} dB max-abs {mx:.3e} launches {m.launches_per_forward()}")
-        assert rel < 2e-2 and psnr > 34, (tag, rel, psnr)
+        assert rel < 1.6e-2 and psnr > 48, (tag, rel, psnr)
         # a second call on the bound plan must give the same bits (deterministic kernels)
         y2 = m(d["x"].to(dev), d["t"].to(dev)).cpu()
         assert torch.equal(y, y2)
@@ -61,7 +63,7 @@ def test_unet_forward_vs_oracle_taps():
     y = m(x.to(dev), t.to(dev)).cpu()
     rel, psnr, mx = _metrics(y, ref)
     print(f"batched-t: rms-rel {rel:.3e} psnr {psnr:.1f} dB")
-    assert rel < 2e-2 and psnr > 34
+    assert rel < 1.6e-2 and psnr > 48
 
 
 def test_sample_trajectory_vs_golden(golden):
@@ -76,5 +78,5 @@ def test_sample_trajectory_vs_golden(golden):
     for k in (0, d["T"] // 2, d["T"] - 1):
         rel, psnr, mx = _metrics(rec[k].cpu(), d["traj"][k])
         print(f"step {k}: rms-rel {rel:.3e} psnr {psnr:.1f} dB max-abs {mx:.3e}")
-        assert psnr > 30, (k, psnr)
+        assert psnr > 62, (k, psnr)
     assert torch.equal(x0, rec[-1])

@@ -101,8 +101,11 @@ a, b = shard_range(6, w, r)
 local = initial_noise((3, 4, 4), a, b)
 parts = gather_images(local, w)
 t = torch.tensor([float(r + 1)]); dist.all_reduce(t, op=dist.ReduceOp.MAX)   # bench.py's max-over-ranks timing
+a7, b7 = shard_range(7, w, r)            # uneven shards (4 + 3): padded gather, sliced on rank 0
+parts7 = gather_images(initial_noise((3, 4, 4), a7, b7), w, global_batch=7)
 if r == 0:
     assert torch.equal(torch.cat(parts), initial_noise((3, 4, 4), 0, 6)) and float(t) == w
+    assert [p.shape[0] for p in parts7] == [4, 3] and torch.equal(torch.cat(parts7), initial_noise((3, 4, 4), 0, 7))
     print("GLOO_OK")
 dist.destroy_process_group()
 """
@@ -225,3 +228,38 @@ def test_tma_epilogue_quadrant_boxes_cover_the_tile_in_lane_order():
                 # position of box row `lane`: x fastest, then y, then b
                 bx, by, bz = lane % qw, (lane // qw) % qh, lane // (qw * qh)
                 assert (xx, yy, bb) == (qx0 + bx, qy0 + by, qb0 + bz), (tb, th, tw, quad, lane)
+
+
+def test_load_model_reads_reference_checkpoint_formats(tmp_path):
+    """The three reference-named load_model functions ingest the reference's checkpoint dictionaries (sample_ddpm.py:56-61
+    'model_state_dict'; srgan_model/inference.py:9-16 'model'; seg_model/inference.py:27-33 'model_state_dict' + config name)
+    and leave the module in eval mode with exactly the saved values.  (Host-side part; the GPU forward after loading is
+    tests/test_gpu_parity_rows.py.)"""
+    import torch
+    from oracle import deeplab
+    from oracle.unet import DEFAULT_MODEL_CONFIG
+    from oracle.weights import synth_state_dict
+    from weatherconverter_b200.diffusion_model.config.models import ModelConfig
+    from weatherconverter_b200.diffusion_model.models.unet_base import param_spec
+    from weatherconverter_b200.diffusion_model import sample_ddpm
+    from weatherconverter_b200.seg_model import inference as seg_inference
+    from weatherconverter_b200.srgan_model import inference as srgan_inference
+    from weatherconverter_b200.srgan_model.models import Generator
+    cfg = dict(DEFAULT_MODEL_CONFIG)
+    sd = synth_state_dict({k: (v, torch.float32) for k, v in param_spec(cfg).items()}, 5)
+    torch.save({"model_state_dict": sd, "optimizer_state_dict": {}, "epoch": 7}, tmp_path / "u.ckpt")
+    m = sample_ddpm.load_model(str(tmp_path / "u.ckpt"), ModelConfig(**cfg))
+    got = m.state_dict()
+    assert not m.training and list(got) == list(sd) and all(torch.equal(got[k].cpu(), sd[k]) for k in sd)
+    sdg = synth_state_dict(Generator(upscale_factor=4).state_dict(), 6)
+    torch.save({"model": sdg}, tmp_path / "g.pth.tar")
+    G = srgan_inference.load_model(str(tmp_path / "g.pth.tar"))
+    got = G.state_dict()
+    assert not G.training and all(torch.equal(got[k].cpu(), sdg[k]) for k in sdg)
+    with pytest.raises(KeyError):     # a diffusion-style file is not an SRGAN checkpoint
+        srgan_inference.load_model(str(tmp_path / "u.ckpt"))
+    sds = synth_state_dict(deeplab.deeplab_param_spec("resnet101"), 8)
+    torch.save({"model_state_dict": sds, "epoch": 40, "loss": 0.0}, tmp_path / "s.pth")
+    S = seg_inference.load_model(str(tmp_path / "s.pth"), {"name": "deeplabv3plus_resnet101", "num_classes": 19, "output_stride": 16})
+    got = S.state_dict()
+    assert not S.training and set(got) == set(sds) and all(torch.equal(got[k].cpu(), sds[k]) for k in sds)

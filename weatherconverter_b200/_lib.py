@@ -38,8 +38,11 @@ _SIGS = {
     "wc_profile_detail": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "wc_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     "wc_ddpm_step": (C.c_int, [c_ptr] * 6 + [C.c_size_t, C.c_int] + [C.c_float] * 4 + [c_ptr]),
-    "wc_ddpm_step_batched": (C.c_int, [c_ptr] * 6 + [C.c_size_t, C.c_int] + [c_ptr] * 4 + [c_ptr]),
-    "wc_add_noise": (C.c_int, [c_ptr] * 3 + [C.c_size_t, C.c_int] + [c_ptr] * 3 + [c_ptr]),
+    "wc_ddpm_step_batched": (C.c_int, [c_ptr] * 6 + [C.c_size_t, C.c_int] + [c_ptr] * 4 + [C.c_int, c_ptr]),
+    "wc_ddpm_step_indexed": (C.c_int, [c_ptr] * 6 + [C.c_size_t, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr]),
+    "wc_add_noise": (C.c_int, [c_ptr] * 3 + [C.c_size_t, C.c_int] + [c_ptr] * 3 + [C.c_int, c_ptr]),
+    "wc_set_time_factor_table": (C.c_int, [C.POINTER(C.c_float), C.c_int]),
+    "wc_time_embedding": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr]),
     "wc_sgg_update": (C.c_int, [c_ptr] * 5 + [C.c_int] * 4 + [C.c_float, c_ptr]),
     "wc_lcg_prepare": (C.c_int, [c_ptr] * 4 + [C.c_int] * 4 + [c_ptr]),
     "wc_lcg_combine": (C.c_int, [c_ptr] * 5 + [C.c_int] * 5 + [C.c_float, c_ptr]),

@@ -192,7 +192,21 @@ __global__ void conv_small_cout_kernel(const __nv_bfloat16* __restrict__ x, cons
 // ---------------------------------------------------------------------------------------------------------
 // Time embedding: emb = [sin(t/f_j), cos(t/f_j)], f_j = 10000^(j/half); h = W2 silu(W1 emb + b1) + b2;
 // writes silu(h) (every consumer applies SiLU first, unet_base.py:97) and h itself.
-__global__ void temb_mlp_kernel(const long long* __restrict__ t, int dim, const float* __restrict__ w1,
+// `factor` (optional, [dim/2]): the reference's 10000**(arange/half) table as torch evaluates it on the host
+// (unet_base.py:22-24), so that t/factor is bit-identical to the reference's argument; NULL -> powf on the device.
+__global__ void time_embedding_kernel(const long long* __restrict__ t, int dim, const float* __restrict__ factor,
+                                      float* __restrict__ out) {
+  const int b = blockIdx.x, half = dim / 2;
+  const float tv = static_cast<float>(t[b]);
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    const float a = tv / time_factor(factor, j, half);
+    out[static_cast<size_t>(b) * dim + j] = sinf(a);
+    out[static_cast<size_t>(b) * dim + j + half] = cosf(a);
+  }
+}
+
+__global__ void temb_mlp_kernel(const long long* __restrict__ t, int dim, const float* __restrict__ factor,
+                                const float* __restrict__ w1,
                                 const float* __restrict__ b1, const float* __restrict__ w2,
                                 const float* __restrict__ b2, float* __restrict__ temb, float* __restrict__ temb_silu) {
   extern __shared__ float sh[];  // emb[dim], h1[dim]
@@ -201,8 +215,7 @@ __global__ void temb_mlp_kernel(const long long* __restrict__ t, int dim, const 
   const int b = blockIdx.x, half = dim / 2;
   const float tv = static_cast<float>(t[b]);
   for (int j = threadIdx.x; j < half; j += blockDim.x) {
-    const float factor = powf(10000.0f, static_cast<float>(j) / static_cast<float>(half));
-    const float a = tv / factor;
+    const float a = tv / time_factor(factor, j, half);
     emb[j] = sinf(a);
     emb[j + half] = cosf(a);
   }
@@ -361,7 +374,15 @@ int conv_small_cout(const __nv_bfloat16* x, const float* w, const float* bias, f
 
 int temb_mlp(const long long* t, int Bt, int dim, const float* w1, const float* b1, const float* w2, const float* b2,
              float* temb, float* temb_silu, cudaStream_t st) {
-  temb_mlp_kernel<<<Bt, 128, 2 * dim * sizeof(float), st>>>(t, dim, w1, b1, w2, b2, temb, temb_silu);
+  temb_mlp_kernel<<<Bt, 128, 2 * dim * sizeof(float), st>>>(t, dim, time_factor_table(dim / 2), w1, b1, w2, b2, temb, temb_silu);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+// get_time_embedding (unet_base.py:7-30): out [n, dim] = [sin(t/f), cos(t/f)]
+int time_embedding(const long long* t, int n, int dim, float* out, cudaStream_t st) {
+  WC_REQUIRE(n >= 1 && dim >= 2 && dim % 2 == 0, "time_embedding: dim must be even");
+  time_embedding_kernel<<<n, 64, 0, st>>>(t, dim, time_factor_table(dim / 2), out);
   WC_LAUNCH_CHECK();
   return 0;
 }

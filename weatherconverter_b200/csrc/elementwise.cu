@@ -12,24 +12,41 @@ struct StepCoef {
   float beta, s, sqrt_alpha, sigma;
 };
 
+// timesteps index the [T] tables: a value outside [0, T) (where the reference raises IndexError) is clamped on the device;
+// the host wrappers range-check host-side t tensors and raise
+__device__ __forceinline__ long long clamp_t(long long t, int T) { return t < 0 ? 0 : (t >= T ? T - 1 : t); }
+
 __device__ __forceinline__ float ddpm_mean(float x, float e, const StepCoef& c) {
   float m = __fsub_rn(x, __fdiv_rn(__fmul_rn(c.beta, e), c.s));
   return __fdiv_rn(m, c.sqrt_alpha);
 }
 
-template <bool kBatched>
+// kMode 0: coefficients by value (host-side scalar t); 1: sample_prev_timestep2 (per-sample t gather, sigma^2 = beta);
+// 2: scalar t READ FROM DEVICE MEMORY, coefficients gathered from four host-built [T] tables (betas = {beta, s, sqrt_alpha,
+//    sigma} rows) - the same fp32 values mode 0 receives by value, so results are bit-identical, but the launch no longer
+//    depends on the step index and a captured CUDA graph of the reverse step can be replayed for every t > 0.
+template <int kMode>
 __global__ void __launch_bounds__(256)
 ddpm_step_kernel(const float4* __restrict__ xt, const float4* __restrict__ eps, const float4* __restrict__ z,
                  float4* __restrict__ out, float4* __restrict__ mean_out, float4* __restrict__ sigz_out,
                  size_t n4_per_sample, int B, StepCoef c, const float* __restrict__ betas,
                  const float* __restrict__ alphas, const float* __restrict__ sqrt_1m_acp,
-                 const long long* __restrict__ t) {
+                 const long long* __restrict__ t, int T) {
   const size_t total = n4_per_sample * B;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     StepCoef cc = c;
-    if (kBatched) {  // sample_prev_timestep2 (scheduler.py:63-77): per-sample gather, sigma^2 = beta
-      const long long tb = t[i / n4_per_sample];
+    bool use_z = z != nullptr;
+    if (kMode == 2) {
+      const long long tb = clamp_t(t[0], T);
+      cc.beta = betas[tb];
+      cc.s = betas[T + tb];
+      cc.sqrt_alpha = betas[2 * T + tb];
+      cc.sigma = betas[3 * T + tb];
+      use_z = use_z && tb != 0;      // t == 0: x_0 = mean (scheduler.py:102-103)
+    }
+    if (kMode == 1) {  // sample_prev_timestep2 (scheduler.py:63-77): per-sample gather, sigma^2 = beta
+      const long long tb = clamp_t(t[i / n4_per_sample], T);
       cc.beta = betas[tb];
       cc.s = sqrt_1m_acp[tb];
       cc.sqrt_alpha = __fsqrt_rn(alphas[tb]);
@@ -40,7 +57,8 @@ ddpm_step_kernel(const float4* __restrict__ xt, const float4* __restrict__ eps, 
     m.x = ddpm_mean(x.x, e.x, cc); m.y = ddpm_mean(x.y, e.y, cc);
     m.z = ddpm_mean(x.z, e.z, cc); m.w = ddpm_mean(x.w, e.w, cc);
     if (mean_out) mean_out[i] = m;
-    if (z) {
+    if (kMode == 2 && !use_z && sigz_out) sigz_out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (use_z) {
       const float4 zz = z[i];
       float4 s;
       s.x = __fmul_rn(cc.sigma, zz.x); s.y = __fmul_rn(cc.sigma, zz.y);
@@ -56,11 +74,11 @@ ddpm_step_kernel(const float4* __restrict__ xt, const float4* __restrict__ eps, 
 __global__ void __launch_bounds__(256)
 add_noise_kernel(const float4* __restrict__ x0, const float4* __restrict__ noise, float4* __restrict__ out,
                  size_t n4_per_sample, int B, const float* __restrict__ sqrt_acp,
-                 const float* __restrict__ sqrt_1m_acp, const long long* __restrict__ t) {
+                 const float* __restrict__ sqrt_1m_acp, const long long* __restrict__ t, int T) {
   const size_t total = n4_per_sample * B;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const long long tb = t[i / n4_per_sample];
+    const long long tb = clamp_t(t[i / n4_per_sample], T);
     const float a = sqrt_acp[tb], b = sqrt_1m_acp[tb];
     const float4 x = x0[i], e = noise[i];
     float4 o;
@@ -175,35 +193,52 @@ int ddpm_step(const float* xt, const float* eps, const float* z, float* out, flo
   StepCoef c{beta, s, sqrt_alpha, sigma};
   const size_t n4 = n_per_sample / 4;
   ProfScope prof(kProfScheduler, st, 4.0 * n_per_sample * B * (2 + (z ? 1 : 0) + (out ? 1 : 0) + (mean_out ? 1 : 0) + (sigz_out ? 1 : 0)));
-  ddpm_step_kernel<false><<<grid_for(n4 * B), 256, 0, st>>>(
+  ddpm_step_kernel<0><<<grid_for(n4 * B), 256, 0, st>>>(
       reinterpret_cast<const float4*>(xt), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(z),
       reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(mean_out), reinterpret_cast<float4*>(sigz_out), n4, B,
-      c, nullptr, nullptr, nullptr, nullptr);
+      c, nullptr, nullptr, nullptr, nullptr, 1);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
+int ddpm_step_indexed(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
+                      size_t n_per_sample, int B, const float* coef_tables, const long long* t_dev, int T, cudaStream_t st) {
+  WC_REQUIRE(n_per_sample % 4 == 0, "elements per sample must be a multiple of 4");
+  WC_REQUIRE(T >= 1 && coef_tables && t_dev, "ddpm_step_indexed: tables and the device timestep are required");
+  StepCoef c{0, 1, 1, 0};
+  const size_t n4 = n_per_sample / 4;
+  ProfScope prof(kProfScheduler, st, 4.0 * n_per_sample * B * (2 + (z ? 1 : 0) + (out ? 1 : 0) + (mean_out ? 1 : 0) + (sigz_out ? 1 : 0)));
+  ddpm_step_kernel<2><<<grid_for(n4 * B), 256, 0, st>>>(
+      reinterpret_cast<const float4*>(xt), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(z),
+      reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(mean_out), reinterpret_cast<float4*>(sigz_out), n4, B,
+      c, coef_tables, nullptr, nullptr, t_dev, T);
   WC_LAUNCH_CHECK();
   return 0;
 }
 
 int ddpm_step_batched(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
                       size_t n_per_sample, int B, const float* betas, const float* alphas, const float* sqrt_1m_acp,
-                      const long long* t, cudaStream_t st) {
+                      const long long* t, int T, cudaStream_t st) {
   WC_REQUIRE(n_per_sample % 4 == 0, "elements per sample must be a multiple of 4");
+  WC_REQUIRE(T >= 1, "num_timesteps must be positive");
   StepCoef c{0, 1, 1, 0};
   const size_t n4 = n_per_sample / 4;
-  ddpm_step_kernel<true><<<grid_for(n4 * B), 256, 0, st>>>(
+  ddpm_step_kernel<1><<<grid_for(n4 * B), 256, 0, st>>>(
       reinterpret_cast<const float4*>(xt), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(z),
       reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(mean_out), reinterpret_cast<float4*>(sigz_out), n4, B,
-      c, betas, alphas, sqrt_1m_acp, t);
+      c, betas, alphas, sqrt_1m_acp, t, T);
   WC_LAUNCH_CHECK();
   return 0;
 }
 
 int add_noise(const float* x0, const float* noise, float* out, size_t n_per_sample, int B, const float* sqrt_acp,
-              const float* sqrt_1m_acp, const long long* t, cudaStream_t st) {
+              const float* sqrt_1m_acp, const long long* t, int T, cudaStream_t st) {
   WC_REQUIRE(n_per_sample % 4 == 0, "elements per sample must be a multiple of 4");
+  WC_REQUIRE(T >= 1, "num_timesteps must be positive");
   const size_t n4 = n_per_sample / 4;
   add_noise_kernel<<<grid_for(n4 * B), 256, 0, st>>>(reinterpret_cast<const float4*>(x0),
                                                       reinterpret_cast<const float4*>(noise),
-                                                      reinterpret_cast<float4*>(out), n4, B, sqrt_acp, sqrt_1m_acp, t);
+                                                      reinterpret_cast<float4*>(out), n4, B, sqrt_acp, sqrt_1m_acp, t, T);
   WC_LAUNCH_CHECK();
   return 0;
 }

@@ -148,7 +148,8 @@ __global__ void flip_transpose_3x3_kernel(const float* __restrict__ w, float* __
 
 // ------------------------------------------------------------------------------------------------ time embedding
 // forward, saving what the backward needs: emb [B][dim], h1 (pre-SiLU) [B][dim], temb (pre-SiLU) [B][dim], silu(temb)
-__global__ void temb_mlp_train_kernel(const long long* __restrict__ t, int dim, const float* __restrict__ w1,
+__global__ void temb_mlp_train_kernel(const long long* __restrict__ t, int dim, const float* __restrict__ factor,
+                                      const float* __restrict__ w1,
                                       const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                       float* __restrict__ emb_out, float* __restrict__ h1_out, float* __restrict__ temb,
                                       float* __restrict__ temb_silu) {
@@ -158,8 +159,7 @@ __global__ void temb_mlp_train_kernel(const long long* __restrict__ t, int dim, 
   const int b = blockIdx.x, half = dim / 2;
   const float tv = static_cast<float>(t[b]);
   for (int j = threadIdx.x; j < half; j += blockDim.x) {
-    const float factor = powf(10000.0f, static_cast<float>(j) / static_cast<float>(half));
-    const float a = tv / factor;
+    const float a = tv / time_factor(factor, j, half);
     emb[j] = sinf(a);
     emb[j + half] = cosf(a);
   }
@@ -322,7 +322,7 @@ int flip_transpose_3x3(const float* w, float* wt, int Co, int Ci, cudaStream_t s
 
 int temb_mlp_train(const long long* t, int Bt, int dim, const float* w1, const float* b1, const float* w2, const float* b2,
                    float* emb, float* h1, float* temb, float* temb_silu, cudaStream_t st) {
-  temb_mlp_train_kernel<<<Bt, 128, 2 * dim * sizeof(float), st>>>(t, dim, w1, b1, w2, b2, emb, h1, temb, temb_silu);
+  temb_mlp_train_kernel<<<Bt, 128, 2 * dim * sizeof(float), st>>>(t, dim, time_factor_table(dim / 2), w1, b1, w2, b2, emb, h1, temb, temb_silu);
   WC_LAUNCH_CHECK();
   return 0;
 }

@@ -9,9 +9,11 @@ int ddpm_step(const float* xt, const float* eps, const float* z, float* out, flo
               size_t n_per_sample, int B, float beta, float s, float sqrt_alpha, float sigma, cudaStream_t st);
 int ddpm_step_batched(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
                       size_t n_per_sample, int B, const float* betas, const float* alphas, const float* sqrt_1m_acp,
-                      const long long* t, cudaStream_t st);
+                      const long long* t, int T, cudaStream_t st);
+int ddpm_step_indexed(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
+                      size_t n_per_sample, int B, const float* coef_tables, const long long* t_dev, int T, cudaStream_t st);
 int add_noise(const float* x0, const float* noise, float* out, size_t n_per_sample, int B, const float* sqrt_acp,
-              const float* sqrt_1m_acp, const long long* t, cudaStream_t st);
+              const float* sqrt_1m_acp, const long long* t, int T, cudaStream_t st);
 int sgg_update(const float* grad, const float* mu, const float* sigz, float* out, float* mag_out, int B, int h, int w,
                int pool, float lam, cudaStream_t st);
 int lcg_prepare(const float* sr, const long long* gt, float* xm, long long* gm, int B, int NC, size_t hw, cudaStream_t st);
@@ -64,6 +66,7 @@ int boundary_wgrad(const __nv_bfloat16* wide, int ldw, const float* narrow, int 
                    float* dbias, void* scratch, cudaStream_t st);
 int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps, int step,
               float grad_scale, cudaStream_t st);
+int time_embedding(const long long* t, int n, int dim, float* out, cudaStream_t st);
 int ddpm_grid_u8(const float* x, uint8_t* out, int B, int H, int W, int nrow, int pad, cudaStream_t st);
 int postprocess_u8(const float* x, uint8_t* out, int B, int H, int W, const float* mean3, const float* std3, cudaStream_t st);
 int label_encode(const uint8_t* lab, int Ws, const int* ytab, const int* xtab, int top, int left, int Hc, int Wc, const long long* lut,
@@ -82,7 +85,7 @@ static inline const __nv_bfloat16* BF(const wc_bf16* p) { return reinterpret_cas
 extern "C" {
 
 const char* wc_last_error(void) { return last_error_cstr(); }
-int wc_abi_version(void) { return 1; }
+int wc_abi_version(void) { return 2; }
 long long wc_launch_count(void) { return launch_count(); }
 void wc_profile_begin(void) { prof_start(); }
 int wc_profile_detail(int cap, int* cls, double* ms, double* work, int* info) { return prof_detail(cap, cls, ms, work, info); }
@@ -98,14 +101,24 @@ int wc_ddpm_step(const float* xt, const float* eps, const float* z, float* out, 
 }
 int wc_ddpm_step_batched(const float* xt, const float* eps, const float* z, float* out, float* mean_out,
                          float* sigz_out, size_t n_per_sample, int batch, const float* betas, const float* alphas,
-                         const float* sqrt_one_minus_acp, const int64_t* t, void* stream) {
+                         const float* sqrt_one_minus_acp, const int64_t* t, int num_timesteps, void* stream) {
   return ddpm_step_batched(xt, eps, z, out, mean_out, sigz_out, n_per_sample, batch, betas, alphas, sqrt_one_minus_acp,
-                           reinterpret_cast<const long long*>(t), S(stream));
+                           reinterpret_cast<const long long*>(t), num_timesteps, S(stream));
+}
+int wc_ddpm_step_indexed(const float* xt, const float* eps, const float* z, float* out, float* mean_out, float* sigz_out,
+                         size_t n_per_sample, int batch, const float* coef_tables, const int64_t* t_dev, int num_timesteps,
+                         void* stream) {
+  return ddpm_step_indexed(xt, eps, z, out, mean_out, sigz_out, n_per_sample, batch, coef_tables,
+                           reinterpret_cast<const long long*>(t_dev), num_timesteps, S(stream));
 }
 int wc_add_noise(const float* x0, const float* noise, float* out, size_t n_per_sample, int batch,
-                 const float* sqrt_acp, const float* sqrt_one_minus_acp, const int64_t* t, void* stream) {
+                 const float* sqrt_acp, const float* sqrt_one_minus_acp, const int64_t* t, int num_timesteps, void* stream) {
   return add_noise(x0, noise, out, n_per_sample, batch, sqrt_acp, sqrt_one_minus_acp,
-                   reinterpret_cast<const long long*>(t), S(stream));
+                   reinterpret_cast<const long long*>(t), num_timesteps, S(stream));
+}
+int wc_set_time_factor_table(const float* factor_host, int half) { return set_time_factor_table(factor_host, half); }
+int wc_time_embedding(const int64_t* t, int n, int dim, float* out, void* stream) {
+  return time_embedding(reinterpret_cast<const long long*>(t), n, dim, out, S(stream));
 }
 int wc_sgg_update(const float* grad, const float* mu, const float* sigz, float* out, float* mag_out, int batch, int h,
                   int w, int pool, float lambda, void* stream) {

@@ -86,6 +86,30 @@ int num_sms() {
   return sms;
 }
 
+namespace {
+struct TimeFactor { float* dev = nullptr; int half = 0; int device = -1; };
+TimeFactor g_tf;
+}  // namespace
+int set_time_factor_table(const float* host_table, int half) {
+  WC_REQUIRE(host_table && half > 0 && half <= 4096, "time factor table: bad size");
+  int dev = 0;
+  WC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (g_tf.dev && (g_tf.half != half || g_tf.device != dev)) {
+    cudaFree(g_tf.dev);
+    g_tf = TimeFactor{};
+  }
+  if (!g_tf.dev) WC_CHECK_CUDA(cudaMalloc(&g_tf.dev, sizeof(float) * half));
+  WC_CHECK_CUDA(cudaMemcpy(g_tf.dev, host_table, sizeof(float) * half, cudaMemcpyHostToDevice));
+  g_tf.half = half;
+  g_tf.device = dev;
+  return 0;
+}
+const float* time_factor_table(int half) {
+  int dev = 0;
+  if (!g_tf.dev || g_tf.half != half || cudaGetDevice(&dev) != cudaSuccess || dev != g_tf.device) return nullptr;
+  return g_tf.dev;
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   static std::once_flag once;

@@ -55,6 +55,17 @@ struct ProfScope {
 };
 
 int num_sms();
+
+// Time-embedding factor table (unet_base.py:22-24: 10000 ** (arange(half) / half), fp32): the host evaluates the reference's
+// torch expression once and hands the table over, so the embedding's argument t / factor is bit-identical to the reference's.
+// time_factor_table(half) returns the device copy for the current device, or nullptr (the kernels then use powf).
+int set_time_factor_table(const float* host_table, int half);
+const float* time_factor_table(int half);
+#ifdef __CUDACC__
+__device__ __forceinline__ float time_factor(const float* table, int j, int half) {
+  return table ? table[j] : powf(10000.0f, static_cast<float>(j) / static_cast<float>(half));
+}
+#endif
 const char* last_error_cstr();
 
 // NHWC bf16 activation view: element (b,y,x,c) at ptr[((b*H + y)*W + x)*ld + c]; ld >= C lets a view

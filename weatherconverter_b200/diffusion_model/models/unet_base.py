@@ -194,6 +194,7 @@ class Unet(nn.Module):
         c_numels = (C.c_int64 * n)(*[t.numel() for t in tensors])
         handle = C.c_void_p()
         cfg = self._config_struct()
+        set_time_factor_table(self.t_emb_dim, device)
         check(lib().wc_unet_create(C.byref(handle), C.byref(cfg), n, c_names, c_ptrs, c_numels, stream_ptr()))
         self._handle, self._handle_key, self._keepalive = handle, key, tensors
         self._workspaces = {}
@@ -237,11 +238,30 @@ class Unet(nn.Module):
         return int(lib().wc_unet_launches(self._handle)) if self._handle is not None else 0
 
 
-def get_time_embedding(time_steps, temb_dim):
-    """Sinusoidal embedding (reference :7-30); kept for API parity.  The UNet computes it on-device in
-    csrc/direct.cu (temb_mlp_kernel); this host version is only a convenience for callers of the old helper."""
-    assert temb_dim % 2 == 0, "time embedding dimension must be divisible by 2"
+_FACTOR_SET = {}
+
+
+def set_time_factor_table(temb_dim, device):
+    """Hand the reference's factor table (reference :22-24, evaluated by torch on the host exactly as written there) to the
+    library once per (device, dim): every time-embedding kernel then divides t by the reference's own fp32 factors."""
+    key = (str(device), temb_dim)
+    if _FACTOR_SET.get("key") == key:
+        return
     half = temb_dim // 2
-    factor = 10000 ** (torch.arange(0, half, dtype=torch.float32, device=time_steps.device) / half)
-    e = time_steps[:, None].repeat(1, half) / factor
-    return torch.cat([torch.sin(e), torch.cos(e)], dim=-1)
+    factor = 10000 ** (torch.arange(start=0, end=half, dtype=torch.float32) / half)
+    arr = (C.c_float * half)(*factor.tolist())
+    with torch.cuda.device(device):
+        check(lib().wc_set_time_factor_table(arr, half))
+    _FACTOR_SET["key"] = key
+
+
+def get_time_embedding(time_steps, temb_dim):
+    """Sinusoidal embedding (reference :7-30) as its own kernel (csrc/direct.cu: time_embedding_kernel - the same code
+    the UNet plan runs inside temb_mlp_kernel): [B] int tensor on the GPU -> [B, temb_dim] fp32."""
+    assert temb_dim % 2 == 0, "time embedding dimension must be divisible by 2"
+    _lib.require_cuda(time_steps)
+    t = time_steps.long().contiguous().reshape(-1)
+    set_time_factor_table(temb_dim, t.device)
+    out = torch.empty(t.numel(), temb_dim, device=t.device)
+    check(lib().wc_time_embedding(ptr(t), t.numel(), temb_dim, ptr(out), stream_ptr()))
+    return out

@@ -34,19 +34,51 @@ class LinearNoiseScheduler:
         for k, v in self._host.items():
             setattr(self, k, v.to(device))
 
+    # ---- argument hygiene: the kernels take raw fp32 pointers, so everything is cast / checked here -------------------
+    @staticmethod
+    def _f32(*tensors):
+        """Contiguous fp32 views (a float64 x_t - which the reference's apply_gsg returns - or a bf16 tensor is converted,
+        never reinterpreted); all tensors must have the first one's shape."""
+        out = []
+        for x in tensors:
+            if x is None:
+                out.append(None)
+                continue
+            if x.shape != tensors[0].shape:
+                raise RuntimeError(f"shape mismatch: {tuple(x.shape)} vs {tuple(tensors[0].shape)}")
+            out.append(x.contiguous().float())
+        return out
+
+    def _check_t_scalar(self, t):
+        t = int(t)
+        if not 0 <= t < self.num_timesteps:   # the reference's table lookup raises IndexError here
+            raise IndexError(f"timestep {t} is out of range for a {self.num_timesteps}-step schedule")
+        return t
+
+    def _check_t_batched(self, t, B, device):
+        t = torch.as_tensor(t).long().reshape(-1)
+        if t.numel() not in (1, B):
+            raise RuntimeError(f"t must have 1 or {B} entries, got {t.numel()}")
+        # range check on the host for host tensors (the usual case: the reference draws t on the CPU, train_ddpm.py:102);
+        # a device tensor is not read back (that would be a sync per step) - the kernels clamp the table index instead
+        if t.device.type == "cpu" and t.numel() and (int(t.min()) < 0 or int(t.max()) >= self.num_timesteps):
+            raise IndexError(f"timestep out of range for a {self.num_timesteps}-step schedule")
+        t = t.to(device)
+        if t.numel() == 1 and B > 1:
+            t = t.expand(B)
+        return t.contiguous()
+
     # ---- forward process ------------------------------------------------------------------------------
     def add_noise(self, original, noise, t):
         """sqrt(acp[t]) * x0 + sqrt(1 - acp[t]) * noise with per-sample t [B] (reference :37-61)."""
         _lib.require_cuda(original, noise)
-        original, noise = original.contiguous().float(), noise.contiguous().float()
+        original, noise = self._f32(original, noise)
         B = original.shape[0]
-        t = torch.as_tensor(t, device=original.device).long().reshape(-1)
-        if t.numel() == 1 and B > 1:
-            t = t.expand(B).contiguous()
+        t = self._check_t_batched(t, B, original.device)
         out = torch.empty_like(original)
         ta, tb = self.sqrt_alpha_cum_prod.to(original.device), self.sqrt_one_minus_alpha_cum_prod.to(original.device)
         check(lib().wc_add_noise(ptr(original), ptr(noise), ptr(out), original[0].numel(), B, ptr(ta), ptr(tb), ptr(t),
-                                 stream_ptr()))
+                                 self.num_timesteps, stream_ptr()))
         return out
 
     add_noise2 = add_noise  # reference :30-35 (same arithmetic, tables indexed on the module device)
@@ -58,23 +90,56 @@ class LinearNoiseScheduler:
     def step(self, xt, noise_pred, t: int, z=None):
         """x_{t-1} in ONE launch: mean + sigma_t * z (z ignored at t == 0).  Fused form of
         sample_prev_timestep + the caller's ``mean + sigma`` (sample_ddpm.py:42-44)."""
-        _lib.require_cuda(xt, noise_pred)
-        t = int(t)
-        xt, noise_pred = xt.contiguous(), noise_pred.contiguous()
+        _lib.require_cuda(xt, noise_pred, z)
+        t = self._check_t_scalar(t)
+        xt, noise_pred = self._f32(xt, noise_pred)
         if t != 0 and z is None:
             z = self._draw(xt)
-        zz = z.contiguous() if t != 0 else None
+        zz = self._f32(xt, z)[1] if t != 0 else None
         out = torch.empty_like(xt)
         c = self._coef
         check(lib().wc_ddpm_step(ptr(xt), ptr(noise_pred), ptr(zz), ptr(out), None, None, xt[0].numel(), xt.shape[0],
                                  c["beta"][t], c["s"][t], c["sqrt_alpha"][t], c["sigma"][t], stream_ptr()))
         return out
 
+    # ---- device-indexed form (CUDA-graph friendly): the timestep lives in a device int64 scalar ----------------------
+    def _tables_on(self, dev):
+        key = str(dev)
+        cache = self.__dict__.setdefault("_coef_dev", {})
+        if key not in cache:
+            c = self._coef
+            cache[key] = torch.tensor([c["beta"], c["s"], c["sqrt_alpha"], c["sigma"]], dtype=torch.float32).to(dev).contiguous()
+        return cache[key]
+
+    def sample_prev_timestep_indexed(self, xt, noise_pred, t_dev, z, out=None):
+        """(mean, sigma*z[, x_{t-1} into ``out``]) like sample_prev_timestep / step, with t read on the device from ``t_dev``
+        (int64 tensor with one element).  Same fp32 coefficients as the scalar path -> bit-identical results, but nothing in
+        the launch depends on t, so a captured reverse step can be replayed for every t > 0 (at t == 0 z is ignored)."""
+        _lib.require_cuda(xt, noise_pred, z, t_dev)
+        if t_dev.dtype != torch.int64 or t_dev.numel() != 1:
+            raise RuntimeError("t_dev must be a CUDA int64 tensor with one element")
+        xt, noise_pred, z = self._f32(xt, noise_pred, z)
+        mean, sigz = torch.empty_like(xt), torch.empty_like(xt)
+        check(lib().wc_ddpm_step_indexed(ptr(xt), ptr(noise_pred), ptr(z), ptr(out), ptr(mean), ptr(sigz), xt[0].numel(),
+                                         xt.shape[0], ptr(self._tables_on(xt.device)), ptr(t_dev), self.num_timesteps,
+                                         stream_ptr()))
+        return mean, sigz, None
+
+    def step_indexed(self, xt, noise_pred, t_dev, z, out=None):
+        """x_{t-1} = mean + sigma_t * z in one launch with the timestep read from device memory (see above)."""
+        _lib.require_cuda(xt, noise_pred, z, t_dev)
+        xt, noise_pred, z = self._f32(xt, noise_pred, z)
+        if out is None:
+            out = torch.empty_like(xt)
+        check(lib().wc_ddpm_step_indexed(ptr(xt), ptr(noise_pred), ptr(z), ptr(out), None, None, xt[0].numel(), xt.shape[0],
+                                         ptr(self._tables_on(xt.device)), ptr(t_dev), self.num_timesteps, stream_ptr()))
+        return out
+
     def sample_prev_timestep(self, xt, noise_pred, t, z=None):
         """Reference :79-116: returns (mean, sigma*z, None); (mean, None, None) at t == 0."""
-        _lib.require_cuda(xt, noise_pred)
-        t = int(t)
-        xt, noise_pred = xt.contiguous(), noise_pred.contiguous()
+        _lib.require_cuda(xt, noise_pred, z)
+        t = self._check_t_scalar(t)
+        xt, noise_pred = self._f32(xt, noise_pred)
         mean = torch.empty_like(xt)
         c = self._coef
         if t == 0:
@@ -83,7 +148,7 @@ class LinearNoiseScheduler:
             return mean, None, None
         if z is None:
             z = self._draw(xt)
-        z = z.contiguous()
+        z = self._f32(xt, z)[1]
         sigz = torch.empty_like(xt)
         check(lib().wc_ddpm_step(ptr(xt), ptr(noise_pred), ptr(z), None, ptr(mean), ptr(sigz), xt[0].numel(),
                                  xt.shape[0], c["beta"][t], c["s"][t], c["sqrt_alpha"][t], c["sigma"][t],
@@ -92,12 +157,10 @@ class LinearNoiseScheduler:
 
     def sample_prev_timestep2(self, xt, noise_pred, t, z=None):
         """Reference :63-77: batched t [B], sigma^2 = beta_t; (mean, None, None) only if ALL t == 0."""
-        _lib.require_cuda(xt, noise_pred)
-        xt, noise_pred = xt.contiguous(), noise_pred.contiguous()
-        t = torch.as_tensor(t, device=xt.device).long().reshape(-1)
+        _lib.require_cuda(xt, noise_pred, z)
+        xt, noise_pred = self._f32(xt, noise_pred)
         B = xt.shape[0]
-        if t.numel() == 1 and B > 1:
-            t = t.expand(B).contiguous()
+        t = self._check_t_batched(t, B, xt.device)
         mean = torch.empty_like(xt)
         all_zero = bool(torch.all(t == 0))  # same host sync as the reference (:71)
         dev = xt.device
@@ -105,12 +168,12 @@ class LinearNoiseScheduler:
         tabs = tuple(ptr(k) for k in keep)
         if all_zero:
             check(lib().wc_ddpm_step_batched(ptr(xt), ptr(noise_pred), None, None, ptr(mean), None, xt[0].numel(), B,
-                                             *tabs, ptr(t), stream_ptr()))
+                                             *tabs, ptr(t), self.num_timesteps, stream_ptr()))
             return mean, None, None
         if z is None:
             z = self._draw(xt)
-        z = z.contiguous()
+        z = self._f32(xt, z)[1]
         sigz = torch.empty_like(xt)
         check(lib().wc_ddpm_step_batched(ptr(xt), ptr(noise_pred), ptr(z), None, ptr(mean), ptr(sigz), xt[0].numel(),
-                                         B, *tabs, ptr(t), stream_ptr()))
+                                         B, *tabs, ptr(t), self.num_timesteps, stream_ptr()))
         return mean, sigz, None

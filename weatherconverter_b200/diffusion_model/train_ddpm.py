@@ -82,13 +82,14 @@ class DenoisingTrainer:
     parameter buffer) and the C training plan bound to one (batch, H, W)."""
 
     def __init__(self, model: Unet, scheduler, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, process_group=None,
-                 bucket_bytes=64 << 20):
+                 bucket_bytes=64 << 20, seed=None):
         if not torch.cuda.is_available():
             raise RuntimeError("wc_b200 training needs a CUDA device (sm_100a); there is no CPU fallback")
         self.model, self.scheduler = model, scheduler
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         self.bucket_bytes = int(bucket_bytes)
         self.step_count = 0
         named = list(model.named_parameters())
@@ -124,6 +125,19 @@ class DenoisingTrainer:
         self._buckets = []
         self._keep = None
         self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
+        # Replicas must start identical (what torch DDP guarantees by broadcasting rank 0's parameters at construction):
+        # do not rely on every rank having seeded its model build the same way.
+        if self.world > 1:
+            dist.broadcast(self.flat_params, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                           group=process_group)
+        # step() draws noise / timesteps from PER-RANK generators (seed + rank): with one global seed on every rank (the
+        # usual way to build identical replicas) the default generators would hand every rank the same t and noise for
+        # its different images.  seed=None keeps the reference's behaviour on one process (global generators, :99-102).
+        self._gen_cpu = self._gen_dev = None
+        if seed is not None or self.world > 1:
+            base = 0 if seed is None else int(seed)
+            self._gen_cpu = torch.Generator().manual_seed(base + self.rank)
+            self._gen_dev = torch.Generator(device=dev).manual_seed(base + self.rank)
 
     # ---- torch.optim.Adam-compatible views of the optimizer state (for checkpoints, train_ddpm.py:55-61) ----
     def export_optimizer_state(self, optimizer):
@@ -134,6 +148,26 @@ class DenoisingTrainer:
             optimizer.state[p] = {"step": torch.tensor(float(self.step_count)),
                                   "exp_avg": self.exp_avg[off:off + n].view(p.shape),
                                   "exp_avg_sq": self.exp_avg_sq[off:off + n].view(p.shape)}
+
+    def import_optimizer_state(self, optimizer):
+        """Resume (train_ddpm.py:63-68,81-84: load_checkpoint fills the optimizer before train()): copy ``exp_avg``,
+        ``exp_avg_sq`` and ``step`` of a torch.optim.Adam whose state is keyed by this model's parameters into the flat
+        moment buffers.  Returns the number of parameters restored (0 when the optimizer has no state yet)."""
+        params = dict(self.model.named_parameters())
+        restored, steps = 0, set()
+        for name, (off, n) in self.slices.items():
+            st = optimizer.state.get(params[name])
+            if not st or "exp_avg" not in st:
+                continue
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1).to(self.exp_avg.device, torch.float32))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1).to(self.exp_avg.device, torch.float32))
+            steps.add(int(float(st["step"])))
+            restored += 1
+        if restored:
+            if restored != len(self.slices) or len(steps) != 1:
+                raise RuntimeError("optimizer state covers only part of the model or has mixed step counts; cannot resume")
+            self.step_count = steps.pop()
+        return restored
 
     def __del__(self):
         try:
@@ -202,9 +236,9 @@ class DenoisingTrainer:
         """One reference training step (train_ddpm.py:95-114); returns the loss as a device scalar tensor."""
         images = images.float().to(self.flat_params.device)
         if noise is None:
-            noise = torch.randn_like(images)                                        # :99
-        if t is None:
-            t = torch.randint(0, self.scheduler.num_timesteps, (images.shape[0],))  # :102 (CPU generator, then H2D)
+            noise = torch.randn(images.shape, device=images.device, generator=self._gen_dev)               # :99
+        if t is None:                                                               # :102 (CPU generator, then H2D)
+            t = torch.randint(0, self.scheduler.num_timesteps, (images.shape[0],), generator=self._gen_cpu)
         t = torch.as_tensor(t).to(images.device)
         noisy = self.scheduler.add_noise(images, noise, t)                          # :105
         loss = self.forward_backward(noisy, t, noise)                               # :106-109
@@ -212,16 +246,23 @@ class DenoisingTrainer:
         return loss
 
 
-def train(dataloader, model: Unet, optimizer, criterion, scheduler, epochs=1, log_interval=10, on_log=None):
+def train(dataloader, model: Unet, optimizer, criterion, scheduler, epochs=1, log_interval=10, on_log=None, on_epoch_end=None,
+          seed=None, process_group=None):
     """Drop-in for the reference's ``train`` (train_ddpm.py:71-133): same arguments; the Adam hyper-parameters are read
     from ``optimizer`` (built as ``Adam(model.parameters(), lr)`` at :151) and ``criterion`` must be ``nn.MSELoss()``.
-    wandb / tqdm / checkpoint I/O of the reference are host-side plumbing and are left to ``on_log(epoch, batch, loss)``."""
+    Resume: an ``optimizer`` that already carries state (the reference's load_checkpoint, :63-68,81-84) has its moments and
+    step count imported, so Adam continues instead of restarting.  ``optimizer.state`` is re-pointed at the live moment buffers
+    before every ``on_log`` and ``on_epoch_end(epoch)`` call (the reference's per-epoch save_checkpoint, :135-141), so
+    ``optimizer.state_dict()`` taken inside those hooks is a valid checkpoint.  wandb / tqdm / file I/O of the reference are
+    host-side plumbing left to the two hooks."""
     if not isinstance(criterion, torch.nn.MSELoss):
         raise RuntimeError("the fused training step implements nn.MSELoss (train_ddpm.py:152)")
     g = optimizer.param_groups[0]
     if g.get("weight_decay", 0) or g.get("amsgrad", False):
         raise RuntimeError("the fused Adam implements torch.optim.Adam without weight decay / amsgrad (train_ddpm.py:151)")
-    trainer = DenoisingTrainer(model, scheduler, lr=g["lr"], betas=g["betas"], eps=g["eps"])
+    trainer = DenoisingTrainer(model, scheduler, lr=g["lr"], betas=g["betas"], eps=g["eps"], seed=seed,
+                               process_group=process_group)
+    trainer.import_optimizer_state(optimizer)
     losses = []
     for epoch_idx in range(1, epochs + 1):
         interval = 0.0
@@ -231,7 +272,11 @@ def train(dataloader, model: Unet, optimizer, criterion, scheduler, epochs=1, lo
             losses.append(float(loss))
             if (batch_idx + 1) % log_interval == 0:
                 if on_log is not None:
+                    trainer.export_optimizer_state(optimizer)
                     on_log(epoch_idx, batch_idx + 1, interval / log_interval)
                 interval = 0.0
+        trainer.export_optimizer_state(optimizer)
+        if on_epoch_end is not None:
+            on_epoch_end(epoch_idx)
     trainer.export_optimizer_state(optimizer)
     return losses

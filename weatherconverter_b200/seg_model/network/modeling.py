@@ -158,6 +158,16 @@ class DeepLabV3(nn.Module):
         self._last = (x, labels)
         return dict(pred=pred, grad=grad, loss=loss, logits=logits)
 
+    def shared_replica(self):
+        """A second module object over the SAME parameter tensors with its own C plan / workspace binding.  A plan is bound to
+        one (batch, H, W) at a time and re-binding frees the packed weights a captured CUDA graph still points to, so a loop
+        that alternates two batch shapes under graphs (GSG on B images, LCG on 19 B masked images) gives each shape its own
+        replica."""
+        import copy
+        r = copy.copy(self)          # shares _parameters / _buffers (no new tensors)
+        r._handle, r._key, r._ws, r._keep = None, None, {}, None
+        return r
+
     def forward(self, x):
         B, _, H, W = x.shape
         dummy = torch.zeros(B, H, W, dtype=torch.long, device=x.device)

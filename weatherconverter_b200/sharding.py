@@ -27,11 +27,23 @@ def initial_noise(shape_chw, start: int, stop: int, seed: int = 1234) -> torch.T
     return torch.stack([torch.randn(shape_chw, generator=image_generator(i, seed)) for i in range(start, stop)])
 
 
-def gather_images(local: torch.Tensor, world_size: int):
-    """Host-side gather of finished images to rank 0 (the only collective; after the timed region)."""
+def gather_images(local: torch.Tensor, world_size: int, global_batch: int = None):
+    """Host-side gather of finished images to rank 0 (the only collective; after the timed region).  Shards may be uneven
+    (shard_range: sizes differ by at most one): every rank pads its shard to the largest shard size, rank 0 slices the
+    padding off again.  ``global_batch`` defaults to world_size * len(local) (even shards)."""
     import torch.distributed as dist
     if world_size == 1:
         return [local]
-    out = [torch.empty_like(local) for _ in range(world_size)] if dist.get_rank() == 0 else None
-    dist.gather(local, out, dst=0)
-    return out
+    rank = dist.get_rank()
+    if global_batch is None:
+        global_batch = world_size * local.shape[0]
+    sizes = [b - a for a, b in (shard_range(global_batch, world_size, r) for r in range(world_size))]
+    if local.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} images, shard_range says {sizes[rank]}")
+    biggest = max(sizes)
+    padded = local
+    if local.shape[0] < biggest:
+        padded = torch.cat([local, local.new_zeros((biggest - local.shape[0],) + tuple(local.shape[1:]))])
+    out = [torch.empty_like(padded) for _ in range(world_size)] if rank == 0 else None
+    dist.gather(padded.contiguous(), out, dst=0)
+    return [o[:n] for o, n in zip(out, sizes)] if rank == 0 else None

@@ -4,13 +4,15 @@
 signature and constants (LAMBDA = 60, N = 500).  The driver as shipped cannot finish (D1 the guided x_t
 is overwritten, D2 ``mu + None`` at i = 0, D3 LCG shape error on the 2nd iteration, D7 float64 promotion, D8 autograd
 graph kept across steps), so the default here is the REPAIRED loop of SURVEY.md 8c: no autograd graph, global
-guidance (GSG) on every step i > 0, ``x_t = mu`` at i = 0, guided x_t kept (fp32).  ``reference_quirks=True``
-reproduces D1 verbatim (guidance computed, then discarded) for step-level comparison with the shipped code.
+guidance (GSG) on every step i > 0, ``x_t = mu`` at i = 0, guided x_t kept (fp32).  ``mode="alternate"`` restores the
+shipped schedule of translation.py:84-87 - local class guidance (LCG, repaired final sum) on even steps, GSG on odd steps.
+``reference_quirks=True`` reproduces D1 verbatim (guidance computed, then discarded) for step-level comparison with the
+shipped code.
 Batches are independent chains: image b is guided by its own loss/gradient (vmap of the reference's B = 1 call).
 """
 import torch
 
-from .sgg.sgg import apply_gsg_batch
+from .sgg.sgg import apply_gsg_batch, apply_lcg
 from .srgan_model.inference import inference as srgan_inference
 
 device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
@@ -29,24 +31,78 @@ def load_input_image(path: str, image_size: int = 128) -> torch.Tensor:
     return image_io.diffusion_input(img, image_size)
 
 
+def _sample_with_sgg_graphed(xt, diff_model, diff_scheduler, seg_model, gt, srgan_model, n_steps, lam, step_noise, device_noise,
+                             generator, mode, record):
+    """The loop of sample_with_sgg with every guided step (i > 0) replayed from a captured CUDA graph.  One graph per
+    guidance kind in use (GSG and / or LCG); the timestep and the noise are fed through static device buffers."""
+    from .graphs import StepGraph
+    dev = xt.device
+    # GSG runs the segmentor on B images, LCG on 19 B masked images: two plan bindings that must both stay alive
+    seg_for = {"gsg": seg_model, "lcg": seg_model.shared_replica() if mode == "alternate" else seg_model}
+
+    def make(kind):
+        def step(x, t_dev, z):
+            eps = diff_model(x, t_dev)                                                      # reference :74
+            mu, sigma, _ = diff_scheduler.sample_prev_timestep_indexed(x, eps, t_dev, z)    # reference :78
+            sr_xt = srgan_inference(srgan_model, x)                                         # reference :81
+            if kind == "lcg":
+                return apply_lcg(seg_for["lcg"], mu, sigma, sr_xt, gt, lam)                 # reference :84-85
+            return apply_gsg_batch(seg_for["gsg"], mu, sigma, sr_xt, gt, lam)               # reference :86-87
+        return StepGraph(step, xt.shape, dev)
+
+    kinds = {"gsg": ("gsg",), "lcg": ("lcg",), "alternate": ("gsg", "lcg")}[mode]
+    graphs = {k: make(k) for k in kinds} if n_steps > 1 else {}
+    t_all = torch.arange(n_steps, device=dev, dtype=torch.int64)
+    cur = xt
+    for i in reversed(range(n_steps)):
+        if i == 0:
+            eps = diff_model(cur, t_all[0:1])
+            cur = diff_scheduler.step(cur, eps, 0)                                          # repair of D2: x_0 = mu
+        else:
+            if step_noise is not None:
+                z = (step_noise(i) if callable(step_noise) else step_noise[i]).to(dev)
+            elif device_noise:
+                z = torch.randn(cur.shape, device=dev, generator=generator)
+            else:
+                z = diff_scheduler._draw(cur)                                               # reference scheduler.py:110
+            g = graphs["lcg" if (mode == "lcg" or (mode == "alternate" and i % 2 == 0)) else "gsg"]
+            if cur is not g.xt:
+                g.load(cur)
+            cur = g.replay(t_all[i:i + 1], z)
+        if record is not None:
+            record.append(cur.clone())
+    return srgan_inference(srgan_model, cur)                                                # reference :95-97
+
+
 @torch.no_grad()
 def sample_with_sgg(input_tensor, diff_model, diff_scheduler, seg_model, gt, srgan_model, *, n_steps=N_STEPS,
                     lam=LAMBDA, noise=None, t_forward=None, step_noise=None, device_noise=False, generator=None,
-                    guidance=True, reference_quirks=False, record=None):
+                    guidance=True, mode="gsg", reference_quirks=False, record=None, record_base=None, use_graph=False):
     """input_tensor [B,3,h,w] in [-1,1]; gt [B,4h,4w] int64 trainIds (255 = ignore).  Returns sr_x0 [B,3,4h,4w].
     Injection points for parity runs: ``t_forward`` [B] (reference :63 draws randint(0, N)), ``noise`` like the input
-    (:64), ``step_noise`` [N, B,3,h,w] or callable i -> z (scheduler.py:110)."""
+    (:64), ``step_noise`` [N, B,3,h,w] or callable i -> z (scheduler.py:110); ``record`` / ``record_base`` collect x_t and
+    the unguided mu + sigma of every step.  ``mode``: "gsg" (global guidance on every
+    step, the repaired default), "alternate" (reference :84-87: LCG when i is even, GSG when i is odd) or "lcg".
+    ``use_graph=True`` captures the guided reverse step once per guidance kind as a CUDA graph (weatherconverter_b200/graphs.py)
+    and replays it: one cudaGraphLaunch per step instead of ~440 kernel launches, bit-identical to the eager loop."""
+    if mode not in ("gsg", "alternate", "lcg"):
+        raise ValueError("mode must be 'gsg', 'alternate' or 'lcg'")
     x0 = input_tensor.to(device).float().contiguous()
     gt = gt.to(device)
     B = x0.shape[0]
     t = t_forward if t_forward is not None else torch.randint(0, n_steps, (B,))            # reference :63
     noise = noise if noise is not None else torch.randn_like(x0)                            # reference :64
     xt = diff_scheduler.add_noise2(x0, noise.to(device), t.to(device))                      # reference :65
+    if use_graph and guidance and not reference_quirks and record_base is None:
+        return _sample_with_sgg_graphed(xt, diff_model, diff_scheduler, seg_model, gt, srgan_model, n_steps, lam, step_noise,
+                                        device_noise, generator, mode, record)
     eps = torch.empty_like(xt)
     for i in reversed(range(n_steps)):                                                      # reference :70
         diff_model(xt, torch.as_tensor(i).unsqueeze(0).to(device), out=eps)                # reference :74
         if i == 0:
             xt = diff_scheduler.step(xt, eps, 0)                                            # repair of D2: x_0 = mu
+            if record_base is not None:
+                record_base.append(xt.clone())
         else:
             if step_noise is not None:
                 z = (step_noise(i) if callable(step_noise) else step_noise[i]).to(device)
@@ -55,9 +111,14 @@ def sample_with_sgg(input_tensor, diff_model, diff_scheduler, seg_model, gt, srg
             else:
                 z = None
             mu, sigma, _ = diff_scheduler.sample_prev_timestep(xt, eps, i, z=z)             # reference :78
+            if record_base is not None:
+                record_base.append(mu + sigma)       # the unguided update: x_t - this = the guidance term alone
             if guidance:
                 sr_xt = srgan_inference(srgan_model, xt)                                    # reference :81
-                guided = apply_gsg_batch(seg_model, mu, sigma, sr_xt, gt, lam)              # reference :87
+                if mode == "lcg" or (mode == "alternate" and i % 2 == 0):
+                    guided = apply_lcg(seg_model, mu, sigma, sr_xt, gt, lam)                # reference :84-85
+                else:
+                    guided = apply_gsg_batch(seg_model, mu, sigma, sr_xt, gt, lam)          # reference :86-87
                 xt = (mu + sigma) if reference_quirks else guided                           # reference :90 (D1)
             else:
                 xt = mu + sigma
