@@ -65,7 +65,8 @@ def test_c2_unet_forward_128x256():
     yb = m(xb.to(dev), t.to(dev))[5].cpu()
     rel_b = float((yb - y[0]).norm() / y[0].norm())
     print(f"C2 batch invariance (image 5 of 16 vs B = 1): rms-rel {rel_b:.3e}")
-    assert rel_b < 2e-3
+    # every reduction of the forward (GroupNorm partial sums, K loops, softmax rows) runs in a batch-independent order
+    assert torch.equal(yb, y[0])
 
 
 def _c3_models(dev):
@@ -115,11 +116,11 @@ def test_c3_geometry_a_two_guided_steps_and_batch_invariance():
         for b in range(B):
             y, ref = rec[k][b].cpu(), rec_ref[k][b]
             print(f"  step {k} image {b}: psnr {_psnr(y, ref):.1f} dB max-abs {float((y - ref).abs().max()):.3e}")
-            assert _psnr(y, ref) > 60, (k, b)
+            assert _psnr(y, ref) > 74, (k, b)
     for b in range(B):
         p = _psnr(sr[b], sr_ref[b], 1.0)
         print(f"  sr_x0 image {b}: psnr {p:.1f} dB")
-        assert sr.shape == (B, 3, 4 * h, 4 * w) and p > 35
+        assert sr.shape == (B, 3, 4 * h, 4 * w) and p > 36
     # the two images really are independent chains with their own labels: swapping the label maps changes the guided x_t
     rec_sw = []
     sample_with_sgg(x0, unet, sched, seg, gt.flip(0), G, n_steps=N, noise=noise, t_forward=t_fwd, step_noise=torch.stack(zs),
@@ -146,8 +147,9 @@ def test_c3_geometry_a_two_guided_steps_and_batch_invariance():
         rel_g = float((d_full - d_one).norm() / d_one.norm())
         agree = float((full_pred[b] == one_pred[0]).float().mean())
         print(f"  batch-32 image {b} vs B = 1: x_t rms-rel {rel:.3e}, guidance term rms-rel {rel_g:.3e}, argmax agreement {agree:.5f}")
-        assert rel < 2e-3 and agree > 0.995
-        assert rel_g < 0.2
+        # independent chains and batch-independent reduction orders: bit-identical (this test found the cross-proxy race of
+        # the TMA residual epilogue in round 2: some images of a batch of 32 came out 2.5x further from the reference)
+        assert torch.equal(full[b], one[0]) and torch.equal(full_pred[b], one_pred[0])
 
 
 def test_c5_training_step_128x256():

@@ -132,6 +132,31 @@ def test_conv2d_fused_epilogue():
     assert _rel(ops.to_nchw_f32(y), ref) < 5e-3
 
 
+@pytest.mark.parametrize("Cin,Cout,H,W", [(768, 768, 16, 32), (256, 256, 64, 128), (512, 512, 32, 64), (128, 128, 64, 128)])
+def test_conv1x1_residual_many_tiles_per_cta(Cin, Cout, H, W):
+    """1x1 convolution + residual with several tiles per persistent CTA (the epilogue is the bottleneck there): regression
+    test of the cross-proxy WAR race on the TMA residual staging buffer (generic-proxy reads vs the next TMA box), which
+    corrupted a few per cent of the rows of SOME images at batch >= 3 in round 1.  Every image is checked on its own,
+    three times (the race was timing dependent)."""
+    from weatherconverter_b200 import ops
+    dev = _dev()
+    for B in (3, 5, 16, 32):
+        g = torch.Generator(device="cpu").manual_seed(Cin + B)
+        x = torch.randn(B, Cin, H, W, generator=g).to(dev)
+        w = (torch.randn(Cout, Cin, 1, 1, generator=g) / math.sqrt(Cin)).to(dev)
+        b = (0.1 * torch.randn(Cout, generator=g)).to(dev)
+        res = torch.randn(B, Cout, H, W, generator=g).to(dev)
+        ref = F.conv2d(_bf(x), _bf(w), b) + _bf(res)
+        xh, rh = ops.to_nhwc_bf16(x), ops.to_nhwc_bf16(res)
+        first = None
+        for rep in range(3):
+            y = ops.to_nchw_f32(ops.conv2d(xh, w, b, residual=rh))
+            worst = max(_rel(y[i], ref[i]) for i in range(B))
+            assert worst < 5e-3, (B, rep, worst)
+            first = y if first is None else first
+            assert torch.equal(y, first), (B, rep)
+
+
 def test_conv_in_out():
     from weatherconverter_b200 import ops
     dev = _dev()

@@ -61,7 +61,7 @@ def _check_driver(d, rec, base, out, seg, dev, tag):
         ref = d["traj"][k]
         psnr = _psnr(rec[k].cpu(), ref)
         line = f"{tag} step {k} (i = {N - 1 - k}): psnr {psnr:.1f} dB max-abs {float((rec[k].cpu() - ref).abs().max()):.3e}"
-        assert psnr > 70, (k, psnr)
+        assert psnr > 72, (k, psnr)
         if k < N - 1:   # i > 0: a guided step
             delta_ref = (d["traj"][k].double() - d["base"][k].double())
             delta = (rec[k].double() - base[k].double()).cpu()
@@ -79,7 +79,7 @@ def _check_driver(d, rec, base, out, seg, dev, tag):
     agree = float((pred[0].to(torch.uint8) == d["final_pred"][0]).float().mean())
     print(f"{tag} sr_x0: psnr {psnr:.1f} dB; segmentation argmax of the final image agrees on {100 * agree:.2f} % of the pixels")
     assert psnr > 36.5
-    assert agree > 0.97
+    assert agree > 0.98
 
 
 def test_repaired_driver_vs_golden(golden):

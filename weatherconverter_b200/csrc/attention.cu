@@ -394,6 +394,7 @@ int launch_attention_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   }
   dim3 grid((ntok + 128 * NQ - 1) / (128 * NQ), BH);
   ProfScope prof(kProfAttention, st, 4.0 * BH * static_cast<double>(ntok) * ntok * HD);
+  prof.note(BH, ntok, HD);
   attention_kernel<HD, BKV, NQ, POLY, TP><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
   WC_LAUNCH_CHECK();
   return 0;

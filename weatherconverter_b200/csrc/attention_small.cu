@@ -684,6 +684,7 @@ int launch_small_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
   const int nqb = (ntok + 128 * kNQ - 1) / (128 * kNQ);
   dim3 grid(HD == 16 ? BH : nqb, HD == 16 ? nqb : BH);
   ProfScope prof(kProfAttention, st, 4.0 * BH * static_cast<double>(ntok) * ntok * HD);
+  prof.note(BH, ntok, HD);
   attention_small_kernel<HD, POLY, TP><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
   WC_LAUNCH_CHECK();
   return 0;

@@ -88,6 +88,12 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
       for (int j = 0; j < NV; ++j)
         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(res_cur[j].x), "=r"(res_cur[j].y), "=r"(res_cur[j].z), "=r"(res_cur[j].w)
                      : "r"(mine + ((static_cast<uint32_t>(j) ^ sw) << 4)) : "memory");
+      // Cross-proxy WAR: the lanes read the staging buffer through the generic proxy and the NEXT residual box is written
+      // into the same bytes by the TMA (async proxy).  Without this fence the two are unordered, and on B200 the next box
+      // did overtake the reads whenever the epilogue was the bottleneck (1x1 convolutions with several tiles per CTA: a
+      // few per cent of the rows picked up the following chunk's residual - found by the batch-invariance tests of
+      // round 2, tools/conv_res_sweep.py; a warp barrier alone does not order the proxies).
+      fence_proxy_async_smem();
       __syncwarp();   // every lane has read its row before the next box may land
     }
     if (c0 + 2 * NC < p.BN) prefetch(nb + 2 * NC);

@@ -371,10 +371,12 @@ size_t groupnorm_workspace_bytes(int B) { return static_cast<size_t>(B) * 64 * k
 
 // Number of per-sample slabs the statistics pass of groupnorm_silu uses for a [B,HW,C] input (the backward pass
 // re-combines the same partial sums).
+// A function of HW only: the partial sums of a sample are then combined in the same order whatever the batch size, so image b
+// of a batch gets bit-identical statistics to the same image processed alone (batch invariance of the whole UNet forward,
+// tests/test_gpu_config_shapes.py).  Large batches simply get more, smaller blocks (B * nsplit).
 int groupnorm_stats_splits(int B, int HW) {
-  int nsplit = (4 * num_sms() + B - 1) / B;
-  const int max_split = (HW + 31) / 32;
-  if (nsplit > max_split) nsplit = max_split;
+  (void)B;
+  int nsplit = (HW + 31) / 32;
   if (nsplit > 64) nsplit = 64;
   if (nsplit < 1) nsplit = 1;
   return nsplit;
