@@ -104,6 +104,8 @@ attention_kernel(const __grid_constant__ AttnMaps maps, const __grid_constant__ 
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();   // programmatic dependent launch: the set-up above overlaps the previous kernel's tail
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -395,7 +397,7 @@ int launch_attention_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   dim3 grid((ntok + 128 * NQ - 1) / (128 * NQ), BH);
   ProfScope prof(kProfAttention, st, 4.0 * BH * static_cast<double>(ntok) * ntok * HD);
   prof.note(BH, ntok, HD);
-  attention_kernel<HD, BKV, NQ, POLY, TP><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
+  launch_k<1>(attention_kernel<HD, BKV, NQ, POLY, TP>, grid, Cfg::kThreads, Cfg::kSmem, st, maps, args);
   WC_LAUNCH_CHECK();
   return 0;
 }

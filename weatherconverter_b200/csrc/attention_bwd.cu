@@ -114,6 +114,8 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const __grid_cons
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();   // programmatic dependent launch: the set-up above overlaps the previous kernel's tail
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -407,7 +409,7 @@ int launch_bwd(const BwdTensors& t, const float* lse, const float* D, __nv_bfloa
   dim3 grid((ntok + 127) / 128, B * heads);
   const double flops = (KV ? 8.0 : 6.0) * B * heads * static_cast<double>(ntok) * ntok * HD;
   ProfScope prof(kProfAttention, st, flops);
-  attention_bwd_kernel<HD, BT, STAGES, KV, NSW, TA><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, a);
+  launch_k<1>(attention_bwd_kernel<HD, BT, STAGES, KV, NSW, TA>, grid, Cfg::kThreads, Cfg::kSmem, st, maps, a);
   WC_LAUNCH_CHECK();
   return 0;
 }

@@ -181,6 +181,8 @@ attention_small_kernel(const __grid_constant__ SmallMaps maps, const __grid_cons
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();   // programmatic dependent launch: the set-up above overlaps the previous kernel's tail
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -685,7 +687,7 @@ int launch_small_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
   dim3 grid(HD == 16 ? BH : nqb, HD == 16 ? nqb : BH);
   ProfScope prof(kProfAttention, st, 4.0 * BH * static_cast<double>(ntok) * ntok * HD);
   prof.note(BH, ntok, HD);
-  attention_small_kernel<HD, POLY, TP><<<grid, Cfg::kThreads, Cfg::kSmem, st>>>(maps, args);
+  launch_k<1>(attention_small_kernel<HD, POLY, TP>, grid, Cfg::kThreads, Cfg::kSmem, st, maps, args);
   WC_LAUNCH_CHECK();
   return 0;
 }

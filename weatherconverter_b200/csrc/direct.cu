@@ -21,6 +21,7 @@ __global__ void conv_small_cin_kernel(const float* __restrict__ x, const float* 
                                       const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int B, int H,
                                       int W, int Ho, int Wo, int Cout, int K, int stride, int pad, int ldy, int relu,
                                       const float* __restrict__ prelu) {
+  pdl_prologue();
   extern __shared__ float sw[];  // [CIN*K*K][Cout]
   const int taps = CIN * K * K;
   for (int i = threadIdx.x; i < taps * Cout; i += blockDim.x) {
@@ -80,6 +81,7 @@ conv_stem64_kernel(const float* __restrict__ x, const float* __restrict__ w /*[6
                    const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                    __nv_bfloat16* __restrict__ y, int B, int H, int W, int Ho, int Wo, int K, int stride, int pad, int ldy,
                    int relu, const float* __restrict__ prelu) {
+  pdl_prologue();
   extern __shared__ float sw[];  // [CIN*K*K][64]
   const int taps = CIN * K * K;
   for (int i = threadIdx.x; i < taps * 64; i += blockDim.x) {
@@ -141,6 +143,7 @@ template <int COUT>
 __global__ void conv_small_cout_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[COUT][Cin][K][K]*/,
                                        const float* __restrict__ bias, float* __restrict__ y, int B, int H, int W,
                                        int Cin, int K, int ldx, int tanh_out) {
+  pdl_prologue();
   extern __shared__ float sw[];  // [K*K][Cin][COUT]
   const int kk = K * K;
   for (int i = threadIdx.x; i < kk * Cin * COUT; i += blockDim.x) {
@@ -196,6 +199,7 @@ __global__ void conv_small_cout_kernel(const __nv_bfloat16* __restrict__ x, cons
 // (unet_base.py:22-24), so that t/factor is bit-identical to the reference's argument; NULL -> powf on the device.
 __global__ void time_embedding_kernel(const long long* __restrict__ t, int dim, const float* __restrict__ factor,
                                       float* __restrict__ out) {
+  pdl_prologue();
   const int b = blockIdx.x, half = dim / 2;
   const float tv = static_cast<float>(t[b]);
   for (int j = threadIdx.x; j < half; j += blockDim.x) {
@@ -209,6 +213,7 @@ __global__ void temb_mlp_kernel(const long long* __restrict__ t, int dim, const 
                                 const float* __restrict__ w1,
                                 const float* __restrict__ b1, const float* __restrict__ w2,
                                 const float* __restrict__ b2, float* __restrict__ temb, float* __restrict__ temb_silu) {
+  pdl_prologue();
   extern __shared__ float sh[];  // emb[dim], h1[dim]
   float* emb = sh;
   float* h1 = sh + dim;
@@ -237,6 +242,7 @@ __global__ void temb_mlp_kernel(const long long* __restrict__ t, int dim, const 
 // out[b][n] = bias[n] + sum_k W[n][k] * in[b][k]; one warp per output, all t_emb_layers of the net in one launch.
 __global__ void linear_rows_kernel(const float* __restrict__ in, int dim, const float* __restrict__ w,
                                    const float* __restrict__ bias, float* __restrict__ out, int N) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   if (warp >= N) return;
@@ -254,6 +260,7 @@ __global__ void linear_rows_kernel(const float* __restrict__ in, int dim, const 
 __global__ void pack_tap_kernel(__nv_bfloat16* __restrict__ dst, int ldk, int koff, const float* __restrict__ src,
                                 int Nn, int Cc, int Cpad, int KH, int KW, int ky, int kx, int transpose,
                                 const float* __restrict__ scale, int row_mul, int row_off, int D0, int D1src) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(Nn) * Cpad;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -282,6 +289,7 @@ struct PackTapsArgs {
   PackTapDesc t[kPackMaxTaps];
 };
 __global__ void pack_taps_kernel(const __grid_constant__ PackTapsArgs a) {
+  pdl_prologue();
   const PackTapDesc t = a.t[blockIdx.y];
   const size_t total = static_cast<size_t>(t.Nn) * t.Cpad;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -299,6 +307,7 @@ __global__ void pack_taps_kernel(const __grid_constant__ PackTapsArgs a) {
 
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
                                              int HW, int ldy) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(B) * HW * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -309,6 +318,7 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
 }
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int C,
                                              int HW, int ldx) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(B) * HW * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -346,12 +356,12 @@ int conv_small_cin(const float* x, const float* w, const float* bias, const floa
       WC_CHECK_CUDA(cudaFuncSetAttribute(conv_stem64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
       attr_set = smem;
     }
-    conv_stem64_kernel<3><<<grid_for(npix, 128), 128, smem, st>>>(x, w, bias, scale, shift, y, B, H, W, Ho, Wo, K, stride, pad,
+    launch_k(conv_stem64_kernel<3>, grid_for(npix, 128), 128, smem, st, x, w, bias, scale, shift, y, B, H, W, Ho, Wo, K, stride, pad,
                                                                  ldy, relu, prelu);
     WC_LAUNCH_CHECK();
     return 0;
   }
-  conv_small_cin_kernel<3><<<grid_for(npix, threads / octs), threads, smem, st>>>(
+  launch_k(conv_small_cin_kernel<3>, grid_for(npix, threads / octs), threads, smem, st, 
       x, w, bias, scale, shift, y, B, H, W, Ho, Wo, Cout, K, stride, pad, ldy, relu, prelu);
   WC_LAUNCH_CHECK();
   return 0;
@@ -367,14 +377,14 @@ int conv_small_cout(const __nv_bfloat16* x, const float* w, const float* bias, f
                                        static_cast<int>(smem)));
   const size_t npix = static_cast<size_t>(B) * H * W;
   ProfScope prof(kProfBoundaryConv, st, static_cast<double>(npix) * (2.0 * Cin + 4.0 * Cout));
-  conv_small_cout_kernel<3><<<grid_for(npix, 128), 128, smem, st>>>(x, w, bias, y, B, H, W, Cin, K, ldx, tanh_out);
+  launch_k(conv_small_cout_kernel<3>, grid_for(npix, 128), 128, smem, st, x, w, bias, y, B, H, W, Cin, K, ldx, tanh_out);
   WC_LAUNCH_CHECK();
   return 0;
 }
 
 int temb_mlp(const long long* t, int Bt, int dim, const float* w1, const float* b1, const float* w2, const float* b2,
              float* temb, float* temb_silu, cudaStream_t st) {
-  temb_mlp_kernel<<<Bt, 128, 2 * dim * sizeof(float), st>>>(t, dim, time_factor_table(dim / 2), w1, b1, w2, b2, temb, temb_silu);
+  launch_k(temb_mlp_kernel, Bt, 128, 2 * dim * sizeof(float), st, t, dim, time_factor_table(dim / 2), w1, b1, w2, b2, temb, temb_silu);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -382,7 +392,7 @@ int temb_mlp(const long long* t, int Bt, int dim, const float* w1, const float* 
 // get_time_embedding (unet_base.py:7-30): out [n, dim] = [sin(t/f), cos(t/f)]
 int time_embedding(const long long* t, int n, int dim, float* out, cudaStream_t st) {
   WC_REQUIRE(n >= 1 && dim >= 2 && dim % 2 == 0, "time_embedding: dim must be even");
-  time_embedding_kernel<<<n, 64, 0, st>>>(t, dim, time_factor_table(dim / 2), out);
+  launch_k(time_embedding_kernel, n, 64, 0, st, t, dim, time_factor_table(dim / 2), out);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -390,7 +400,7 @@ int time_embedding(const long long* t, int n, int dim, float* out, cudaStream_t 
 int linear_rows(const float* in, int Bt, int dim, const float* w, const float* bias, float* out, int N,
                 cudaStream_t st) {
   const int warps_per_block = 8;
-  linear_rows_kernel<<<dim3((N + warps_per_block - 1) / warps_per_block, Bt), warps_per_block * 32, 0, st>>>(
+  launch_k(linear_rows_kernel, dim3((N + warps_per_block - 1) / warps_per_block, Bt), warps_per_block * 32, 0, st, 
       in, dim, w, bias, out, N);
   WC_LAUNCH_CHECK();
   return 0;
@@ -399,7 +409,7 @@ int linear_rows(const float* in, int Bt, int dim, const float* w, const float* b
 int pack_tap(__nv_bfloat16* dst, int ldk, int koff, const float* src, int Nn, int Cc, int Cpad, int KH, int KW, int ky,
              int kx, int transpose, const float* scale, int row_mul, int row_off, cudaStream_t st) {
   // source dim-1 extent: transposed sources are [Cc][Nn], plain sources [rows][Cc]
-  pack_tap_kernel<<<grid_for(static_cast<size_t>(Nn) * Cpad), 256, 0, st>>>(dst, ldk, koff, src, Nn, Cc, Cpad, KH, KW,
+  launch_k(pack_tap_kernel, grid_for(static_cast<size_t>(Nn) * Cpad), 256, 0, st, dst, ldk, koff, src, Nn, Cc, Cpad, KH, KW,
                                                                            ky, kx, transpose, scale, row_mul, row_off, 0,
                                                                            transpose ? Nn : Cc);
   WC_LAUNCH_CHECK();
@@ -423,18 +433,18 @@ int pack_taps(__nv_bfloat16* dst, int ldk, int ntaps, const float* const* src, c
     max_total = std::max(max_total, static_cast<size_t>(t.Nn) * t.Cpad);
   }
   const int gx = static_cast<int>(std::min<size_t>((max_total + 255) / 256, 256));
-  pack_taps_kernel<<<dim3(gx, ntaps), 256, 0, st>>>(a);
+  launch_k(pack_taps_kernel, dim3(gx, ntaps), 256, 0, st, a);
   WC_LAUNCH_CHECK();
   return 0;
 }
 
 int nchw_f32_to_nhwc_bf16(const float* x, __nv_bfloat16* y, int B, int C, int HW, int ldy, cudaStream_t st) {
-  nchw_f32_to_nhwc_bf16_kernel<<<grid_for(static_cast<size_t>(B) * C * HW), 256, 0, st>>>(x, y, B, C, HW, ldy);
+  launch_k(nchw_f32_to_nhwc_bf16_kernel, grid_for(static_cast<size_t>(B) * C * HW), 256, 0, st, x, y, B, C, HW, ldy);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int nhwc_bf16_to_nchw_f32(const __nv_bfloat16* x, float* y, int B, int C, int HW, int ldx, cudaStream_t st) {
-  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(static_cast<size_t>(B) * C * HW), 256, 0, st>>>(x, y, B, C, HW, ldx);
+  launch_k(nhwc_bf16_to_nchw_f32_kernel, grid_for(static_cast<size_t>(B) * C * HW), 256, 0, st, x, y, B, C, HW, ldx);
   WC_LAUNCH_CHECK();
   return 0;
 }

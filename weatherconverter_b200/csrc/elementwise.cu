@@ -32,6 +32,7 @@ ddpm_step_kernel(const float4* __restrict__ xt, const float4* __restrict__ eps, 
                  size_t n4_per_sample, int B, StepCoef c, const float* __restrict__ betas,
                  const float* __restrict__ alphas, const float* __restrict__ sqrt_1m_acp,
                  const long long* __restrict__ t, int T) {
+  pdl_prologue();
   const size_t total = n4_per_sample * B;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256)
 add_noise_kernel(const float4* __restrict__ x0, const float4* __restrict__ noise, float4* __restrict__ out,
                  size_t n4_per_sample, int B, const float* __restrict__ sqrt_acp,
                  const float* __restrict__ sqrt_1m_acp, const long long* __restrict__ t, int T) {
+  pdl_prologue();
   const size_t total = n4_per_sample * B;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -96,6 +98,7 @@ add_noise_kernel(const float4* __restrict__ x0, const float4* __restrict__ noise
 __global__ void __launch_bounds__(256)
 sgg_update_kernel(const float* __restrict__ grad, const float* __restrict__ mu, const float* __restrict__ sigz,
                   float* __restrict__ out, float* __restrict__ mag_out, int B, int h, int w, int pool, float lam) {
+  pdl_prologue();
   const size_t hw = static_cast<size_t>(h) * w;
   const size_t total = hw * B;
   const int Ws = w * pool, Hs = h * pool;
@@ -132,6 +135,7 @@ sgg_update_kernel(const float* __restrict__ grad, const float* __restrict__ mu, 
 __global__ void __launch_bounds__(256)
 lcg_prepare_kernel(const float* __restrict__ sr, const long long* __restrict__ gt, float* __restrict__ xm,
                    long long* __restrict__ gm, int B, int NC, size_t hw) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(B) * NC * hw;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -147,6 +151,7 @@ lcg_prepare_kernel(const float* __restrict__ sr, const long long* __restrict__ g
 __global__ void __launch_bounds__(256)
 lcg_combine_kernel(const float* __restrict__ g4, const long long* __restrict__ gt, const float* __restrict__ mu,
                    const float* __restrict__ sigz, float* __restrict__ out, int B, int NC, int h, int w, int pool, float lam) {
+  pdl_prologue();
   const size_t hw = static_cast<size_t>(h) * w;
   const double stdv[3] = {0.229, 0.224, 0.225};
   const int Ws = w * pool;
@@ -193,7 +198,7 @@ int ddpm_step(const float* xt, const float* eps, const float* z, float* out, flo
   StepCoef c{beta, s, sqrt_alpha, sigma};
   const size_t n4 = n_per_sample / 4;
   ProfScope prof(kProfScheduler, st, 4.0 * n_per_sample * B * (2 + (z ? 1 : 0) + (out ? 1 : 0) + (mean_out ? 1 : 0) + (sigz_out ? 1 : 0)));
-  ddpm_step_kernel<0><<<grid_for(n4 * B), 256, 0, st>>>(
+  launch_k(ddpm_step_kernel<0>, grid_for(n4 * B), 256, 0, st, 
       reinterpret_cast<const float4*>(xt), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(z),
       reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(mean_out), reinterpret_cast<float4*>(sigz_out), n4, B,
       c, nullptr, nullptr, nullptr, nullptr, 1);
@@ -208,7 +213,7 @@ int ddpm_step_indexed(const float* xt, const float* eps, const float* z, float* 
   StepCoef c{0, 1, 1, 0};
   const size_t n4 = n_per_sample / 4;
   ProfScope prof(kProfScheduler, st, 4.0 * n_per_sample * B * (2 + (z ? 1 : 0) + (out ? 1 : 0) + (mean_out ? 1 : 0) + (sigz_out ? 1 : 0)));
-  ddpm_step_kernel<2><<<grid_for(n4 * B), 256, 0, st>>>(
+  launch_k(ddpm_step_kernel<2>, grid_for(n4 * B), 256, 0, st, 
       reinterpret_cast<const float4*>(xt), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(z),
       reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(mean_out), reinterpret_cast<float4*>(sigz_out), n4, B,
       c, coef_tables, nullptr, nullptr, t_dev, T);
@@ -223,7 +228,7 @@ int ddpm_step_batched(const float* xt, const float* eps, const float* z, float* 
   WC_REQUIRE(T >= 1, "num_timesteps must be positive");
   StepCoef c{0, 1, 1, 0};
   const size_t n4 = n_per_sample / 4;
-  ddpm_step_kernel<1><<<grid_for(n4 * B), 256, 0, st>>>(
+  launch_k(ddpm_step_kernel<1>, grid_for(n4 * B), 256, 0, st, 
       reinterpret_cast<const float4*>(xt), reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(z),
       reinterpret_cast<float4*>(out), reinterpret_cast<float4*>(mean_out), reinterpret_cast<float4*>(sigz_out), n4, B,
       c, betas, alphas, sqrt_1m_acp, t, T);
@@ -236,7 +241,7 @@ int add_noise(const float* x0, const float* noise, float* out, size_t n_per_samp
   WC_REQUIRE(n_per_sample % 4 == 0, "elements per sample must be a multiple of 4");
   WC_REQUIRE(T >= 1, "num_timesteps must be positive");
   const size_t n4 = n_per_sample / 4;
-  add_noise_kernel<<<grid_for(n4 * B), 256, 0, st>>>(reinterpret_cast<const float4*>(x0),
+  launch_k(add_noise_kernel, grid_for(n4 * B), 256, 0, st, reinterpret_cast<const float4*>(x0),
                                                       reinterpret_cast<const float4*>(noise),
                                                       reinterpret_cast<float4*>(out), n4, B, sqrt_acp, sqrt_1m_acp, t, T);
   WC_LAUNCH_CHECK();
@@ -245,14 +250,14 @@ int add_noise(const float* x0, const float* noise, float* out, size_t n_per_samp
 
 int lcg_prepare(const float* sr, const long long* gt, float* xm, long long* gm, int B, int NC, size_t hw, cudaStream_t st) {
   WC_REQUIRE(NC <= 32, "at most 32 classes");
-  lcg_prepare_kernel<<<grid_for(static_cast<size_t>(B) * NC * hw), 256, 0, st>>>(sr, gt, xm, gm, B, NC, hw);
+  launch_k(lcg_prepare_kernel, grid_for(static_cast<size_t>(B) * NC * hw), 256, 0, st, sr, gt, xm, gm, B, NC, hw);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int lcg_combine(const float* g4, const long long* gt, const float* mu, const float* sigz, float* out, int B, int NC, int h,
                 int w, int pool, float lam, cudaStream_t st) {
   WC_REQUIRE(NC <= 32, "at most 32 classes");
-  lcg_combine_kernel<<<grid_for(static_cast<size_t>(B) * h * w), 256, 0, st>>>(g4, gt, mu, sigz, out, B, NC, h, w, pool, lam);
+  launch_k(lcg_combine_kernel, grid_for(static_cast<size_t>(B) * h * w), 256, 0, st, g4, gt, mu, sigz, out, B, NC, h, w, pool, lam);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -260,7 +265,7 @@ int lcg_combine(const float* g4, const long long* gt, const float* mu, const flo
 int sgg_update(const float* grad, const float* mu, const float* sigz, float* out, float* mag_out, int B, int h, int w,
                int pool, float lam, cudaStream_t st) {
   ProfScope prof(kProfScheduler, st, static_cast<double>(B) * h * w * (12.0 * pool * pool + 36.0));
-  sgg_update_kernel<<<grid_for(static_cast<size_t>(B) * h * w), 256, 0, st>>>(grad, mu, sigz, out, mag_out, B, h, w,
+  launch_k(sgg_update_kernel, grid_for(static_cast<size_t>(B) * h * w), 256, 0, st, grad, mu, sigz, out, mag_out, B, h, w,
                                                                               pool, lam);
   WC_LAUNCH_CHECK();
   return 0;

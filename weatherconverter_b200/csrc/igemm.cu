@@ -261,12 +261,6 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   // bias / PReLU vectors -> shared memory (read once per CTA instead of once per tile from L2)
   float* s_vec = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
   const bool bias_in_smem = p.bias && p.N <= kBiasMaxN, prelu_in_smem = p.prelu && p.N <= kPreluMaxN;
-  {
-    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
-      if (bias_in_smem) s_vec[i] = p.bias[i];
-      if (prelu_in_smem) s_vec[kBiasMaxN + i] = p.prelu[i];
-    }
-  }
   const float* s_bias = bias_in_smem ? s_vec : nullptr;
   const float* s_prelu = prelu_in_smem ? s_vec + kBiasMaxN : nullptr;
 
@@ -295,6 +289,14 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     __syncwarp();
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
+  }
+  // Programmatic dependent launch: everything above (descriptor prefetch, mbarrier init, TMEM allocation) touches no global
+  // data and overlaps the tail of the previous kernel; from here on this kernel reads activations / writes outputs.
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+    if (bias_in_smem) s_vec[i] = p.bias[i];
+    if (prelu_in_smem) s_vec[kBiasMaxN + i] = p.prelu[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -502,7 +504,7 @@ static int launch_variant(const IgemmPlan& plan, cudaStream_t stream) {
     WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<ROW3, TMA_OUT, TMA_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  igemm_kernel<ROW3, TMA_OUT, TMA_RES><<<plan.grid, kThreads, kSmemBytes, stream>>>(plan.maps, plan.args);
+  launch_k<1>(igemm_kernel<ROW3, TMA_OUT, TMA_RES>, plan.grid, kThreads, kSmemBytes, stream, plan.maps, plan.args);
   return 0;
 }
 

@@ -21,6 +21,7 @@ __device__ __forceinline__ uint8_t to_byte_trunc(float v) {  // Tensor.byte() of
 // out: HWC uint8 grid [Hg][Wg][3] (the PIL image ToPILImage builds from the CHW float grid)
 __global__ void ddpm_grid_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int B, int H, int W, int xmaps, int ymaps,
                                     int pad, int Hg, int Wg) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(Hg) * Wg;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int gx = static_cast<int>(i % Wg), gy = static_cast<int>(i / Wg);
@@ -51,6 +52,7 @@ __global__ void ddpm_grid_u8_kernel(const float* __restrict__ x, uint8_t* __rest
 // NCHW float -> NCHW uint8: (x*std + mean) * 255, clamp(0, 255), truncate
 __global__ void postprocess_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, size_t n, int HW, float m0, float m1, float m2,
                                       float s0, float s1, float s2) {
+  pdl_prologue();
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>((i / HW) % 3);
     const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), std = c == 0 ? s0 : (c == 1 ? s1 : s2);
@@ -65,6 +67,7 @@ __global__ void postprocess_u8_kernel(const float* __restrict__ x, uint8_t* __re
 __global__ void label_encode_kernel(const uint8_t* __restrict__ lab, int Ws, const int* __restrict__ ytab, const int* __restrict__ xtab,
                                     int top, int left, int Hc, int Wc, const long long* __restrict__ lut, int nlut,
                                     long long* __restrict__ out) {
+  pdl_prologue();
   const int total = Hc * Wc;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int y = i / Wc, x = i % Wc;
@@ -77,6 +80,7 @@ __global__ void label_encode_kernel(const uint8_t* __restrict__ lab, int Ws, con
 // One pass of Pillow's 8-bit resampling along x: out[y][xx][c] = clip8((sum_k in[y][xmin+k][c] * kk[xx][k] + 2^21) >> 22)
 __global__ void resample_h_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int Win, int Wout, int C,
                                   const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(H) * Wout * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C), xx = static_cast<int>((i / C) % Wout);
@@ -91,6 +95,7 @@ __global__ void resample_h_kernel(const uint8_t* __restrict__ in, uint8_t* __res
 // ... and along y
 __global__ void resample_v_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int Hout, int W, int C,
                                   const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(Hout) * W * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t col = i % (static_cast<size_t>(W) * C);
@@ -107,6 +112,7 @@ __global__ void resample_v_kernel(const uint8_t* __restrict__ in, uint8_t* __res
 // (x - mean)/std (mode 1, ExtNormalize)
 __global__ void u8_to_tensor_kernel(const uint8_t* __restrict__ in, int Win, int top, int left, int Hc, int Wc, int mode, float m0, float m1,
                                     float m2, float s0, float s1, float s2, float* __restrict__ out) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(3) * Hc * Wc;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int x = static_cast<int>(i % Wc), y = static_cast<int>((i / Wc) % Hc), c = static_cast<int>(i / (static_cast<size_t>(Wc) * Hc));
@@ -132,28 +138,28 @@ int ddpm_grid_u8(const float* x, uint8_t* out, int B, int H, int W, int nrow, in
   if (B == 1) { pad = 0; Hg = H; Wg = W; }   // make_grid returns a single image unpadded
   else { Hg = (H + pad) * ymaps + pad; Wg = (W + pad) * xmaps + pad; }
   ProfScope prof(kProfOther, st, 12.0 * B * H * W + 3.0 * Hg * Wg);
-  ddpm_grid_u8_kernel<<<nblocks(static_cast<size_t>(Hg) * Wg), 256, 0, st>>>(x, out, B, H, W, xmaps, ymaps, pad, Hg, Wg);
+  launch_k(ddpm_grid_u8_kernel, nblocks(static_cast<size_t>(Hg) * Wg), 256, 0, st, x, out, B, H, W, xmaps, ymaps, pad, Hg, Wg);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int postprocess_u8(const float* x, uint8_t* out, int B, int H, int W, const float* mean3, const float* std3, cudaStream_t st) {
   const size_t n = static_cast<size_t>(B) * 3 * H * W;
   ProfScope prof(kProfOther, st, 5.0 * n);
-  postprocess_u8_kernel<<<nblocks(n), 256, 0, st>>>(x, out, n, H * W, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
+  launch_k(postprocess_u8_kernel, nblocks(n), 256, 0, st, x, out, n, H * W, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2]);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int label_encode(const uint8_t* lab, int Ws, const int* ytab, const int* xtab, int top, int left, int Hc, int Wc, const long long* lut,
                  int nlut, long long* out, cudaStream_t st) {
-  label_encode_kernel<<<nblocks(static_cast<size_t>(Hc) * Wc), 256, 0, st>>>(lab, Ws, ytab, xtab, top, left, Hc, Wc, lut, nlut, out);
+  launch_k(label_encode_kernel, nblocks(static_cast<size_t>(Hc) * Wc), 256, 0, st, lab, Ws, ytab, xtab, top, left, Hc, Wc, lut, nlut, out);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int resample_u8(const uint8_t* in, uint8_t* tmp, uint8_t* out, int Hin, int Win, int Hout, int Wout, int C, const int* bounds_h,
                 const int* kk_h, int ksize_h, const int* bounds_v, const int* kk_v, int ksize_v, cudaStream_t st) {
-  resample_h_kernel<<<nblocks(static_cast<size_t>(Hin) * Wout * C), 256, 0, st>>>(in, tmp, Hin, Win, Wout, C, bounds_h, kk_h, ksize_h);
+  launch_k(resample_h_kernel, nblocks(static_cast<size_t>(Hin) * Wout * C), 256, 0, st, in, tmp, Hin, Win, Wout, C, bounds_h, kk_h, ksize_h);
   WC_LAUNCH_CHECK();
-  resample_v_kernel<<<nblocks(static_cast<size_t>(Hout) * Wout * C), 256, 0, st>>>(tmp, out, Hout, Wout, C, bounds_v, kk_v, ksize_v);
+  launch_k(resample_v_kernel, nblocks(static_cast<size_t>(Hout) * Wout * C), 256, 0, st, tmp, out, Hout, Wout, C, bounds_v, kk_v, ksize_v);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -162,7 +168,7 @@ int u8_to_tensor(const uint8_t* in, int Win, int top, int left, int Hc, int Wc, 
   const float one[3] = {1.f, 1.f, 1.f}, zero[3] = {0.f, 0.f, 0.f};
   const float* m = mean3 ? mean3 : zero;
   const float* s = std3 ? std3 : one;
-  u8_to_tensor_kernel<<<nblocks(static_cast<size_t>(3) * Hc * Wc), 256, 0, st>>>(in, Win, top, left, Hc, Wc, mode, m[0], m[1], m[2], s[0], s[1],
+  launch_k(u8_to_tensor_kernel, nblocks(static_cast<size_t>(3) * Hc * Wc), 256, 0, st, in, Win, top, left, Hc, Wc, mode, m[0], m[1], m[2], s[0], s[1],
                                                                                 s[2], out);
   WC_LAUNCH_CHECK();
   return 0;

@@ -41,6 +41,7 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&f)[8]) {
 // eval-mode BatchNorm2d as a per-channel affine map (old_modules.py:146): y = x*scale[c] + shift[c]
 __global__ void channel_affine_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t npix, int C,
                                       int ldx, int ldy, const float* __restrict__ scale, const float* __restrict__ shift) {
+  pdl_prologue();
   const int vpp = C / 8;
   const size_t total = npix * vpp;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -57,6 +58,7 @@ __global__ void channel_affine_kernel(const __nv_bfloat16* __restrict__ x, __nv_
 // nn.LayerNorm([C]) over the channels of every token (old_modules.py:80,82): one warp per token
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t rows, int C, int ldx,
                                  int ldy, const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  pdl_prologue();
   const size_t row = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -81,6 +83,7 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloa
 // nn.AvgPool2d(2) (old_modules.py:183)
 __global__ void avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int Ho, int Wo, int C,
                                 int ldx, int ldy) {
+  pdl_prologue();
   const int vpp = C / 8;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * vpp;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -106,6 +109,7 @@ __global__ void avgpool2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
 // sinusoidal_embedding (old_modules.py:283-307) of the per-sample noise variance + nn.Upsample(nearest) to the image
 // (:313-315): 32 channels [sin(2 pi f_j t) | cos(2 pi f_j t)], f_j = exp(linspace(ln 1, ln 1000, 16)), broadcast per pixel
 __global__ void embed_broadcast_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ y, int HW, int ldy) {
+  pdl_prologue();
   __shared__ __align__(16) __nv_bfloat16 emb[32];
   const int b = blockIdx.y;
   if (threadIdx.x < 16) {
@@ -131,7 +135,7 @@ int channel_affine(const __nv_bfloat16* x, __nv_bfloat16* y, size_t npix, int C,
                    const float* shift, cudaStream_t st) {
   WC_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "channel_affine: channel counts must be multiples of 8");
   ProfScope prof(kProfGroupNorm, st, 4.0 * npix * C);
-  channel_affine_kernel<<<blocks_for(npix * (C / 8)), 256, 0, st>>>(x, y, npix, C, ldx, ldy, scale, shift);
+  launch_k(channel_affine_kernel, blocks_for(npix * (C / 8)), 256, 0, st, x, y, npix, C, ldx, ldy, scale, shift);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -139,20 +143,20 @@ int layernorm_rows(const __nv_bfloat16* x, __nv_bfloat16* y, size_t rows, int C,
                    const float* beta, float eps, cudaStream_t st) {
   WC_REQUIRE(C <= 256, "layernorm_rows supports C <= 256");
   ProfScope prof(kProfGroupNorm, st, 4.0 * rows * C);
-  layernorm_kernel<<<static_cast<int>((rows * 32 + 255) / 256), 256, 0, st>>>(x, y, rows, C, ldx, ldy, gamma, beta, eps);
+  launch_k(layernorm_kernel, static_cast<int>((rows * 32 + 255) / 256), 256, 0, st, x, y, rows, C, ldx, ldy, gamma, beta, eps);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int avgpool2(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int Ho, int Wo, int C, int ldx, int ldy, cudaStream_t st) {
   WC_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "avgpool2: channel counts must be multiples of 8");
   ProfScope prof(kProfOther, st, 2.5 * B * Ho * Wo * 4.0 * C);
-  avgpool2_kernel<<<blocks_for(static_cast<size_t>(B) * Ho * Wo * (C / 8)), 256, 0, st>>>(x, y, B, Ho, Wo, C, ldx, ldy);
+  launch_k(avgpool2_kernel, blocks_for(static_cast<size_t>(B) * Ho * Wo * (C / 8)), 256, 0, st, x, y, B, Ho, Wo, C, ldx, ldy);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int embed_broadcast(const float* t, __nv_bfloat16* y, int B, int HW, int ldy, cudaStream_t st) {
   ProfScope prof(kProfOther, st, 64.0 * B * HW);
-  embed_broadcast_kernel<<<dim3(64, B), 256, 0, st>>>(t, y, HW, ldy);
+  launch_k(embed_broadcast_kernel, dim3(64, B), 256, 0, st, t, y, HW, ldy);
   WC_LAUNCH_CHECK();
   return 0;
 }

@@ -14,6 +14,7 @@ constexpr int kGroups = 8;
 // Each thread owns one 8-channel vector column (fixed group) and strides over pixels.
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int ld, int nsplit,
                                 float2* __restrict__ partial) {
+  pdl_prologue();
   extern __shared__ float2 stash[];
   const int vpp = C / 8, gv = (C / kGroups) / 8;  // vectors per pixel, vectors per group
   const int rows = blockDim.x / vpp;
@@ -61,6 +62,7 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int HW, int C,
                                 int ld, int ldy, int nsplit_stats, int nsplit, const float2* __restrict__ partial,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu) {
+  pdl_prologue();
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
   const int b = blockIdx.y, split = blockIdx.x;
   if (threadIdx.x < kGroups) {
@@ -164,6 +166,7 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
                                     int ld, int ldd, int nsplit_stats, int nsplit, const float2* __restrict__ partial,
                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                     float2* __restrict__ part) {
+  pdl_prologue();
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
   extern __shared__ float2 stash[];  // [rows][C]
   const int b = blockIdx.y, split = blockIdx.x;
@@ -218,6 +221,7 @@ __global__ void gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ x, const _
 // pass 2: per-sample channel sums bc[b][c] and group sums gs[b][g] = (S1, S2)
 __global__ void gn_bwd_reduce_kernel(const float2* __restrict__ part, int C, int nsplit, const float* __restrict__ gamma,
                                      float2* __restrict__ bc, float2* __restrict__ gs) {
+  pdl_prologue();
   extern __shared__ float2 prod[];  // [C]
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -238,6 +242,7 @@ __global__ void gn_bwd_reduce_kernel(const float2* __restrict__ part, int C, int
 
 __global__ void gn_bwd_param_kernel(const float2* __restrict__ bc, int B, int C, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s0 = 0.f, s1 = 0.f;
@@ -253,6 +258,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                     const __nv_bfloat16* __restrict__ add1, int lda1, const __nv_bfloat16* __restrict__ add2,
                                     int lda2) {
+  pdl_prologue();
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
   const int b = blockIdx.y, split = blockIdx.x;
   group_stats(partial, b, nsplit_stats, HW, C, eps, s_mean, s_rstd);
@@ -300,6 +306,7 @@ __global__ void gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ x, const _
 
 // per-sample column sums of an NHWC bf16 tensor: part[b][split][c]
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int ld, int nsplit, float* __restrict__ part) {
+  pdl_prologue();
   extern __shared__ float cstash[];  // [rows][C]
   const int b = blockIdx.y, split = blockIdx.x;
   const int vpp = C / 8;
@@ -343,6 +350,7 @@ __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C
 // sample lanes; every sum runs in a fixed order (deterministic).
 __global__ void colsum_finish_kernel(const float* __restrict__ part, int B, int C, int nsplit, float* __restrict__ out_rows,
                                      int ldo, float* __restrict__ out_total) {
+  pdl_prologue();
   __shared__ float tot[8][64];
   const int cl = threadIdx.x & 63, bl = threadIdx.x >> 6;   // 512 threads
   const int c = blockIdx.x * 64 + cl;
@@ -376,8 +384,8 @@ size_t groupnorm_workspace_bytes(int B) { return static_cast<size_t>(B) * 64 * k
 // tests/test_gpu_config_shapes.py).  Large batches simply get more, smaller blocks (B * nsplit).
 int groupnorm_stats_splits(int B, int HW) {
   (void)B;
-  int nsplit = (HW + 31) / 32;
-  if (nsplit > 64) nsplit = 64;
+  int nsplit = (HW + 127) / 128;     // >= 128 pixels per block (a block of 2048 got 1.5x slower with 32-pixel slabs)
+  if (nsplit > 32) nsplit = 32;
   if (nsplit < 1) nsplit = 1;
   return nsplit;
 }
@@ -393,12 +401,12 @@ int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int 
   const int max_split = (HW + 31) / 32;
   float2* partial = reinterpret_cast<float2*>(workspace);
   ProfScope prof(kProfGroupNorm, st, 6.0 * B * static_cast<double>(HW) * C);  // algorithmic bytes: 2 reads + 1 write, bf16
-  gn_stats_kernel<<<dim3(nsplit, B), threads, threads * sizeof(float2), st>>>(x, HW, C, ld, nsplit, partial);
+  launch_k(gn_stats_kernel, dim3(nsplit, B), threads, threads * sizeof(float2), st, x, HW, C, ld, nsplit, partial);
   WC_LAUNCH_CHECK();
   int asplit = (8 * num_sms() + B - 1) / B;
   if (asplit > max_split) asplit = max_split;
   if (asplit < 1) asplit = 1;
-  gn_apply_kernel<<<dim3(asplit, B), threads, 0, st>>>(x, y, HW, C, ld, ldy, nsplit, asplit, partial, gamma, beta, eps,
+  launch_k(gn_apply_kernel, dim3(asplit, B), threads, 0, st, x, y, HW, C, ld, ldy, nsplit, asplit, partial, gamma, beta, eps,
                                                        silu);
   WC_LAUNCH_CHECK();
   return 0;
@@ -443,18 +451,18 @@ int groupnorm_silu_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfl
   float2* gs = bc + static_cast<size_t>(B) * C;
   const float2* partial = reinterpret_cast<const float2*>(stats);
   ProfScope prof(kProfGroupNorm, st, 10.0 * B * static_cast<double>(HW) * C);  // x, dy read twice, dx written (bf16)
-  gn_bwd_stats_kernel<<<dim3(nsplit, B), threads, static_cast<size_t>(rows) * C * sizeof(float2), st>>>(
+  launch_k(gn_bwd_stats_kernel, dim3(nsplit, B), threads, static_cast<size_t>(rows) * C * sizeof(float2), st, 
       x, dy, HW, C, ld, ldd, ns_stats, nsplit, partial, gamma, beta, eps, silu, part);
   WC_LAUNCH_CHECK();
-  gn_bwd_reduce_kernel<<<B, 256, C * sizeof(float2), st>>>(part, C, nsplit, gamma, bc, gs);
+  launch_k(gn_bwd_reduce_kernel, B, 256, C * sizeof(float2), st, part, C, nsplit, gamma, bc, gs);
   WC_LAUNCH_CHECK();
-  gn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st>>>(bc, B, C, dgamma, dbeta);
+  launch_k(gn_bwd_param_kernel, (C + 127) / 128, 128, 0, st, bc, B, C, dgamma, dbeta);
   WC_LAUNCH_CHECK();
   int asplit = (8 * num_sms() + B - 1) / B;
   const int max_split = (HW + 31) / 32;
   if (asplit > max_split) asplit = max_split;
   if (asplit < 1) asplit = 1;
-  gn_bwd_apply_kernel<<<dim3(asplit, B), threads, 0, st>>>(x, dy, dx, HW, C, ld, ldd, ldo, ns_stats, asplit, partial, gs, gamma,
+  launch_k(gn_bwd_apply_kernel, dim3(asplit, B), threads, 0, st, x, dy, dx, HW, C, ld, ldd, ldo, ns_stats, asplit, partial, gs, gamma,
                                                            beta, eps, silu, add1, lda1, add2, lda2);
   WC_LAUNCH_CHECK();
   return 0;
@@ -473,9 +481,9 @@ int colsum(const __nv_bfloat16* x, int B, int HW, int C, int ld, float* out_rows
   const int nsplit = bwd_splits(B, HW);
   float* part = reinterpret_cast<float*>(workspace);
   ProfScope prof(kProfOther, st, 2.0 * B * static_cast<double>(HW) * C);
-  colsum_kernel<<<dim3(nsplit, B), threads, static_cast<size_t>(rows) * C * sizeof(float), st>>>(x, HW, C, ld, nsplit, part);
+  launch_k(colsum_kernel, dim3(nsplit, B), threads, static_cast<size_t>(rows) * C * sizeof(float), st, x, HW, C, ld, nsplit, part);
   WC_LAUNCH_CHECK();
-  colsum_finish_kernel<<<(C + 63) / 64, 512, 0, st>>>(part, B, C, nsplit, out_rows, ldo, out_total);
+  launch_k(colsum_finish_kernel, (C + 63) / 64, 512, 0, st, part, B, C, nsplit, out_rows, ldo, out_total);
   WC_LAUNCH_CHECK();
   return 0;
 }

@@ -20,6 +20,7 @@ inline int grid_for(size_t n_items, int per_block = 256) {
 // scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (eval-mode BatchNorm folded into the conv)
 __global__ void bn_fold_kernel(const float* g, const float* b, const float* mean, const float* var, float eps,
                                float* scale, float* shift, int n, int n_pad) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pad) return;
   if (i < n) {
@@ -35,6 +36,7 @@ __global__ void bn_fold_kernel(const float* g, const float* b, const float* mean
 // ---- MaxPool 3x3 s2 p1, NHWC bf16, 8 channels per thread; stores the argmax tap (0..8) per element.
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    uint8_t* __restrict__ idx, int B, int H, int W, int C, int Ho, int Wo) {
+  pdl_prologue();
   const int c8n = C / 8;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * c8n;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -81,6 +83,7 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                                    const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx, int B, int H,
                                    int W, int C, int Ho, int Wo) {
+  pdl_prologue();
   const int c8n = C / 8;
   const size_t total = static_cast<size_t>(B) * H * W * c8n;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -124,6 +127,7 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const u
 
 // ---- global average pool: x [B,HW,C] (ld) -> y [B,C]; one block per (b, 64-channel slab)
 __global__ void gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int HW, int C, int ld) {
+  pdl_prologue();
   __shared__ float red[4][64];
   const int b = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
   float acc = 0.f;
@@ -136,6 +140,7 @@ __global__ void gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
 }
 // y[b,p,c] (ldy) = v[b,c]  (bilinear up-sampling of a 1x1 map = broadcast, _deeplab.py:131)
 __global__ void broadcast_kernel(const __nv_bfloat16* __restrict__ v, __nv_bfloat16* __restrict__ y, int B, int HW, int C, int ldy) {
+  pdl_prologue();
   const int c8n = C / 8;
   const size_t total = static_cast<size_t>(B) * HW * c8n;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -148,6 +153,7 @@ __global__ void broadcast_kernel(const __nv_bfloat16* __restrict__ v, __nv_bfloa
 // adjoint of broadcast: v[b,c] = sum_p y[b,p,c], optionally masked by (m[b,c] > 0) (ReLU of the pooled branch)
 __global__ void sum_hw_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ m,
                               __nv_bfloat16* __restrict__ v, int HW, int C, int ldy) {
+  pdl_prologue();
   __shared__ float red[4][64];
   const int b = blockIdx.y, c = blockIdx.x * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
   float acc = 0.f;
@@ -163,6 +169,7 @@ __global__ void sum_hw_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bf
 }
 // adjoint of the global average pool, accumulated into dx: dx[b,p,c] += g[b,c] / HW
 __global__ void gap_bwd_add_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dx, int B, int HW, int C, int ld) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(B) * HW * C;
   const float inv = 1.f / HW;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -187,6 +194,7 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
 // NHWC bf16 -> NHWC bf16 (channel slice views allowed), 8 channels per thread
 __global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int Hi,
                                     int Wi, int Ho, int Wo, int C, int ldx, int ldy) {
+  pdl_prologue();
   const int c8n = C / 8;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * c8n;
   const float sy = static_cast<float>(Hi) / Ho, sx = static_cast<float>(Wi) / Wo;
@@ -222,6 +230,7 @@ __global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 __global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ m,
                                     __nv_bfloat16* __restrict__ dx, int B, int Hi, int Wi, int Ho, int Wo, int C,
                                     int ldy, int ldm, int ldx) {
+  pdl_prologue();
   const int c8n = C / 8;
   const size_t total = static_cast<size_t>(B) * Hi * Wi * c8n;
   const float sy = static_cast<float>(Hi) / Ho, sx = static_cast<float>(Wi) / Wo;
@@ -280,6 +289,7 @@ __global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const 
 // ---- segmentation loss head (seg_model/inference.py:124-141 + network/utils.py:17)
 // n_valid[b] = #pixels with label != ignore
 __global__ void count_valid_kernel(const long long* __restrict__ labels, int HW, int ignore, int* __restrict__ n_valid) {
+  pdl_prologue();
   const int b = blockIdx.y;
   int cnt = 0;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x)
@@ -296,6 +306,7 @@ __global__ void seg_loss_grad_kernel(const float* __restrict__ logits_lo, const 
                                      const int* __restrict__ n_valid, long long* __restrict__ pred,
                                      float* __restrict__ dlogit_hi, float* __restrict__ loss, float* __restrict__ logits_hi,
                                      int B, int h, int w, int H, int W, int ignore) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(B) * H * W;
   const float sy = static_cast<float>(h) / H, sx = static_cast<float>(w) / W;
   // warp-uniform trip count (the loss reduction below uses full-warp shuffles)
@@ -366,6 +377,7 @@ __global__ void seg_loss_grad_kernel(const float* __restrict__ logits_lo, const 
 template <int NC>
 __global__ void logits_bilinear_bwd_kernel(const float* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo, int B, int h,
                                            int w, int H, int W, int CP, int ldo) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(B) * h * w;
   const float sy = static_cast<float>(h) / H, sx = static_cast<float>(w) / W;
   const int fy = (H + h - 1) / h, fx = (W + w - 1) / w;
@@ -410,6 +422,7 @@ __global__ void logits_bilinear_bwd_kernel(const float* __restrict__ dhi, __nv_b
 __global__ void __launch_bounds__(128)
 conv1_dgrad_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ w /*[64][3][7][7]*/,
                    const float* __restrict__ scale, float* __restrict__ dx, int B, int H, int W, int Ho, int Wo) {
+  pdl_prologue();
   extern __shared__ float sw[];  // [49][3][64]
   for (int i = threadIdx.x; i < 49 * 3 * 64; i += blockDim.x) {
     const int o = i & 63, c = (i >> 6) % 3, t = i / 192;
@@ -461,6 +474,7 @@ conv1_dgrad_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict
 // (position independent; dZ outside the map contributes nothing).  One thread per pooled pixel, weights in smem.
 __global__ void conv1_dgrad_weff_kernel(const float* __restrict__ w, const float* __restrict__ scale, float* __restrict__ weff,
                                         int P) {
+  pdl_prologue();
   const int R = P / 2 + 3;
   const int total = R * R * 3 * 64;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -482,6 +496,7 @@ __global__ void conv1_dgrad_weff_kernel(const float* __restrict__ w, const float
 __global__ void __launch_bounds__(128)
 conv1_dgrad_pooled_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ weff, float* __restrict__ out, int B,
                           int Ho, int Wo, int P) {
+  pdl_prologue();
   extern __shared__ float sw[];  // [R*R][3][64]
   const int R = P / 2 + 3, half = P / 2;
   for (int i = threadIdx.x; i < R * R * 192; i += blockDim.x) sw[i] = weff[i];
@@ -524,6 +539,7 @@ conv1_dgrad_pooled_kernel(const __nv_bfloat16* __restrict__ dz, const float* __r
 // d[p,c] = 0 where m[p,c] <= 0 (ReLU derivative applied to a gradient slice in place)
 __global__ void relu_mask_kernel(__nv_bfloat16* __restrict__ d, const __nv_bfloat16* __restrict__ m, size_t npix, int C,
                                  int ldd, int ldm) {
+  pdl_prologue();
   const size_t total = npix * C;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -538,6 +554,7 @@ __global__ void relu_mask_kernel(__nv_bfloat16* __restrict__ d, const __nv_bfloa
 __global__ void compose_sep_kernel(const float* __restrict__ dw, const float* __restrict__ pw, const float* __restrict__ dwb,
                                    const float* __restrict__ pwb, float* __restrict__ w, float* __restrict__ bias, int Co,
                                    int Ci, int KK) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(Co) * Ci * KK;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -559,14 +576,14 @@ __global__ void compose_sep_kernel(const float* __restrict__ dw, const float* __
 // ------------------------------------------------------------------------------------------ host launchers
 int bn_fold(const float* g, const float* b, const float* mean, const float* var, float eps, float* scale, float* shift,
             int n, int n_pad, cudaStream_t st) {
-  bn_fold_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(g, b, mean, var, eps, scale, shift, n, n_pad);
+  launch_k(bn_fold_kernel, (n_pad + 255) / 256, 256, 0, st, g, b, mean, var, eps, scale, shift, n, n_pad);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   ProfScope prof(kProfOther, st, 0);
-  maxpool_fwd_kernel<<<grid_for(static_cast<size_t>(B) * Ho * Wo * C / 8), 256, 0, st>>>(x, y, idx, B, H, W, C, Ho, Wo);
+  launch_k(maxpool_fwd_kernel, grid_for(static_cast<size_t>(B) * Ho * Wo * C / 8), 256, 0, st, x, y, idx, B, H, W, C, Ho, Wo);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -574,31 +591,31 @@ int maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* idx, const __nv_bfloat16
                 int W, int C, cudaStream_t st) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   ProfScope prof(kProfOther, st, 0);
-  maxpool_bwd_kernel<<<grid_for(static_cast<size_t>(B) * H * W * C / 8), 256, 0, st>>>(dy, idx, x, dx, B, H, W, C, Ho, Wo);
+  launch_k(maxpool_bwd_kernel, grid_for(static_cast<size_t>(B) * H * W * C / 8), 256, 0, st, dy, idx, x, dx, B, H, W, C, Ho, Wo);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int gap_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, int ld, cudaStream_t st) {
   ProfScope prof(kProfOther, st, 0);
-  gap_fwd_kernel<<<dim3((C + 63) / 64, B), 256, 0, st>>>(x, y, HW, C, ld);
+  launch_k(gap_fwd_kernel, dim3((C + 63) / 64, B), 256, 0, st, x, y, HW, C, ld);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int broadcast_hw(const __nv_bfloat16* v, __nv_bfloat16* y, int B, int HW, int C, int ldy, cudaStream_t st) {
   ProfScope prof(kProfOther, st, 0);
-  broadcast_kernel<<<grid_for(static_cast<size_t>(B) * HW * C / 8), 256, 0, st>>>(v, y, B, HW, C, ldy);
+  launch_k(broadcast_kernel, grid_for(static_cast<size_t>(B) * HW * C / 8), 256, 0, st, v, y, B, HW, C, ldy);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int sum_hw(const __nv_bfloat16* y, const __nv_bfloat16* mask, __nv_bfloat16* v, int B, int HW, int C, int ldy, cudaStream_t st) {
   ProfScope prof(kProfOther, st, 0);
-  sum_hw_kernel<<<dim3((C + 63) / 64, B), 256, 0, st>>>(y, mask, v, HW, C, ldy);
+  launch_k(sum_hw_kernel, dim3((C + 63) / 64, B), 256, 0, st, y, mask, v, HW, C, ldy);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int gap_bwd_add(const __nv_bfloat16* g, __nv_bfloat16* dx, int B, int HW, int C, int ld, cudaStream_t st) {
   ProfScope prof(kProfOther, st, 0);
-  gap_bwd_add_kernel<<<grid_for(static_cast<size_t>(B) * HW * C), 256, 0, st>>>(g, dx, B, HW, C, ld);
+  launch_k(gap_bwd_add_kernel, grid_for(static_cast<size_t>(B) * HW * C), 256, 0, st, g, dx, B, HW, C, ld);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -606,7 +623,7 @@ int bilinear_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int Hi, int Wi
                  cudaStream_t st) {
   WC_REQUIRE(C % 8 == 0, "bilinear: C must be a multiple of 8");
   ProfScope prof(kProfOther, st, 0);
-  bilinear_fwd_kernel<<<grid_for(static_cast<size_t>(B) * Ho * Wo * C / 8), 256, 0, st>>>(x, y, B, Hi, Wi, Ho, Wo, C, ldx, ldy);
+  launch_k(bilinear_fwd_kernel, grid_for(static_cast<size_t>(B) * Ho * Wo * C / 8), 256, 0, st, x, y, B, Hi, Wi, Ho, Wo, C, ldx, ldy);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -614,7 +631,7 @@ int bilinear_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* mask, __nv_bfloat
                  int Wo, int C, int ldy, int ldm, int ldx, cudaStream_t st) {
   ProfScope prof(kProfOther, st, 0);
   WC_REQUIRE(C % 8 == 0 && ldy % 8 == 0 && ldx % 8 == 0, "bilinear_bwd: channels / strides must be multiples of 8");
-  bilinear_bwd_kernel<<<grid_for(static_cast<size_t>(B) * Hi * Wi * C / 8), 256, 0, st>>>(dy, mask, dx, B, Hi, Wi, Ho, Wo, C, ldy, ldm, ldx);
+  launch_k(bilinear_bwd_kernel, grid_for(static_cast<size_t>(B) * Hi * Wi * C / 8), 256, 0, st, dy, mask, dx, B, Hi, Wi, Ho, Wo, C, ldy, ldm, ldx);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -624,9 +641,9 @@ int seg_loss_grad(const float* logits_lo, const long long* labels, int* n_valid,
   ProfScope prof(kProfOther, st, 0);
   WC_CHECK_CUDA(cudaMemsetAsync(n_valid, 0, B * sizeof(int), st));
   if (loss) WC_CHECK_CUDA(cudaMemsetAsync(loss, 0, B * sizeof(float), st));
-  count_valid_kernel<<<dim3(std::min(64, (H * W + 255) / 256), B), 256, 0, st>>>(labels, H * W, ignore, n_valid);
+  launch_k(count_valid_kernel, dim3(std::min(64, (H * W + 255) / 256), B), 256, 0, st, labels, H * W, ignore, n_valid);
   WC_LAUNCH_CHECK();
-  seg_loss_grad_kernel<19><<<grid_for(static_cast<size_t>(B) * H * W, 128), 128, 0, st>>>(logits_lo, labels, n_valid, pred, dlogit_hi, loss, logits_hi, B, h, w, H, W, ignore);
+  launch_k(seg_loss_grad_kernel<19>, grid_for(static_cast<size_t>(B) * H * W, 128), 128, 0, st, logits_lo, labels, n_valid, pred, dlogit_hi, loss, logits_hi, B, h, w, H, W, ignore);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -634,7 +651,7 @@ int logits_bilinear_bwd(const float* dhi, __nv_bfloat16* dlo, int B, int h, int 
                         cudaStream_t st) {
   WC_REQUIRE(nc == 19, "loss head is compiled for 19 classes");
   ProfScope prof(kProfOther, st, 0);
-  logits_bilinear_bwd_kernel<19><<<grid_for(static_cast<size_t>(B) * h * w, 128), 128, 0, st>>>(dhi, dlo, B, h, w, H, W, cp, ldo);
+  launch_k(logits_bilinear_bwd_kernel<19>, grid_for(static_cast<size_t>(B) * h * w, 128), 128, 0, st, dhi, dlo, B, h, w, H, W, cp, ldo);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -645,12 +662,12 @@ int conv1_dgrad(const __nv_bfloat16* dz, const float* w, const float* scale, flo
   const size_t smem = static_cast<size_t>(49) * 64 * 3 * sizeof(float);
   ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * (12.0 * H * W + 2.0 * Ho * Wo * Cout));
   const int gx = std::max(1, grid_for(static_cast<size_t>(B) * Ho * Wo, 128) / 2);
-  conv1_dgrad_kernel<<<dim3(gx, 4), 128, smem, st>>>(dz, w, scale, dx, B, H, W, Ho, Wo);
+  launch_k(conv1_dgrad_kernel, dim3(gx, 4), 128, smem, st, dz, w, scale, dx, B, H, W, Ho, Wo);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int conv1_dgrad_weff(const float* w, const float* scale, float* weff, int P, cudaStream_t st) {
-  conv1_dgrad_weff_kernel<<<8, 256, 0, st>>>(w, scale, weff, P);
+  launch_k(conv1_dgrad_weff_kernel, 8, 256, 0, st, w, scale, weff, P);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -665,19 +682,19 @@ int conv1_dgrad_pooled(const __nv_bfloat16* dz, const float* weff, float* out, i
     attr = smem;
   }
   ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * (12.0 * (H / P) * (W / P) + 2.0 * (H / 2) * (W / 2) * 64));
-  conv1_dgrad_pooled_kernel<<<grid_for(static_cast<size_t>(B) * (H / P) * (W / P), 128), 128, smem, st>>>(dz, weff, out, B, H / 2, W / 2, P);
+  launch_k(conv1_dgrad_pooled_kernel, grid_for(static_cast<size_t>(B) * (H / P) * (W / P), 128), 128, smem, st, dz, weff, out, B, H / 2, W / 2, P);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int relu_mask_inplace(__nv_bfloat16* d, const __nv_bfloat16* m, size_t npix, int C, int ldd, int ldm, cudaStream_t st) {
   ProfScope prof(kProfOther, st, 0);
-  relu_mask_kernel<<<grid_for(npix * C), 256, 0, st>>>(d, m, npix, C, ldd, ldm);
+  launch_k(relu_mask_kernel, grid_for(npix * C), 256, 0, st, d, m, npix, C, ldd, ldm);
   WC_LAUNCH_CHECK();
   return 0;
 }
 int compose_sep(const float* dw, const float* pw, const float* dwb, const float* pwb, float* w, float* bias, int Co, int Ci,
                 int KK, cudaStream_t st) {
-  compose_sep_kernel<<<grid_for(static_cast<size_t>(Co) * Ci * KK), 256, 0, st>>>(dw, pw, dwb, pwb, w, bias, Co, Ci, KK);
+  launch_k(compose_sep_kernel, grid_for(static_cast<size_t>(Co) * Ci * KK), 256, 0, st, dw, pw, dwb, pwb, w, bias, Co, Ci, KK);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -699,6 +716,7 @@ __global__ void __launch_bounds__(512, 1)
 srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ dw /*[64][81]*/,
                    const float* __restrict__ dwb, const float* __restrict__ pw /*[3][64]*/, const float* __restrict__ pwb,
                    float* __restrict__ y, int B, int H, int W, int ldx) {
+  pdl_prologue();
   extern __shared__ uint32_t sm[];
   uint32_t* tile = sm;                                            // [32][kFPlane] bf16x2
   float* wsm = reinterpret_cast<float*>(sm + 32 * kFPlane);       // [32][81][2]
@@ -785,6 +803,7 @@ srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
 }
 
 __global__ void gather_stride_kernel(const float* src, float* dst, int n, int mul, int off) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i * mul + off];
 }
@@ -801,7 +820,7 @@ int srgan_final(const __nv_bfloat16* x, const float* dw, const float* dwb, const
   }
   const int tiles = B * ((W + kFT_W - 1) / kFT_W) * ((H + kFT_H - 1) / kFT_H);
   ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * H * W * (128.0 + 12.0));
-  srgan_final_kernel<<<std::min(tiles, num_sms()), 512, smem, st>>>(x, dw, dwb, pw, pwb, y, B, H, W, ldx);
+  launch_k(srgan_final_kernel, std::min(tiles, num_sms()), 512, smem, st, x, dw, dwb, pw, pwb, y, B, H, W, ldx);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -814,6 +833,7 @@ __global__ void __launch_bounds__(kSI_T * kSI_T)
 srgan_initial_kernel(const float* __restrict__ x, const float* __restrict__ dw, const float* __restrict__ dwb,
                      const float* __restrict__ pw, const float* __restrict__ pwb, const float* __restrict__ slope,
                      __nv_bfloat16* __restrict__ y, int H, int W, int ldy) {
+  pdl_prologue();
   constexpr int HT = kSI_T + 8;
   __shared__ float tile[3][HT][HT + 1];
   __shared__ float s_dw[3][81], s_pw[64][3], s_b[64], s_sl[64], s_dwb[3];
@@ -863,13 +883,13 @@ int srgan_initial(const float* x, const float* dw, const float* dwb, const float
   WC_REQUIRE(ldy % 8 == 0, "output pixel stride must be a multiple of 8");
   ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * H * W * (3 * 4.0 + 64 * 2.0));
   dim3 grid((W + kSI_T - 1) / kSI_T, (H + kSI_T - 1) / kSI_T, B);
-  srgan_initial_kernel<<<grid, dim3(kSI_T, kSI_T), 0, st>>>(x, dw, dwb, pw, pwb, slope, y, H, W, ldy);
+  launch_k(srgan_initial_kernel, grid, dim3(kSI_T, kSI_T), 0, st, x, dw, dwb, pw, pwb, slope, y, H, W, ldy);
   WC_LAUNCH_CHECK();
   return 0;
 }
 
 int gather_stride(const float* src, float* dst, int n, int mul, int off, cudaStream_t st) {
-  gather_stride_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, dst, n, mul, off);
+  launch_k(gather_stride_kernel, (n + 255) / 256, 256, 0, st, src, dst, n, mul, off);
   WC_LAUNCH_CHECK();
   return 0;
 }

@@ -13,6 +13,7 @@ namespace {
 // loss = mean((pred - target)^2) (nn.MSELoss, train_ddpm.py:107); dpred = 2 (pred - target) / numel * grad_scale.
 __global__ void mse_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ dpred,
                                    size_t n, float gscale, double* __restrict__ part) {
+  pdl_prologue();
   __shared__ double sh[32];
   double acc = 0.0;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -30,6 +31,7 @@ __global__ void mse_partial_kernel(const float* __restrict__ pred, const float* 
   }
 }
 __global__ void mse_finish_kernel(const double* __restrict__ part, int nparts, size_t n, float* __restrict__ loss) {
+  pdl_prologue();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double s = 0.0;
     for (int i = 0; i < nparts; ++i) s += part[i];
@@ -50,6 +52,7 @@ constexpr int kBwTile = 64;  // pixels of one image row per tile
 __global__ void __launch_bounds__(kBwThreads)
 boundary_wgrad_kernel(const __nv_bfloat16* __restrict__ wide, int ldw, const float* __restrict__ narrow, int B, int H, int W,
                       int sign, float* __restrict__ part /*[blocks][64*28 + 4]*/) {
+  pdl_prologue();
   __shared__ float s_wide[kBwTile][65];
   __shared__ float s_nar[3][3][kBwTile + 2];
   __shared__ float red[kBwThreads / 64][64 * 28 + 4];
@@ -120,6 +123,7 @@ boundary_wgrad_kernel(const __nv_bfloat16* __restrict__ wide, int ldw, const flo
 
 __global__ void boundary_wgrad_finish_kernel(const float* __restrict__ part, int nblocks, int sign, float* __restrict__ dw,
                                              float* __restrict__ dbias) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 28 + 3) return;
   float s = 0.f;
@@ -140,6 +144,7 @@ __global__ void boundary_wgrad_finish_kernel(const float* __restrict__ part, int
 
 // w'[ci][co][ky][kx] = w[co][ci][2-ky][2-kx]: the conv_out data gradient as a 3 -> 64 convolution of dpred
 __global__ void flip_transpose_3x3_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int Ci) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Co * Ci * 9) return;
   const int tap = i % 9, ci = (i / 9) % Ci, co = i / (9 * Ci);
@@ -153,6 +158,7 @@ __global__ void temb_mlp_train_kernel(const long long* __restrict__ t, int dim, 
                                       const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                       float* __restrict__ emb_out, float* __restrict__ h1_out, float* __restrict__ temb,
                                       float* __restrict__ temb_silu) {
+  pdl_prologue();
   extern __shared__ float sh[];
   float* emb = sh;
   float* s1 = sh + dim;
@@ -188,6 +194,7 @@ __device__ __forceinline__ float silu_grad(float z) {
 // dtemb[b][k] = silu'(temb[b][k]) * sum_j dtproj[b][j] * Wcat[j][k]     (grid B, block dim threads)
 __global__ void temb_bwd_proj_kernel(const float* __restrict__ dtproj, int total, const float* __restrict__ wcat, int dim,
                                      const float* __restrict__ temb, float* __restrict__ dtemb) {
+  pdl_prologue();
   const int b = blockIdx.x, k = threadIdx.x;
   if (k >= dim) return;
   float acc = 0.f;
@@ -204,6 +211,7 @@ constexpr int kMaxLinSegs = 40;
 struct LinSegs { int n; LinSeg s[kMaxLinSegs]; };
 __global__ void linear_wgrad_rows_kernel(const float* __restrict__ dout, int ldd, const float* __restrict__ in, int dim, int B,
                                          const __grid_constant__ LinSegs segs) {
+  pdl_prologue();
   const int j = blockIdx.x, k = threadIdx.x;
   int si = 0;
   while (si + 1 < segs.n && j >= segs.s[si + 1].row0) ++si;
@@ -225,6 +233,7 @@ __global__ void linear_wgrad_rows_kernel(const float* __restrict__ dout, int ldd
 // ds1[b][k] = silu'(h1[b][k]) * sum_n dtemb[b][n] * W2[n][k]
 __global__ void temb_bwd_hidden_kernel(const float* __restrict__ dtemb, const float* __restrict__ w2, int dim,
                                        const float* __restrict__ h1, float* __restrict__ dh1) {
+  pdl_prologue();
   const int b = blockIdx.x, k = threadIdx.x;
   if (k >= dim) return;
   float acc = 0.f;
@@ -233,11 +242,13 @@ __global__ void temb_bwd_hidden_kernel(const float* __restrict__ dtemb, const fl
 }
 
 __global__ void silu_rows_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  pdl_prologue();
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i < n) { const float v = x[i]; y[i] = v / (1.f + expf(-v)); }
 }
 
 __global__ void add_vectors_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = a[i] + b[i];
 }
@@ -246,6 +257,7 @@ __global__ void add_vectors_kernel(const float* __restrict__ a, const float* __r
 // torch.optim.Adam(lr, betas, eps), no weight decay / amsgrad (train_ddpm.py:151): one launch over the flat buffers.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             size_t n, float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float gscale) {
+  pdl_prologue();
   const float step_size = lr / bc1;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float gr = g[i] * gscale;
@@ -262,6 +274,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // D[bh][tok] = sum_d dO[b][tok][h*hd+d] * O[b][tok][h*hd+d]  (the softmax-backward row term); one warp per (b, tok)
 __global__ void attn_rowdot_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int ldo, int ldd,
                                    int B, int ntok, int heads, int hd, float* __restrict__ D) {
+  pdl_prologue();
   const size_t row = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= static_cast<size_t>(B) * ntok) return;
@@ -287,9 +300,9 @@ int mse_loss_grad(const float* pred, const float* target, float* dpred, size_t n
   const int blocks = 1024;
   double* part = static_cast<double*>(scratch);
   ProfScope prof(kProfScheduler, st, 12.0 * n);
-  mse_partial_kernel<<<blocks, 256, 0, st>>>(pred, target, dpred, n, 2.0f * grad_scale / static_cast<float>(n), part);
+  launch_k(mse_partial_kernel, blocks, 256, 0, st, pred, target, dpred, n, 2.0f * grad_scale / static_cast<float>(n), part);
   WC_LAUNCH_CHECK();
-  mse_finish_kernel<<<1, 32, 0, st>>>(part, blocks, n, loss);
+  launch_k(mse_finish_kernel, 1, 32, 0, st, part, blocks, n, loss);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -301,28 +314,28 @@ int boundary_wgrad(const __nv_bfloat16* wide, int ldw, const float* narrow, int 
   const int blocks = 4 * 148;
   float* part = static_cast<float*>(scratch);
   ProfScope prof(kProfBoundaryConv, st, 2.0 * 27 * 64 * static_cast<double>(B) * H * W);
-  boundary_wgrad_kernel<<<blocks, kBwThreads, 0, st>>>(wide, ldw, narrow, B, H, W, sign, part);
+  launch_k(boundary_wgrad_kernel, blocks, kBwThreads, 0, st, wide, ldw, narrow, B, H, W, sign, part);
   WC_LAUNCH_CHECK();
-  boundary_wgrad_finish_kernel<<<(64 * 28 + 3 + 127) / 128, 128, 0, st>>>(part, blocks, sign, dw, dbias);
+  launch_k(boundary_wgrad_finish_kernel, (64 * 28 + 3 + 127) / 128, 128, 0, st, part, blocks, sign, dw, dbias);
   WC_LAUNCH_CHECK();
   return 0;
 }
 
 int add_vectors(const float* a, const float* b, float* o, int n, cudaStream_t st) {
-  add_vectors_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, o, n);
+  launch_k(add_vectors_kernel, (n + 255) / 256, 256, 0, st, a, b, o, n);
   WC_LAUNCH_CHECK();
   return 0;
 }
 
 int flip_transpose_3x3(const float* w, float* wt, int Co, int Ci, cudaStream_t st) {
-  flip_transpose_3x3_kernel<<<(Co * Ci * 9 + 127) / 128, 128, 0, st>>>(w, wt, Co, Ci);
+  launch_k(flip_transpose_3x3_kernel, (Co * Ci * 9 + 127) / 128, 128, 0, st, w, wt, Co, Ci);
   WC_LAUNCH_CHECK();
   return 0;
 }
 
 int temb_mlp_train(const long long* t, int Bt, int dim, const float* w1, const float* b1, const float* w2, const float* b2,
                    float* emb, float* h1, float* temb, float* temb_silu, cudaStream_t st) {
-  temb_mlp_train_kernel<<<Bt, 128, 2 * dim * sizeof(float), st>>>(t, dim, time_factor_table(dim / 2), w1, b1, w2, b2, emb, h1, temb, temb_silu);
+  launch_k(temb_mlp_train_kernel, Bt, 128, 2 * dim * sizeof(float), st, t, dim, time_factor_table(dim / 2), w1, b1, w2, b2, emb, h1, temb, temb_silu);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -340,22 +353,22 @@ int temb_backward(const float* dtproj, int total, int B, int dim, const float* w
   LinSegs segs;
   segs.n = nsegs;
   for (int i = 0; i < nsegs; ++i) segs.s[i] = {seg_row0[i], seg_rows[i], seg_dw[i], seg_db[i]};
-  linear_wgrad_rows_kernel<<<total, dim, 0, st>>>(dtproj, total, temb_silu, dim, B, segs);
+  launch_k(linear_wgrad_rows_kernel, total, dim, 0, st, dtproj, total, temb_silu, dim, B, segs);
   WC_LAUNCH_CHECK();
-  temb_bwd_proj_kernel<<<B, dim, 0, st>>>(dtproj, total, wcat, dim, temb, dtemb);
+  launch_k(temb_bwd_proj_kernel, B, dim, 0, st, dtproj, total, wcat, dim, temb, dtemb);
   WC_LAUNCH_CHECK();
   const size_t n = static_cast<size_t>(B) * dim;
-  silu_rows_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, st>>>(h1, s1, n);
+  launch_k(silu_rows_kernel, static_cast<int>((n + 255) / 256), 256, 0, st, h1, s1, n);
   WC_LAUNCH_CHECK();
   LinSegs one;
   one.n = 1;
   one.s[0] = {0, dim, dw2, db2};
-  linear_wgrad_rows_kernel<<<dim, dim, 0, st>>>(dtemb, dim, s1, dim, B, one);
+  launch_k(linear_wgrad_rows_kernel, dim, dim, 0, st, dtemb, dim, s1, dim, B, one);
   WC_LAUNCH_CHECK();
-  temb_bwd_hidden_kernel<<<B, dim, 0, st>>>(dtemb, w2, dim, h1, dh1);
+  launch_k(temb_bwd_hidden_kernel, B, dim, 0, st, dtemb, w2, dim, h1, dh1);
   WC_LAUNCH_CHECK();
   one.s[0] = {0, dim, dw1, db1};
-  linear_wgrad_rows_kernel<<<dim, dim, 0, st>>>(dh1, dim, emb, dim, B, one);
+  launch_k(linear_wgrad_rows_kernel, dim, dim, 0, st, dh1, dim, emb, dim, B, one);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -365,7 +378,7 @@ int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, 
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   ProfScope prof(kProfScheduler, st, 28.0 * n);
-  adam_kernel<<<4 * num_sms(), 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, static_cast<float>(bc1),
+  launch_k(adam_kernel, 4 * num_sms(), 256, 0, st, p, g, m, v, n, lr, beta1, beta2, eps, static_cast<float>(bc1),
                                              static_cast<float>(sqrt(bc2)), grad_scale);
   WC_LAUNCH_CHECK();
   return 0;
@@ -376,7 +389,7 @@ int attn_rowdot(const __nv_bfloat16* o, const __nv_bfloat16* d_o, int ldo, int l
   WC_REQUIRE(hd % 2 == 0, "attn_rowdot: head_dim must be even");
   const size_t rows = static_cast<size_t>(B) * ntok;
   ProfScope prof(kProfOther, st, 4.0 * rows * heads * hd);
-  attn_rowdot_kernel<<<static_cast<int>((rows * 32 + 255) / 256), 256, 0, st>>>(o, d_o, ldo, ldd, B, ntok, heads, hd, D);
+  launch_k(attn_rowdot_kernel, static_cast<int>((rows * 32 + 255) / 256), 256, 0, st, o, d_o, ldo, ldd, B, ntok, heads, hd, D);
   WC_LAUNCH_CHECK();
   return 0;
 }

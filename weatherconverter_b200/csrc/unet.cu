@@ -36,6 +36,7 @@ int linear_rows(const float* in, int Bt, int dim, const float* w, const float* b
 namespace {
 
 __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = a[i] + b[i];
 }
@@ -172,7 +173,7 @@ struct Builder {
       const float* b2 = P(p + ".resnet_conv_second." + ls + ".2.bias");
       const float* br = P(p + ".residual_input_conv." + ls + ".bias");
       if (!bsum || err) { if (!err) err = 1; return out; }
-      add_vec_kernel<<<(cout + 255) / 256, 256, 0, st>>>(b2, br, bsum, cout);
+      launch_k(add_vec_kernel, (cout + 255) / 256, 256, 0, st, b2, br, bsum, cout);
     }
     conv(a2, p + ".resnet_conv_second." + ls + ".2", cout, 3, 1, 1, bsum, nullptr, 0, nullptr, &x,
          p + ".residual_input_conv." + ls, out);

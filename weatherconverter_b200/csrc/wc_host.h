@@ -56,6 +56,37 @@ struct ProfScope {
 
 int num_sms();
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------------
+// Every kernel of the library is launched through launch_k with cudaLaunchAttributeProgrammaticStreamSerialization set (unless
+// WC_PDL=0): the kernel may then be scheduled while its predecessor in the stream is still draining, and its set-up (block
+// scheduling, shared-memory carve-up, mbarrier init, TMEM allocation, tensor-map prefetch) overlaps the predecessor's tail.
+// Contract: a kernel launched this way executes pdl_prologue() / pdl_wait() (griddepcontrol.wait) BEFORE its first access to
+// global memory that any earlier kernel may write or still read; griddepcontrol.launch_dependents lets its own successor in.
+// A step is ~440 back-to-back launches (~520 at batch 1), so the per-launch gap is what the small-batch regime is made of.
+bool pdl_enabled(int klass = 0);   // klass 0: light kernels (no TMEM / full-SM shared memory); 1: tcgen05 kernels (one CTA per SM)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+template <int KLASS = 0, typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(KLASS) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Time-embedding factor table (unet_base.py:22-24: 10000 ** (arange(half) / half), fp32): the host evaluates the reference's
 // torch expression once and hands the table over, so the embedding's argument t / factor is bit-identical to the reference's.
 // time_factor_table(half) returns the device copy for the current device, or nullptr (the kernels then use powf).

@@ -76,6 +76,8 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ Wgr
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();   // programmatic dependent launch: the set-up above overlaps the previous kernel's tail
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -210,6 +212,7 @@ wgrad_kernel(const __grid_constant__ WgradMaps maps, const __grid_constant__ Wgr
 
 // Sum the split partials in a fixed order and scatter into the PyTorch weight-gradient layout.
 __global__ void wgrad_unpack_kernel(const __grid_constant__ WgradUnpackArgs p) {
+  pdl_prologue();
   const size_t total = static_cast<size_t>(p.N) * p.ktot;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -376,13 +379,13 @@ int wgrad_launch(const WgradPlan& plan, cudaStream_t st) {
   {
     ProfScope prof(kProfIgemm, st, plan.flops);
     prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.ktot, plan.args.nsplit, 1000 + plan.args.ntaps, plan.grid);
-    wgrad_kernel<<<plan.grid, kThreads, kSmemBytes, st>>>(plan.maps, plan.args);
+    launch_k<1>(wgrad_kernel, plan.grid, kThreads, kSmemBytes, st, plan.maps, plan.args);
     WC_LAUNCH_CHECK();
   }
   const size_t total = static_cast<size_t>(plan.unpack.N) * plan.unpack.ktot;
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 4096));
   ProfScope prof(kProfOther, st, 0);
-  wgrad_unpack_kernel<<<blocks, 256, 0, st>>>(plan.unpack);
+  launch_k(wgrad_unpack_kernel, blocks, 256, 0, st, plan.unpack);
   WC_LAUNCH_CHECK();
   return 0;
 }
