@@ -32,6 +32,12 @@ groups = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for r in rows:
     key = (r[3], r[4], r[5], r[6], r[7])
     g = groups[key]; g[0] += 1; g[1] += r[1]; g[2] += r[9]
-print(f"{'us':>9} {'share':>6} {'n':>3} {'TF/s':>6}  M N K BN taps")
-for key, g in sorted(groups.items(), key=lambda kv: -kv[1][1])[:45]:
-    print(f"{g[1]:9.1f} {100*g[1]/tot:5.1f}% {g[0]:3d} {g[2]/g[1]*1e3:6.0f}  {key}")
+print(f"{'us':>9} {'share':>6} {'n':>3} {'TF/s':>6} {'floor us':>9} {'x floor':>7}  M N K BN taps   (floor = max(FLOPs / 1370 TF/s, bytes / 6553 GB/s) per launch)")
+fl_tot = 0.0
+for key, g in sorted(groups.items(), key=lambda kv: -kv[1][1])[:60]:
+    M, N, K, BN, taps = key
+    t = max(1, taps % 100)
+    fl = max(g[2] / g[0] * 1e9 / 1370e12, 2.0 * (M * K / t + N * K + M * N) / 6553e9) * 1e6 * g[0]
+    fl_tot += fl
+    print(f"{g[1]:9.1f} {100*g[1]/tot:5.1f}% {g[0]:3d} {g[2]/g[1]*1e3:6.0f} {fl:9.1f} {g[1]/fl:7.2f}  {key}")
+print(f"sum of floors (listed): {fl_tot/1e3:.2f} ms")

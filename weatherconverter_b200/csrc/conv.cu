@@ -228,7 +228,16 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   if (int e = finish_plan(&plan, arena, taps, B, H, W, tb, th, tw, N, ep, out, out.up, out.up, out.py, out.px, st)) return e;
   plan.args.row3 = (want_row3 && plan.args.BN <= 128) ? row3_mode() : 0;
   plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3);
-  plan.args.tma_res = (plan.args.tma_res == 2 && igemm_res_staging_fits(plan.args.BN, plan.args.row3, plan.args.nstages)) ? 1 : 0;
+  plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, plan.args.row3, plan.args.nstages) ? 1 : 0;
+  plan.args.tma_res = (plan.args.tma_res == 2 && plan.args.stage2) ? 1 : 0;
+  {
+    static int lean = -1;   // WC_IGEMM_LEAN=0: previous epilogue everywhere
+    if (lean < 0) {
+      const char* e = getenv("WC_IGEMM_LEAN");
+      lean = e ? atoi(e) : 1;
+    }
+    plan.args.lean = (lean && plan.args.tma_store && !plan.args.mask && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
+  }
   { const char* e = getenv("WC_IGEMM_DBG"); plan.args.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("WC_IGEMM_TRACE"); plan.args.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   op->flops = plan.flops;

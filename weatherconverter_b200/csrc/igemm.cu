@@ -237,7 +237,130 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
   }
 }
 
-template <bool ROW3, bool TMA_OUT, bool TMA_RES>
+
+// Lean epilogue of one accumulator tile for the common case: bf16 NHWC output through TMA, optional residual through TMA, no
+// ReLU-mask input.  Compared with epilogue_tile it has no per-lane global accesses, no look-ahead register arrays and every
+// mode decision is a compile-time or tile-uniform choice; ncu on the 1x1 64->256 layer (profiles/r2_ncu_igemm_1x1_64_256_generic.txt)
+// showed the generic version executing 320 warp instructions per 32-channel chunk, a quarter of them register moves.
+// Staging: every epilogue warp owns two 2 KiB buffers (nbuf == 2 when the ring leaves 16 KiB free) and alternates between them
+// chunk by chunk (ectr counts this warp's chunks across tiles): the TMA store of chunk i reads buffer i & 1 while chunk i + 1 is
+// staged in the other one.  With a residual the box of chunk i is loaded by TMA INTO the buffer chunk i will be stored from; each
+// lane reads its row, adds, and writes the bf16 result back in place.
+template <int NC, bool RES>
+__device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t tacc, int n0, int b, int grp, const float* s_bias,
+                                                   const float* s_prelu, uint32_t tfull_addr, uint32_t tfull_parity,
+                                                   const CUtensorMap* cmap, const CUtensorMap* rmap, uint32_t buf0, uint32_t buf1,
+                                                   int nbuf, int qx, int qy, int qb0, uint32_t res_bar, uint32_t& res_phase,
+                                                   uint32_t& ectr) {
+  constexpr int NV = NC / 8;
+  const int lane = threadIdx.x & 31;
+  const uint32_t sw = NC == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+  const uint32_t row_off = static_cast<uint32_t>(lane) * (NC * 2);
+  auto buf_of = [&](uint32_t i) { return ((i & 1u) && nbuf == 2) ? buf1 : buf0; };
+  auto request = [&](uint32_t i, int nb) {   // residual box of chunk i (channels nb ..) -> its staging buffer
+    if (lane == 0) {
+      tma_store_wait_read<0>();              // the store that last used this buffer (chunk i - 2) has finished reading it
+      mbar_arrive_expect_tx(res_bar, NC * 2 * 32);
+      tma_load_4d(buf_of(i), rmap, res_bar, nb, qx, qy, qb0);
+    }
+  };
+  const int c_first = grp * NC;
+  if (RES && c_first < p.BN && n0 + c_first < p.N) request(ectr, n0 + c_first);   // before the accumulator is ready: overlaps the main loop
+  mbar_wait(tfull_addr, tfull_parity);
+  tc_fence_after();
+  const float* rb = p.rowbias ? p.rowbias + static_cast<size_t>(b < p.B ? b : p.B - 1) * p.ldrb : nullptr;
+  for (int c0 = c_first; c0 < p.BN; c0 += 2 * NC) {
+    const int nb = n0 + c0;
+    if (nb >= p.N) break;  // warp-uniform
+    uint32_t r[NC];
+    tmem_ld_n<NC>(tacc + c0, r);
+    const uint32_t mine = buf_of(ectr) + row_off;
+    uint4 rr[NV];
+    if (RES) {
+      mbar_wait(res_bar, res_phase);
+      res_phase ^= 1u;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[j].x), "=r"(rr[j].y), "=r"(rr[j].z), "=r"(rr[j].w)
+                     : "r"(mine + ((static_cast<uint32_t>(j) ^ sw) << 4)) : "memory");
+      // the next box goes into the OTHER buffer (last touched, through the generic proxy, one chunk ago and fenced then)
+      if (c0 + 2 * NC < p.BN && nb + 2 * NC < p.N) request(ectr + 1, nb + 2 * NC);
+    }
+    tmem_wait_ld();
+    float v[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
+    if (s_bias) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        const float4 bv = *reinterpret_cast<const float4*>(s_bias + nb + j);
+        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+      }
+    } else if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+      }
+    }
+    if (rb) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + nb + j));
+        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+      }
+    }
+    if (RES) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float2 f0 = unpack_bf16(rr[j].x), f1 = unpack_bf16(rr[j].y), f2 = unpack_bf16(rr[j].z), f3 = unpack_bf16(rr[j].w);
+        v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
+        v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.act == 2) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+    } else if (p.act == 3) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) v[j] = 0.5f * v[j] * (1.f + erff(v[j] * 0.70710678118654752f));
+    }
+    if (p.prelu) {
+#pragma unroll
+      for (int j = 0; j < NC; j += 4) {
+        const float4 sv = s_prelu ? *reinterpret_cast<const float4*>(s_prelu + nb + j)
+                                  : __ldg(reinterpret_cast<const float4*>(p.prelu + nb + j));
+        v[j] = v[j] > 0.f ? v[j] : v[j] * sv.x; v[j + 1] = v[j + 1] > 0.f ? v[j + 1] : v[j + 1] * sv.y;
+        v[j + 2] = v[j + 2] > 0.f ? v[j + 2] : v[j + 2] * sv.z; v[j + 3] = v[j + 3] > 0.f ? v[j + 3] : v[j + 3] * sv.w;
+      }
+    }
+    if (!RES) {   // the store that last read this buffer (two chunks ago with two buffers, the previous one otherwise)
+      if (lane == 0) {
+        if (nbuf == 2) tma_store_wait_read<1>();
+        else tma_store_wait_read<0>();
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(mine + ((static_cast<uint32_t>(j) ^ sw) << 4)),
+                   "r"(pack_bf16(v[8 * j + 0], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
+                   "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7])) : "memory");
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(cmap, buf_of(ectr), nb, qx, qy, qb0);
+      tma_store_commit();
+    }
+    ++ectr;
+  }
+}
+
+template <bool ROW3, bool TMA_OUT, bool TMA_RES, bool LEAN = false>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -450,6 +573,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const uint32_t res_stage = smem_base + kPipeBytes - kOutStageBytes + static_cast<uint32_t>(warp - 2) * 2048u;
     const uint32_t res_bar = bar_base + 8u * (2 * kMaxStages + 5 + (warp - 2));
     uint32_t res_phase = 0;
+    uint32_t ectr = 0;     // lean epilogue: this warp's running chunk count (selects the staging buffer)
     const int q_pix = quad * 32;
     const int qx0 = q_pix % p.tw, qy0 = (q_pix / p.tw) % p.th, qb0 = q_pix / (p.tw * p.th);
     const int bb = row / (p.th * p.tw), rem = row % (p.th * p.tw), yy = rem / p.tw, xx = rem % p.tw;
@@ -463,7 +587,14 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       const bool valid = (b < p.B) && (y < p.H) && (x < p.W);
       const uint32_t tacc = tmem_base + static_cast<uint32_t>(a) * 256u + (static_cast<uint32_t>(quad * 32) << 16);
       if (warp == 2 && lane == 0) trace(2, 20);
-      if (p.out_mode != kOutQKV && (p.BN % 32 == 0) && (p.N % 32 == 0))
+      if (LEAN) {
+        if ((p.BN % 32 == 0) && (p.N % 32 == 0))
+          epilogue_tile_lean<32, TMA_RES>(p, tacc, n0, b, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
+                                          p.stage2 ? 2 : 1, x0 + qx0, y0 + qy0, b0 + qb0, res_bar, res_phase, ectr);
+        else
+          epilogue_tile_lean<16, TMA_RES>(p, tacc, n0, b, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
+                                          p.stage2 ? 2 : 1, x0 + qx0, y0 + qy0, b0 + qb0, res_bar, res_phase, ectr);
+      } else if (p.out_mode != kOutQKV && (p.BN % 32 == 0) && (p.N % 32 == 0))
         epilogue_tile<32, TMA_OUT, TMA_RES>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, out_stage, x0 + qx0,
                           y0 + qy0, b0 + qb0, &maps.r, res_stage, res_bar, res_phase);
       else
@@ -497,14 +628,14 @@ bool igemm_res_staging_fits(int BN, int row3, int nstages) {
   return static_cast<uint32_t>(nstages) * stage + kOutStageBytes <= kPipeBytes;
 }
 
-template <bool ROW3, bool TMA_OUT, bool TMA_RES>
+template <bool ROW3, bool TMA_OUT, bool TMA_RES, bool LEAN = false>
 static int launch_variant(const IgemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<ROW3, TMA_OUT, TMA_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<ROW3, TMA_OUT, TMA_RES, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  launch_k<1>(igemm_kernel<ROW3, TMA_OUT, TMA_RES>, plan.grid, kThreads, kSmemBytes, stream, plan.maps, plan.args);
+  launch_k<1>(igemm_kernel<ROW3, TMA_OUT, TMA_RES, LEAN>, plan.grid, kThreads, kSmemBytes, stream, plan.maps, plan.args);
   return 0;
 }
 
@@ -513,7 +644,10 @@ int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
   prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.total_kb * kIgemmBK, plan.args.BN, plan.args.ntaps + 100 * plan.args.row3, plan.grid);
   const int variant = plan.args.tma_store ? (plan.args.tma_res ? 2 : 1) : 0;   // epilogue: per-lane stores / TMA store / TMA store + TMA residual
   int e = 0;
-  if (plan.args.row3) e = variant == 2 ? launch_variant<true, true, true>(plan, stream) : variant == 1 ? launch_variant<true, true, false>(plan, stream) : launch_variant<true, false, false>(plan, stream);
+  if (plan.args.lean) {
+    if (plan.args.row3) e = plan.args.tma_res ? launch_variant<true, true, true, true>(plan, stream) : launch_variant<true, true, false, true>(plan, stream);
+    else e = plan.args.tma_res ? launch_variant<false, true, true, true>(plan, stream) : launch_variant<false, true, false, true>(plan, stream);
+  } else if (plan.args.row3) e = variant == 2 ? launch_variant<true, true, true>(plan, stream) : variant == 1 ? launch_variant<true, true, false>(plan, stream) : launch_variant<true, false, false>(plan, stream);
   else e = variant == 2 ? launch_variant<false, true, true>(plan, stream) : variant == 1 ? launch_variant<false, true, false>(plan, stream) : launch_variant<false, false, false>(plan, stream);
   if (e) return e;
   WC_LAUNCH_CHECK();

@@ -67,6 +67,9 @@ struct IgemmArgs {
   // residual through TMA as well (tma_res == 1): needs tma_store and 16 KiB of the ring area free behind the last stage; every
   // epilogue warp loads the (NC, qw, qh, qb) box of its next chunk with IgemmMaps::r and reads its own row from shared memory
   int tma_res;
+  // lean epilogue (igemm.cu: epilogue_tile_lean): TMA store, no ReLU-mask input, residual (if any) through TMA; stage2 = the ring
+  // leaves 16 KiB free, i.e. every epilogue warp owns TWO 2 KiB staging buffers and alternates between them
+  int lean, stage2;
 };
 
 struct IgemmMaps {
