@@ -90,7 +90,13 @@ def block_plan(backbone="resnet50"):
 def deeplab_forward(sd, x, backbone="resnet50", taps=None):
     """x [B,3,H,W] -> logits [B,nc,H,W]."""
     H, W = x.shape[-2:]
-    h = _q(F.relu(_bn(sd, "backbone.bn1", F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=3))))  # fp32 weights in both
+    if EMULATE == "bf16":
+        # the CUDA stem runs on the tensor core (csrc/conv.cu: build_conv_stem7s2): image and BN-folded weights in bf16, fp32
+        # accumulation; the gradient w.r.t. the image stays fp32 (straight-through on the input rounding)
+        xq = x + (x.to(torch.bfloat16).float() - x).detach()
+        h = _q(F.relu(_cb(sd, "backbone.conv1", "backbone.bn1", xq, stride=2, padding=3)))
+    else:
+        h = _q(F.relu(_bn(sd, "backbone.bn1", F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=3))))
     h = F.max_pool2d(h, 3, 2, 1)
     low = None
     for (p, _, _, stride, dil, has_down) in block_plan(backbone):

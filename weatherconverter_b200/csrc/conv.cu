@@ -244,6 +244,45 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   return 0;
 }
 
+// 7x7 / stride 2 / pad 3 convolution of a 3-channel image (ResNet stem, resnet.py:142) on the tensor core.  The image is first
+// re-laid as NHWC bf16 with 8 channels (3 real) and 4 zero columns on either side: then the 7 taps of one kernel ROW are 56
+// CONTIGUOUS elements, and a tensor map whose x stride (16 elements = one stride-2 step) is smaller than its 64-element inner
+// box yields, for 128 output pixels, the im2col rows of that kernel row directly in the canonical K-major layout - an implicit
+// im2col with overlapping boxes, no gather kernel.  K = 7 kernel rows x 64 (147 real), weights re-laid to match (wprime
+// [N][64][7]: element kx*8 + c of kernel row ky).  Input rows alternate between two phase views (stride 2 in y).
+int build_conv_stem7s2(ConvOp* op, DeviceArena* arena, const __nv_bfloat16* xp, int B, int H, int W, const float* wprime,
+                       const float* scale, int N, const Epilogue& ep, const OutSpec& out, cudaStream_t st) {
+  WC_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem: even image dims");
+  op->plans.clear();
+  op->plans.emplace_back();
+  IgemmPlan& plan = op->plans.back();
+  const int Ho = H / 2, Wo = W / 2, Wp = W + 8;
+  int tb, th, tw;
+  igemm_pick_tile(B, Ho, Wo, &tb, &th, &tw);
+  for (int ph = 0; ph < 2; ++ph) {
+    uint64_t dims[4] = {64, static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho), static_cast<uint64_t>(B)};
+    uint64_t strides[4] = {1, 16, static_cast<uint64_t>(2) * Wp * 8, static_cast<uint64_t>(H) * Wp * 8};
+    uint32_t box[4] = {64, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), static_cast<uint32_t>(tb)};
+    if (int e = encode_tmap_bf16(&plan.maps.a[ph], xp + (static_cast<size_t>(ph) * Wp + 1) * 8, 4, dims, strides, box, 128)) return e;
+  }
+  for (int i = 2; i < kMaxMaps; ++i) plan.maps.a[i] = plan.maps.a[0];
+  WeightSrc w; w.w = wprime; w.d0 = N; w.d1 = 64; w.KH = 7; w.KW = 1; w.scale = scale;
+  std::vector<TapDef> taps;
+  for (int ky = 0; ky < 7; ++ky) {
+    const int o = ky - 3, dy = (o >= 0) ? o / 2 : -((-o + 1) / 2), ph = o - 2 * dy;   // o = 2 dy + ph, ph in {0, 1}
+    taps.push_back({ph, dy, 0, &w, ky, 0, 64});
+  }
+  if (int e = finish_plan(&plan, arena, taps, B, Ho, Wo, tb, th, tw, N, ep, out, 1, 1, 0, 0, st)) return e;
+  plan.args.row3 = 0;
+  plan.args.nstages = igemm_stages_for(plan.args.BN, 0);
+  plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, 0, plan.args.nstages) ? 1 : 0;
+  plan.args.tma_res = 0;
+  plan.args.lean = (plan.args.tma_store && !plan.args.mask && !plan.args.res) ? 1 : 0;
+  plan.flops = 2.0 * 147.0 * N * static_cast<double>(B) * Ho * Wo;   // algorithmic (the reference's 7x7x3 taps), not the padded K
+  op->flops = plan.flops;
+  return 0;
+}
+
 int build_conv_transposed_s2(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w, int K, int pad, int N,
                              const Epilogue& ep, const OutSpec& out, cudaStream_t st) {
   WC_REQUIRE(w.transpose == 1, "transposed conv expects a [Cin][Cout][K][K] weight view");

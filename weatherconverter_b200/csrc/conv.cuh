@@ -77,6 +77,13 @@ struct ConvOp {
 int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w, const ConvGeom& g, int N,
                const Act* x2, const WeightSrc* w2, const Epilogue& ep, const OutSpec& out, cudaStream_t st);
 
+// ResNet stem (7x7, stride 2, pad 3, 3 input channels) as an implicit GEMM over a padded NHWC-8 copy of the image (see conv.cu).
+// xp: [B][H][W+8][8] bf16 made by stem_prepare(); wprime: [N][64][7] fp32 made by stem_weights().
+int build_conv_stem7s2(ConvOp* op, DeviceArena* arena, const __nv_bfloat16* xp, int B, int H, int W, const float* wprime,
+                       const float* scale, int N, const Epilogue& ep, const OutSpec& out, cudaStream_t st);
+int stem_prepare(const float* x_nchw, __nv_bfloat16* xp, int B, int H, int W, cudaStream_t st);
+int stem_weights(const float* w /*[N][3][7][7]*/, float* wprime /*[N][64][7]*/, int N, cudaStream_t st);
+
 // Transposed convolution with stride 2 (ConvTranspose2d(k, 2, pad), output exactly 2x) or, equivalently, the
 // data gradient of a stride-2 convolution: out[2j+q] = sum_{k = (q+pad) mod 2 ...} in[j + (q+pad-k)/2] * W[k].
 // Weight source must have transpose = 1 semantics (out-channel = dim1).

@@ -382,6 +382,47 @@ int conv_small_cout(const __nv_bfloat16* x, const float* w, const float* bias, f
   return 0;
 }
 
+// ---- ResNet stem on the tensor core (conv.cu: build_conv_stem7s2): input re-layout and weight re-layout
+__global__ void stem_prepare_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, int B, int H, int W) {
+  pdl_prologue();
+  const int Wp = W + 8;
+  const size_t total = static_cast<size_t>(B) * H * Wp;
+  const size_t plane = static_cast<size_t>(H) * W;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int xq = static_cast<int>(i % Wp) - 4;
+    const size_t by = i / Wp;
+    const int y = static_cast<int>(by % H);
+    const size_t b = by / H;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (xq >= 0 && xq < W) {
+      const float* src = x + (b * 3) * plane + static_cast<size_t>(y) * W + xq;
+      u.x = pack_bf16(__ldg(src), __ldg(src + plane));
+      u.y = pack_bf16(__ldg(src + 2 * plane), 0.f);
+    }
+    *reinterpret_cast<uint4*>(xp + i * 8) = u;
+  }
+}
+__global__ void stem_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int N) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [N][64][7]
+  if (i >= N * 64 * 7) return;
+  const int ky = i % 7, e = (i / 7) % 64, n = i / (7 * 64);
+  const int kx = e / 8, c = e % 8;
+  wp[i] = (kx < 7 && c < 3) ? w[((n * 3 + c) * 7 + ky) * 7 + kx] : 0.f;
+}
+int stem_prepare(const float* x_nchw, __nv_bfloat16* xp, int B, int H, int W, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(B) * H * (W + 8);
+  ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * H * (12.0 * W + 16.0 * (W + 8)));
+  launch_k(stem_prepare_kernel, grid_for(total), 256, 0, st, x_nchw, xp, B, H, W);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int stem_weights(const float* w, float* wprime, int N, cudaStream_t st) {
+  launch_k(stem_weights_kernel, (N * 64 * 7 + 255) / 256, 256, 0, st, w, wprime, N);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+
 int temb_mlp(const long long* t, int Bt, int dim, const float* w1, const float* b1, const float* w2, const float* b2,
              float* temb, float* temb_silu, cudaStream_t st) {
   launch_k(temb_mlp_kernel, Bt, 128, 2 * dim * sizeof(float), st, t, dim, time_factor_table(dim / 2), w1, b1, w2, b2, temb, temb_silu);
