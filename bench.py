@@ -522,7 +522,7 @@ def class_floors(records, peaks, sm_mhz, sms=148):
         d["measured_ms"] += ms
         d["launches"] += 1
         if cls == 0:
-            M, N, K, taps = info[0], info[1], info[2], max(1, info[4] % 100)
+            M, N, K, taps = info[0], info[1], info[2], max(1, info[4] % 100)   # info[4] also carries epilogue flags in its thousands
             t_t, t_h = work / tf * 1e3, 2.0 * (M * (K / taps) + N * K + M * N) / hbm * 1e3
             d["tensor_ms"] += t_t; d["hbm_ms"] += t_h; d["floor_ms"] += max(t_t, t_h)
         elif cls == 1:

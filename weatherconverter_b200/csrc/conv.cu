@@ -227,8 +227,23 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   }
   if (int e = finish_plan(&plan, arena, taps, B, H, W, tb, th, tw, N, ep, out, out.up, out.up, out.py, out.px, st)) return e;
   plan.args.row3 = (want_row3 && plan.args.BN <= 128) ? row3_mode() : 0;
-  plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3);
-  plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, plan.args.row3, plan.args.nstages) ? 1 : 0;
+  int wres_bytes = 0;
+  {
+    // resident weights: one N tile, the packed matrix fits next to a useful ring, and every CTA processes several tiles
+    static int wres = -1;   // WC_IGEMM_WRES=0: weights stream through the ring with the activations (round-1 behaviour)
+    if (wres < 0) {
+      const char* e = getenv("WC_IGEMM_WRES");
+      wres = e ? atoi(e) : 1;
+    }
+    const long wb = static_cast<long>(plan.args.BN) * plan.args.total_kb * kIgemmBK * 2;
+    const long m_tiles = (static_cast<long>(B) * H * W + kIgemmBM - 1) / kIgemmBM;
+    if (wres && plan.args.BN >= N && wb <= kIgemmWresMaxBytes && m_tiles >= 2 * num_sms()) {
+      plan.args.wres = 1;
+      wres_bytes = static_cast<int>(wb);
+    }
+  }
+  plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3, wres_bytes);
+  plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, plan.args.row3, plan.args.nstages, wres_bytes) ? 1 : 0;
   plan.args.tma_res = (plan.args.tma_res == 2 && plan.args.stage2) ? 1 : 0;
   {
     static int lean = -1;   // WC_IGEMM_LEAN=0: previous epilogue everywhere

@@ -368,14 +368,17 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   // flight per SM (these layers are TMA-latency bound, not tensor bound).
   constexpr uint32_t kAOff = ROW3 ? kRowABytes : kABytes;   // offset of the B tile(s) inside a stage
   const int kStages = p.nstages;
-  const uint32_t kStageSz = kAOff + (ROW3 ? 3u : 1u) * static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
+  const uint32_t kBTile = static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
+  const uint32_t kStageSz = kAOff + (p.wres ? 0u : (ROW3 ? 3u : 1u) * kBTile);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t wres_base = smem_base + static_cast<uint32_t>(kStages) * kStageSz;   // resident weights sit right behind the ring
   const uint32_t bar_base = smem_base + kPipeBytes + kOutStageBytes;   // [ring | output staging | barriers | bias / PReLU]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t wfull_bar = bar_base + 8u * (2 * kMaxStages + 13);   // resident weights have landed
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -407,6 +410,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         mbar_init(tempty_bar(a), 256);
       }
       for (int w = 0; w < 8; ++w) mbar_init(bar_base + 8u * (2 * kMaxStages + 5 + w), 1);   // residual boxes (tma_res)
+      mbar_init(wfull_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -452,7 +456,14 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kABytes + static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
+      const uint32_t tx_bytes = kABytes + (p.wres ? 0u : kBTile);
+      if (p.wres) {   // the whole weight matrix, once: total_kb tiles of BN x 64 (n_tiles == 1)
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(wfull_bar, static_cast<uint32_t>(p.total_kb) * kBTile);
+          for (int kb = 0; kb < p.total_kb; ++kb) tma_load_2d(wres_base + kb * kBTile, &maps.b, wfull_bar, kb * kIgemmBK, 0);
+        }
+        __syncwarp();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n0, b0, y0, x0;
         decode(tile, n0, b0, y0, x0);
@@ -468,9 +479,9 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
               if (elect_one_sync()) {
                 trace(0, 1);
                 const uint32_t sa = smem_base + stage * kStageSz;
-                mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0u : kRowSegPixels * 128u) + ((p.dbg & 4) ? 0u : 3u * b_bytes));
+                mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0u : kRowSegPixels * 128u) + (((p.dbg & 4) || p.wres) ? 0u : 3u * b_bytes));
                 if (!(p.dbg & 8)) tma_load_4d(sa, &maps.a[2], full_bar(stage), kb * kIgemmBK, x0 - 1, y0 + ky - 1, b0);
-                for (int kx = 0; kx < 3 && !(p.dbg & 4); ++kx)
+                for (int kx = 0; kx < 3 && !(p.dbg & 4) && !p.wres; ++kx)
                   tma_load_2d(sa + kAOff + kx * b_bytes, &maps.b, full_bar(stage), ((ky * 3 + kx) * nkb + kb) * kIgemmBK, n0);
                 trace(0, 2);
               }
@@ -489,7 +500,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
               const uint32_t sa = smem_base + stage * kStageSz;
               mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
               tma_load_4d(sa, amap, full_bar(stage), kb * kIgemmBK, x0 + tap.dx, y0 + tap.dy, b0);
-              tma_load_2d(sa + kAOff, &maps.b, full_bar(stage), kb_global * kIgemmBK, n0);
+              if (!p.wres) tma_load_2d(sa + kAOff, &maps.b, full_bar(stage), kb_global * kIgemmBK, n0);
             }
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -505,10 +516,12 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       // descriptor pieces (see umma_desc_join): constant high word, low words for stage 0, per-stage increment
       const uint64_t d0 = umma_smem_desc(smem_base, 128, 1024);
       const uint32_t dhi = umma_desc_hi(d0), a_lo0 = umma_desc_lo(d0), b_lo0 = a_lo0 + (kAOff >> 4);
-      const uint32_t stage16 = kStageSz >> 4, bt16 = (static_cast<uint32_t>(p.BN) * kIgemmBK * 2) >> 4;
+      const uint32_t stage16 = kStageSz >> 4, bt16 = kBTile >> 4;
+      const uint32_t w_lo0 = a_lo0 + ((wres_base - smem_base) >> 4);   // resident weights: descriptor start of k-block 0
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      if (p.wres) mbar_wait(wfull_bar, 0);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int a = it & 1;
         const uint32_t aphase = (it >> 1) & 1u;
@@ -523,7 +536,11 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             tc_fence_after();
             if (elect_one_sync()) {
               trace(1, 11);
-              const uint32_t a_lo = a_lo0 + stage * stage16, b_lo = b_lo0 + stage * stage16;
+              // stage sg = (ky, kb): its three B tiles are k-blocks (ky*3 + kx) * nkb + kb of the packed weights
+              const int nkb3 = p.taps[0].nkb, ky3 = sg / nkb3, kb3 = sg - ky3 * nkb3;
+              const uint32_t a_lo = a_lo0 + stage * stage16;
+              const uint32_t b_lo = p.wres ? w_lo0 + static_cast<uint32_t>(ky3 * 3 * nkb3 + kb3) * bt16 : b_lo0 + stage * stage16;
+              const uint32_t bkx16 = p.wres ? static_cast<uint32_t>(nkb3) * bt16 : bt16;
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
                 // window of 128 pixels starting kx pixels (kx*128 B = 8 descriptor units) into the 130-pixel segment; the
@@ -531,7 +548,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
 #pragma unroll
                 for (int k = 0; k < kIgemmBK / 16; ++k)
                   if (!(p.dbg & 32))
-                    umma_bf16(d_tmem, umma_desc_join(a_lo + 8u * kx + 2u * k, dhi), umma_desc_join(b_lo + kx * bt16 + 2u * k, dhi), idesc,
+                    umma_bf16(d_tmem, umma_desc_join(a_lo + 8u * kx + 2u * k, dhi), umma_desc_join(b_lo + kx * bkx16 + 2u * k, dhi), idesc,
                               (sg | kx | k) != 0 ? 1u : 0u);
               }
               umma_commit(empty_bar(stage));
@@ -546,7 +563,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           if (elect_one_sync()) {
-            const uint32_t a_lo = a_lo0 + stage * stage16, b_lo = b_lo0 + stage * stage16;
+            const uint32_t a_lo = a_lo0 + stage * stage16;
+            const uint32_t b_lo = p.wres ? w_lo0 + static_cast<uint32_t>(ks) * bt16 : b_lo0 + stage * stage16;
 #pragma unroll
             for (int k = 0; k < kIgemmBK / 16; ++k)
               umma_bf16(d_tmem, umma_desc_join(a_lo + 2u * k, dhi), umma_desc_join(b_lo + 2u * k, dhi), idesc, (ks | k) != 0 ? 1u : 0u);
@@ -616,16 +634,23 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
 
 }  // namespace
 
-int igemm_stages_for(int BN, int row3) {
+// wres_bytes > 0: resident weights (that many bytes behind the ring), stages carry activations only; 16 KiB are then always
+// left for the second staging buffer of the lean epilogue
+int igemm_stages_for(int BN, int row3, int wres_bytes) {
+  if (wres_bytes > 0) {
+    const uint32_t stage = row3 ? kRowABytes : kABytes;
+    int n = static_cast<int>((kPipeBytes - kOutStageBytes - static_cast<uint32_t>(wres_bytes)) / stage);
+    return n > kMaxStages ? kMaxStages : n;
+  }
   const uint32_t stage = (row3 ? kRowABytes : kABytes) + (row3 ? 3u : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2;
   // stages must stay 1024-byte aligned: BN is a multiple of 16 -> BN*128 is a multiple of 2048
   int n = static_cast<int>(kPipeBytes / stage);
   return n > kMaxStages ? kMaxStages : n;
 }
 
-bool igemm_res_staging_fits(int BN, int row3, int nstages) {
-  const uint32_t stage = (row3 ? kRowABytes : kABytes) + (row3 ? 3u : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2;
-  return static_cast<uint32_t>(nstages) * stage + kOutStageBytes <= kPipeBytes;
+bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes) {
+  const uint32_t stage = (row3 ? kRowABytes : kABytes) + (wres_bytes > 0 ? 0u : (row3 ? 3u : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2);
+  return static_cast<uint32_t>(nstages) * stage + static_cast<uint32_t>(wres_bytes > 0 ? wres_bytes : 0) + kOutStageBytes <= kPipeBytes;
 }
 
 template <bool ROW3, bool TMA_OUT, bool TMA_RES, bool LEAN = false>
@@ -641,7 +666,8 @@ static int launch_variant(const IgemmPlan& plan, cudaStream_t stream) {
 
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
   ProfScope prof(kProfIgemm, stream, plan.flops);
-  prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.total_kb * kIgemmBK, plan.args.BN, plan.args.ntaps + 100 * plan.args.row3, plan.grid);
+  prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.total_kb * kIgemmBK, plan.args.BN, plan.args.ntaps + 100 * plan.args.row3 + 1000 * plan.args.lean + 2000 * (plan.args.mask != nullptr) + 4000 * (plan.args.res != nullptr) +
+                8000 * (plan.args.out_mode != kOutNHWC) + 16000 * (plan.args.tma_store == 0), plan.grid);
   const int variant = plan.args.tma_store ? (plan.args.tma_res ? 2 : 1) : 0;   // epilogue: per-lane stores / TMA store / TMA store + TMA residual
   int e = 0;
   if (plan.args.lean) {

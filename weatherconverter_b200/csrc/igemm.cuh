@@ -70,7 +70,11 @@ struct IgemmArgs {
   // lean epilogue (igemm.cu: epilogue_tile_lean): TMA store, no ReLU-mask input, residual (if any) through TMA; stage2 = the ring
   // leaves 16 KiB free, i.e. every epilogue warp owns TWO 2 KiB staging buffers and alternates between them
   int lean, stage2;
+  // resident weights (wres == 1): the whole packed weight matrix (N == BN, N * Ktotal * 2 bytes <= kIgemmWresMaxBytes) is loaded
+  // into shared memory ONCE per persistent CTA and the ring stages carry activations only
+  int wres;
 };
+constexpr int kIgemmWresMaxBytes = 98304;
 
 struct IgemmMaps {
   CUtensorMap a[kMaxMaps];
@@ -87,9 +91,9 @@ struct IgemmPlan {
 };
 
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
-int igemm_stages_for(int BN, int row3);
+int igemm_stages_for(int BN, int row3, int wres_bytes = 0);
 // true if 16 KiB stay free behind `nstages` stages of the TMA ring (room for the residual staging of the TMA epilogue)
-bool igemm_res_staging_fits(int BN, int row3, int nstages);
+bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes = 0);
 
 // Choose the M-tile shape for a (B,H,W) grid: widest power-of-two span of x, then y, then b.
 void igemm_pick_tile(int B, int H, int W, int* tb, int* th, int* tw);
