@@ -230,10 +230,13 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   int wres_bytes = 0;
   {
     // resident weights: one N tile, the packed matrix fits next to a useful ring, and every CTA processes several tiles
-    static int wres = -1;   // WC_IGEMM_WRES=0: weights stream through the ring with the activations (round-1 behaviour)
+    // WC_IGEMM_WRES=1 enables it.  Default OFF: measured on B200 (batch 32, 64 x 128) it does not pay - 3x3 64->64 (row-segment
+    // mode) 34.7 -> 40.9 us, 1x1 256->64 37.2 -> 35.9 us, 1x1 64->256 unchanged - although it cuts the L2->SM traffic of the 3x3
+    // layer 2.4x: that traffic is not what bounds these layers (same finding as in round 1, before the TMA epilogue).
+    static int wres = -1;
     if (wres < 0) {
       const char* e = getenv("WC_IGEMM_WRES");
-      wres = e ? atoi(e) : 1;
+      wres = e ? atoi(e) : 0;
     }
     const long wb = static_cast<long>(plan.args.BN) * plan.args.total_kb * kIgemmBK * 2;
     const long m_tiles = (static_cast<long>(B) * H * W + kIgemmBM - 1) / kIgemmBM;
