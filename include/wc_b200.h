@@ -260,6 +260,9 @@ int wc_legacy_unet_launches(const wc_legacy_unet* net);
 typedef struct wc_seg wc_seg;
 int wc_seg_create(wc_seg** out, const int* blocks_per_layer, int num_classes, int n_params, const char* const* names,
                   const float* const* ptrs, void* stream);
+/* output_stride of the backbone (seg_model/network/modeling.py:34-39): 16 (default; replace_stride_with_dilation [F,F,T], ASPP
+ * rates 6/12/18) or 8 (the reference factories' default argument; [F,T,T], rates 12/24/36).  Call before the first infer. */
+int wc_seg_set_output_stride(wc_seg* net, int output_stride);
 void wc_seg_destroy(wc_seg* net);
 size_t wc_seg_workspace_bytes(const wc_seg* net, int batch, int H, int W, int with_grad);
 /* infer(): x nchw_f32 [B,3,H,W]; labels int64 [B,H,W] (255 = ignore); outputs (each may be NULL): pred int64 [B,H,W]

@@ -69,11 +69,13 @@ def _bottleneck(sd, p, x, stride, dilation, has_down):
     return _q(F.relu(out + idt))
 
 
-def block_plan(backbone="resnet50"):
-    """[(prefix, inplanes, planes, stride, dilation, has_down)] for os=16 (replace_stride_with_dilation=[F,F,T])."""
+def block_plan(backbone="resnet50", output_stride=16):
+    """[(prefix, inplanes, planes, stride, dilation, has_down)]; os=16: replace_stride_with_dilation=[F,F,T], os=8: [F,T,T]
+    (modeling.py:34-39)."""
     plan, inplanes, dilation = [], 64, 1
+    dilate_flags = [False, False, False, True] if output_stride == 16 else [False, False, True, True]
     for li, (planes, nblocks, stride, dilate) in enumerate(
-            zip([64, 128, 256, 512], LAYERS[backbone], [1, 2, 2, 2], [False, False, False, True])):
+            zip([64, 128, 256, 512], LAYERS[backbone], [1, 2, 2, 2], dilate_flags)):
         prev = dilation
         if dilate:
             dilation *= stride
@@ -87,8 +89,9 @@ def block_plan(backbone="resnet50"):
     return plan
 
 
-def deeplab_forward(sd, x, backbone="resnet50", taps=None):
-    """x [B,3,H,W] -> logits [B,nc,H,W]."""
+def deeplab_forward(sd, x, backbone="resnet50", taps=None, output_stride=16):
+    """x [B,3,H,W] -> logits [B,nc,H,W].  output_stride 16 -> ASPP rates (6, 12, 18); 8 -> (12, 24, 36) (modeling.py:34-39)."""
+    assert output_stride in (8, 16)
     H, W = x.shape[-2:]
     if EMULATE == "bf16":
         # the CUDA stem runs on the tensor core (csrc/conv.cu: build_conv_stem7s2): image and BN-folded weights in bf16, fp32
@@ -99,7 +102,7 @@ def deeplab_forward(sd, x, backbone="resnet50", taps=None):
         h = _q(F.relu(_bn(sd, "backbone.bn1", F.conv2d(x, sd["backbone.conv1.weight"], stride=2, padding=3))))
     h = F.max_pool2d(h, 3, 2, 1)
     low = None
-    for (p, _, _, stride, dil, has_down) in block_plan(backbone):
+    for (p, _, _, stride, dil, has_down) in block_plan(backbone, output_stride):
         h = _bottleneck(sd, p, h, stride, dil, has_down)
         if p.startswith("backbone.layer1.") and p.endswith(str(LAYERS[backbone][0] - 1)):
             low = h
@@ -108,7 +111,7 @@ def deeplab_forward(sd, x, backbone="resnet50", taps=None):
     c = "classifier"
     ll = _q(F.relu(_cb(sd, c + ".project.0", c + ".project.1", low)))
     res = [_q(F.relu(_cb(sd, c + ".aspp.convs.0.0", c + ".aspp.convs.0.1", h)))]
-    for k, r in zip((1, 2, 3), (6, 12, 18)):
+    for k, r in zip((1, 2, 3), (6, 12, 18) if output_stride == 16 else (12, 24, 36)):
         res.append(_q(F.relu(_cb(sd, f"{c}.aspp.convs.{k}.0", f"{c}.aspp.convs.{k}.1", h, padding=r, dilation=r))))
     g = _q(F.adaptive_avg_pool2d(h, 1))
     g = _q(F.relu(_cb(sd, c + ".aspp.convs.4.1", c + ".aspp.convs.4.2", g)))
@@ -122,13 +125,13 @@ def deeplab_forward(sd, x, backbone="resnet50", taps=None):
     return F.interpolate(y, size=(H, W), mode="bilinear", align_corners=False)
 
 
-def infer(sd, x, labels, backbone="resnet50"):
+def infer(sd, x, labels, backbone="resnet50", output_stride=16):
     """seg_model/inference.py:118-152 for B=1 (looped per image for B>1).
     Returns (pred int64 [B,H,W], input_grad [B,3,H,W], loss [B])."""
     preds, grads, losses = [], [], []
     for b in range(x.shape[0]):
         xb = x[b:b + 1].detach().clone().requires_grad_(True)
-        out = deeplab_forward(sd, xb, backbone)
+        out = deeplab_forward(sd, xb, backbone, output_stride=output_stride)
         preds.append(out.argmax(1))
         loss = F.cross_entropy(out, labels[b:b + 1], ignore_index=255)
         g, = torch.autograd.grad(loss, xb)

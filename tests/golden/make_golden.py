@@ -132,8 +132,8 @@ def g_sample():
     save("sample_traj.pt", dict(cfg=cfg, seed=3455, T=T, xT=xT, zs=torch.stack(zs), traj=torch.stack(traj)))
 
 
-def seg_for(backbone, seed):
-    m = network.modeling.__dict__["deeplabv3plus_" + backbone](num_classes=19, output_stride=16,
+def seg_for(backbone, seed, output_stride=16):
+    m = network.modeling.__dict__["deeplabv3plus_" + backbone](num_classes=19, output_stride=output_stride,
                                                                pretrained_backbone=False).eval()
     sd = synth_state_dict(m.state_dict(), seed)
     m.load_state_dict(sd)
@@ -163,6 +163,24 @@ def g_seg():
                                            pred=torch.from_numpy(pred).to(torch.uint8), grad=grad.detach().clone())
         print(backbone, H, W, float(grad.abs().max()))
     save("seg_infer.pt", out)
+    g_seg_os8()
+
+
+def g_seg_os8():
+    """output_stride = 8, the default argument of the reference factories (modeling.py:182-202): layers 3 and 4 dilated, ASPP
+    rates 12 / 24 / 36."""
+    g = torch.Generator().manual_seed(33)
+    H, W = 64, 128
+    m = seg_for("resnet50", 42, output_stride=8)
+    x = torch.rand(1, 3, H, W, generator=g)
+    gt = block_labels(g, 1, H, W)
+    feats = {}
+    hook = m.classifier.classifier.register_forward_hook(lambda mod, i, o: feats.__setitem__("low", o.detach()))
+    with contextlib.redirect_stdout(io.StringIO()):
+        pred, grad, _ = seg_infer.infer(m, x.clone(), gt)
+    hook.remove()
+    save("seg_infer_os8.pt", {"resnet50_os8_64x128": dict(seed=42, output_stride=8, x=x, gt=gt, logits_lowres=feats["low"],
+                                                           pred=torch.from_numpy(pred).to(torch.uint8), grad=grad.detach().clone())})
 
 
 def g_seg_conditioned():
@@ -404,6 +422,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if only == ["legacy"]:
         g_legacy()
+        sys.exit(0)
+    if only == ["seg_os8"]:
+        g_seg_os8()
         sys.exit(0)
     if only == ["sgg"]:
         g_gsg_and_driver(g_srgan())

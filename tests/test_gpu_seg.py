@@ -64,6 +64,32 @@ def test_seg_infer_vs_golden(golden):
         assert cos_e > 0.975 and rel_e < 0.25, (tag, cos_e, rel_e)
 
 
+def test_seg_output_stride_8_vs_golden(golden):
+    """deeplabv3plus_resnet50(output_stride=8) - the reference factories' DEFAULT argument (modeling.py:182-202): layers 3 and 4
+    dilated (dilation 2 / 4), ASPP rates 12 / 24 / 36 - against a golden made by the reference itself."""
+    from oracle import deeplab
+    from oracle.weights import synth_state_dict
+    from weatherconverter_b200.seg_model.network import modeling
+    dev = _dev()
+    for tag, d in golden("seg_infer_os8.pt").items():
+        m = modeling.deeplabv3plus_resnet50(num_classes=19, pretrained_backbone=False)      # output_stride defaults to 8
+        assert m.output_stride == 8
+        m.load_state_dict(synth_state_dict(m.state_dict(), d["seed"]))
+        m = m.to(dev).eval()
+        out = m.infer(d["x"].to(dev), d["gt"].to(dev), want_grad=True, want_logits=True)
+        sd = synth_state_dict(deeplab.deeplab_param_spec("resnet50"), d["seed"])
+        with torch.no_grad():
+            ref_logits = deeplab.deeplab_forward(sd, d["x"], "resnet50", output_stride=8)
+        lrel = float((out["logits"].cpu() - ref_logits).norm() / ref_logits.norm())
+        agree = float((out["pred"][0].cpu().to(torch.uint8) == d["pred"]).float().mean())
+        grad = out["grad"].cpu()
+        cos = float(torch.nn.functional.cosine_similarity(grad.flatten(), d["grad"].flatten(), dim=0))
+        rel = float((grad - d["grad"]).norm() / d["grad"].norm())
+        print(f"{tag}: argmax agreement {agree:.4f} logits rms-rel {lrel:.3e} | grad vs fp32 golden: cosine {cos:.5f} rms-rel {rel:.3e}")
+        assert lrel < 3e-2 and agree > 0.99, (tag, lrel, agree)
+        assert cos > 0.96 and rel < 0.30, (tag, cos, rel)
+
+
 def test_seg_gradient_on_conditioned_fixture(golden):
     """Input gradient on a WELL-CONDITIONED fixture (tests/golden/seg_conditioned.pt, made by the reference's infer): the last
     BatchNorm scale of every bottleneck x 0.2, i.e. residual branches are small corrections of the identity path as in a

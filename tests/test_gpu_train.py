@@ -140,3 +140,61 @@ def test_train_step_ragged_shapes_vs_oracle():
     print(f"ragged step: loss {float(loss):.5f} vs {float(loss_ref):.5f}, gradient rms-rel {(num / den) ** 0.5:.3e}, worst {worst_name} {worst:.3e}")
     assert (num / den) ** 0.5 < 3e-2
     assert worst < 1.5e-1, (worst_name, worst)
+
+
+def test_resume_from_checkpoint_continues_adam():
+    """The reference's resume flow (train_ddpm.py:63-68,81-84): save model + optimizer state dicts, load them into a fresh model
+    and a fresh torch.optim.Adam, keep training.  The resumed run must continue the moments and the bias-correction step count:
+    two steps + save / load + one step == three uninterrupted steps, bit for bit; and train() (the drop-in loop) imports the
+    optimizer state by itself and exports a loadable one after every epoch."""
+    import io
+    from oracle.unet import DEFAULT_MODEL_CONFIG
+    from weatherconverter_b200.diffusion_model.train_ddpm import DenoisingTrainer, train
+    dev = _dev()
+    cfg = dict(DEFAULT_MODEL_CONFIG); cfg["im_size"] = 32
+    g = torch.Generator().manual_seed(5)
+    images = (torch.rand(2, 3, 32, 32, generator=g) * 2 - 1).to(dev)
+    noises = [torch.randn(2, 3, 32, 32, generator=g).to(dev) for _ in range(3)]
+    ts = [torch.tensor([100 + 7 * k, 600 - 11 * k]) for k in range(3)]
+
+    _, model_a, sched = _build(cfg, 7, dev)
+    tr_a = DenoisingTrainer(model_a, sched, lr=1e-4)
+    for k in range(3):
+        tr_a.step(images, noise=noises[k], t=ts[k])
+
+    _, model_b, _ = _build(cfg, 7, dev)
+    opt_b = torch.optim.Adam(model_b.parameters(), lr=1e-4)
+    tr_b = DenoisingTrainer(model_b, sched, lr=1e-4)
+    for k in range(2):
+        tr_b.step(images, noise=noises[k], t=ts[k])
+    tr_b.export_optimizer_state(opt_b)
+    buf = io.BytesIO()      # the reference's save_checkpoint dictionary (train_ddpm.py:56-61)
+    torch.save({"epoch": 1, "model_state_dict": model_b.state_dict(), "optimizer_state_dict": opt_b.state_dict()}, buf)
+    buf.seek(0)
+    ckpt = torch.load(buf, map_location=dev)
+
+    _, model_c, _ = _build(cfg, 99, dev)          # different initial weights: everything must come from the checkpoint
+    model_c.load_state_dict(ckpt["model_state_dict"])
+    opt_c = torch.optim.Adam(model_c.parameters(), lr=1e-4)
+    opt_c.load_state_dict(ckpt["optimizer_state_dict"])
+    tr_c = DenoisingTrainer(model_c, sched, lr=1e-4)
+    assert tr_c.import_optimizer_state(opt_c) == len(tr_c.slices) and tr_c.step_count == 2
+    tr_c.step(images, noise=noises[2], t=ts[2])
+    torch.cuda.synchronize()
+    for (na, pa), (nc, pc) in zip(model_a.named_parameters(), model_c.named_parameters()):
+        assert na == nc and torch.equal(pa, pc), na
+    # a trainer that ignores the saved moments (fresh Adam) does NOT reproduce the uninterrupted run
+    _, model_d, _ = _build(cfg, 99, dev)
+    model_d.load_state_dict(ckpt["model_state_dict"])
+    tr_d = DenoisingTrainer(model_d, sched, lr=1e-4)
+    tr_d.step(images, noise=noises[2], t=ts[2])
+    assert not torch.equal(tr_d.flat_params, tr_a.flat_params)
+    # train(): imports the state of the optimizer it is given, exports after every epoch
+    _, model_e, _ = _build(cfg, 99, dev)
+    model_e.load_state_dict(ckpt["model_state_dict"])
+    opt_e = torch.optim.Adam(model_e.parameters(), lr=1e-4)
+    opt_e.load_state_dict(ckpt["optimizer_state_dict"])
+    seen = []
+    train([images.cpu()], model_e, opt_e, torch.nn.MSELoss(), sched, epochs=2, seed=11,
+          on_epoch_end=lambda ep: seen.append(int(float(next(iter(opt_e.state.values()))["step"]))))
+    assert seen == [3, 4]       # continued from step 2: one batch per epoch

@@ -150,11 +150,15 @@ def test_bench_roofline_traffic_comes_from_the_committed_ncu_capture():
     import json
     sys.path.insert(0, ROOT)
     import bench
-    t = bench._dram_traffic_per_launch("c3")
-    meta = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic_c3.json")))
+    import glob
+    t, src = bench._dram_traffic_per_launch("c3")
+    newest = max(glob.glob(os.path.join(ROOT, "profiles", "r*_dram_traffic_c3.json")),
+                 key=lambda f: int(re.match(r"r(\d+)_", os.path.basename(f)).group(1)))
+    assert src == os.path.basename(newest)          # the NEWEST round's capture is the one reported (and named in the line)
+    meta = json.load(open(newest))
     assert t == pytest.approx(meta["dram_bytes_per_launch"]) and t > 1e6
     assert os.path.exists(os.path.join(ROOT, meta["source"]))
-    assert bench._dram_traffic_per_launch("no_such_workload") is None
+    assert bench._dram_traffic_per_launch("no_such_workload") == (None, None)
 
 
 def test_launch_traffic_tool_parses_an_ncu_log(tmp_path, monkeypatch):

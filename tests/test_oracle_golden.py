@@ -69,6 +69,19 @@ def test_seg_infer(golden):
         assert (grad - d["grad"]).abs().max() <= 1e-5 * d["grad"].abs().max() + 1e-9, tag
 
 
+def test_seg_infer_output_stride_8(golden):
+    """output_stride = 8 (the reference factories' default argument, modeling.py:182-202): layers 3-4 dilated, ASPP 12/24/36."""
+    for tag, d in golden("seg_infer_os8.pt").items():
+        sd = synth_state_dict(deeplab.deeplab_param_spec("resnet50"), d["seed"])
+        taps = {}
+        with torch.no_grad():
+            deeplab.deeplab_forward(sd, d["x"], "resnet50", taps, output_stride=8)
+        assert (taps["logits_lowres"] - d["logits_lowres"]).abs().max() < 1e-4, tag
+        pred, grad, _ = deeplab.infer(sd, d["x"], d["gt"], "resnet50", output_stride=8)
+        assert (pred[0].to(torch.uint8) == d["pred"]).float().mean() > 0.9999, tag
+        assert (grad - d["grad"]).abs().max() <= 1e-5 * d["grad"].abs().max() + 1e-9, tag
+
+
 def test_srgan(golden):
     d = golden("srgan.pt")
     sd = synth_state_dict(srgan.srgan_param_spec(), d["seed"])

@@ -36,8 +36,19 @@ def main():
         torch.cuda.synchronize()
         return float(loss)
 
-    model = Unet(cfg).to(dev); model.load_state_dict(sd)
+    # every rank deliberately starts from DIFFERENT weights: the trainer must broadcast rank 0's at construction (torch DDP's
+    # contract) instead of relying on identical seeding
+    sd_rank = sd if rank == 0 else synth_state_dict({k: (v, torch.float32) for k, v in param_spec(cfg).items()}, 11 + 97 * rank)
+    model = Unet(cfg).to(dev); model.load_state_dict(sd_rank)
     tr = DenoisingTrainer(model, sched, lr=1e-4, bucket_bytes=32 << 20)
+    ref0 = tr.flat_params.clone()
+    dist.broadcast(ref0, 0)
+    assert torch.equal(ref0, tr.flat_params), f"rank {rank}: parameters were not broadcast from rank 0"
+    # default noise / timestep draws come from per-rank generators: the ranks must NOT draw the same t for their different images
+    t_draw = torch.randint(0, 1000, (4,), generator=tr._gen_cpu)
+    gathered = [torch.empty(4, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, t_draw.to(dev))
+    assert world == 1 or not torch.equal(gathered[0], gathered[1]), "ranks drew identical timesteps"
     per = Bg // world
     loss = run(tr, rank * per, (rank + 1) * per)
     nb = len(tr._buckets)

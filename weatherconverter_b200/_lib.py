@@ -103,6 +103,7 @@ _SIGS = {
     "wc_legacy_unet_launches": (C.c_int, [c_ptr]),
     "wc_seg_create": (C.c_int, [C.POINTER(c_ptr), C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_char_p),
                                 C.POINTER(c_ptr), c_ptr]),
+    "wc_seg_set_output_stride": (C.c_int, [c_ptr, C.c_int]),
     "wc_seg_destroy": (None, [c_ptr]),
     "wc_seg_workspace_bytes": (C.c_size_t, [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int]),
     "wc_seg_infer": (C.c_int, [c_ptr] * 7 + [C.c_int] * 3 + [c_ptr, C.c_size_t, c_ptr]),

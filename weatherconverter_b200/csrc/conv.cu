@@ -46,6 +46,15 @@ bool row3_enabled() {
   return v == 1;
 }
 
+bool lean_enabled() {   // WC_IGEMM_LEAN=0: previous epilogue everywhere
+  static int lean = -1;
+  if (lean < 0) {
+    const char* e = getenv("WC_IGEMM_LEAN");
+    lean = e ? atoi(e) : 1;
+  }
+  return lean != 0;
+}
+
 struct TapDef {
   int map, dy, dx;
   const WeightSrc* w;
@@ -144,13 +153,19 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
       const char* e = getenv("WC_IGEMM_TMA_STORE");
       tma_store = e ? atoi(e) : 1;
     }
-    if (tma_store && sy == 1 && sx == 1) {
+    static int tma_strided = -1;   // WC_IGEMM_TMA_STRIDED=0: up-sampling phases (sy = sx = 2) keep the row-per-lane stores
+    if (tma_strided < 0) {
+      const char* e = getenv("WC_IGEMM_TMA_STRIDED");
+      tma_strided = e ? atoi(e) : 1;
+    }
+    const bool unit = (sy == 1 && sx == 1);
+    if (tma_store && (unit || (tma_strided && out.out.H == H * sy && out.out.W == W * sx && (out.out.ld * sx * 2) % 16 == 0))) {
       const int nc = (a.BN % 32 == 0 && N % 32 == 0) ? 32 : 16;   // the epilogue's chunk width (see igemm_kernel)
       a.qw = tw < 32 ? tw : 32;
       a.qh = th < 32 / a.qw ? th : 32 / a.qw;
       a.qb = 32 / (a.qw * a.qh);
       if (a.qb <= tb) {
-        if (int e = igemm_make_cmap(&plan->maps.c, out.out, N, nc, a.qw, a.qh, a.qb)) return e;
+        if (int e = igemm_make_cmap(&plan->maps.c, out.out, N, nc, a.qw, a.qh, a.qb, sy, sx, py, px)) return e;
         a.tma_store = 1;
         static int tma_res = -1;   // WC_IGEMM_TMA_RES=0: residual rows through per-lane global loads
         if (tma_res < 0) {
@@ -158,7 +173,7 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
           tma_res = e2 ? atoi(e2) : 1;
         }
         if (tma_res && ep.res && ep.res->ld % 8 == 0) {
-          if (int e = igemm_make_cmap(&plan->maps.r, *ep.res, N, nc, a.qw, a.qh, a.qb)) return e;
+          if (int e = igemm_make_cmap(&plan->maps.r, *ep.res, N, nc, a.qw, a.qh, a.qb, sy, sx, py, px)) return e;
           a.tma_res = 2;   // candidate: confirmed by the caller once the ring depth is known
         }
       }
@@ -248,14 +263,7 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3, wres_bytes);
   plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, plan.args.row3, plan.args.nstages, wres_bytes) ? 1 : 0;
   plan.args.tma_res = (plan.args.tma_res == 2 && plan.args.stage2) ? 1 : 0;
-  {
-    static int lean = -1;   // WC_IGEMM_LEAN=0: previous epilogue everywhere
-    if (lean < 0) {
-      const char* e = getenv("WC_IGEMM_LEAN");
-      lean = e ? atoi(e) : 1;
-    }
-    plan.args.lean = (lean && plan.args.tma_store && !plan.args.mask && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
-  }
+  plan.args.lean = (lean_enabled() && plan.args.tma_store && !plan.args.mask && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
   { const char* e = getenv("WC_IGEMM_DBG"); plan.args.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("WC_IGEMM_TRACE"); plan.args.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   op->flops = plan.flops;
@@ -295,7 +303,7 @@ int build_conv_stem7s2(ConvOp* op, DeviceArena* arena, const __nv_bfloat16* xp, 
   plan.args.nstages = igemm_stages_for(plan.args.BN, 0);
   plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, 0, plan.args.nstages) ? 1 : 0;
   plan.args.tma_res = 0;
-  plan.args.lean = (plan.args.tma_store && !plan.args.mask && !plan.args.res) ? 1 : 0;
+  plan.args.lean = (lean_enabled() && plan.args.tma_store && !plan.args.mask && !plan.args.res) ? 1 : 0;
   plan.flops = 2.0 * 147.0 * N * static_cast<double>(B) * Ho * Wo;   // algorithmic (the reference's 7x7x3 taps), not the padded K
   op->flops = plan.flops;
   return 0;
@@ -322,6 +330,9 @@ int build_conv_transposed_s2(ConvOp* op, DeviceArena* arena, const Act& x, const
       for (int i = 1; i < kMaxMaps; ++i) plan.maps.a[i] = plan.maps.a[0];
       if (int e = finish_plan(&plan, arena, taps, x.B, x.H, x.W, tb, th, tw, N, ep, out, 2, 2, qy, qx, st)) return e;
       plan.args.nstages = igemm_stages_for(plan.args.BN, 0);
+      plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, 0, plan.args.nstages) ? 1 : 0;
+      plan.args.tma_res = (plan.args.tma_res == 2 && plan.args.stage2) ? 1 : 0;
+      plan.args.lean = (lean_enabled() && plan.args.tma_store && !plan.args.mask && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
       op->flops += plan.flops;
     }
   return 0;

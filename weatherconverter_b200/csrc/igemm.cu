@@ -739,13 +739,16 @@ int igemm_make_rowseg_map(CUtensorMap* out, const Act& act) {
   return encode_tmap_bf16(out, act.ptr, 4, dims, strides, box, 128);
 }
 
-int igemm_make_cmap(CUtensorMap* out, const Act& act, int N, int nc, int qw, int qh, int qb) {
-  uint64_t dims[4] = {static_cast<uint64_t>(N), static_cast<uint64_t>(act.W), static_cast<uint64_t>(act.H),
+int igemm_make_cmap(CUtensorMap* out, const Act& act, int N, int nc, int qw, int qh, int qb, int sy, int sx, int py, int px) {
+  // (sy, sx, py, px) != (1, 1, 0, 0): the map covers the phase view act(b, y*sy + py, x*sx + px, c) of an up-sampled output grid
+  // (transposed convolutions, stride-2 data gradients, PixelShuffle), so those launches can use the TMA-store epilogue too
+  uint64_t dims[4] = {static_cast<uint64_t>(N), static_cast<uint64_t>(act.W / sx), static_cast<uint64_t>(act.H / sy),
                       static_cast<uint64_t>(act.B)};
-  uint64_t strides[4] = {1, static_cast<uint64_t>(act.ld), static_cast<uint64_t>(act.ld) * act.W,
+  uint64_t strides[4] = {1, static_cast<uint64_t>(act.ld) * sx, static_cast<uint64_t>(act.ld) * act.W * sy,
                          static_cast<uint64_t>(act.ld) * act.W * act.H};
   uint32_t box[4] = {static_cast<uint32_t>(nc), static_cast<uint32_t>(qw), static_cast<uint32_t>(qh), static_cast<uint32_t>(qb)};
-  return encode_tmap_bf16(out, act.ptr, 4, dims, strides, box, static_cast<uint32_t>(nc * 2));
+  const __nv_bfloat16* base = act.ptr + (static_cast<size_t>(py) * act.W + px) * act.ld;
+  return encode_tmap_bf16(out, base, 4, dims, strides, box, static_cast<uint32_t>(nc * 2));
 }
 
 int igemm_make_bmap(CUtensorMap* out, const __nv_bfloat16* wpacked, int n_rows, int ktotal, int BN) {

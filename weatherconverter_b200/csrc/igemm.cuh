@@ -107,6 +107,7 @@ int igemm_make_amap(CUtensorMap* out, const Act& act, int tb, int th, int tw, in
 int igemm_make_rowseg_map(CUtensorMap* out, const Act& act);
 int igemm_make_bmap(CUtensorMap* out, const __nv_bfloat16* wpacked, int n_rows, int ktotal, int BN);
 // Output map for the TMA-store epilogue: channels [0, N) of an NHWC view, box (nc, qw, qh, qb), swizzle = nc*2 bytes.
-int igemm_make_cmap(CUtensorMap* out, const Act& act, int N, int nc, int qw, int qh, int qb);
+int igemm_make_cmap(CUtensorMap* out, const Act& act, int N, int nc, int qw, int qh, int qb, int sy = 1, int sx = 1, int py = 0,
+                    int px = 0);
 
 }  // namespace wc

@@ -39,6 +39,7 @@ int conv1_dgrad_pooled(const __nv_bfloat16* dz, const float* weff, float* out, i
 struct wc_seg {
   int layers[4];
   int num_classes;
+  int output_stride = 16;   // 16: layer4 dilated, ASPP rates 6/12/18; 8: layers 3-4 dilated, rates 12/24/36 (modeling.py:34-39)
   wc::ParamTable params;
   std::unique_ptr<wc::DeviceArena> arena;
   int B = 0, H = 0, W = 0, with_grad = 0, grad_pool = 1;
@@ -188,7 +189,8 @@ int build(wc_seg* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
   {
     int inplanes = 64, dilation = 1;
     const int planes_l[4] = {64, 128, 256, 512}, stride_l[4] = {1, 2, 2, 2};
-    const bool dilate_l[4] = {false, false, false, true};  // output_stride 16 (modeling.py:37-39)
+    const bool os8 = net->output_stride == 8;
+    const bool dilate_l[4] = {false, false, os8, true};  // replace_stride_with_dilation: os 16 [F,F,T], os 8 [F,T,T] (modeling.py:34-39)
     for (int li = 0; li < 4; ++li) {
       const int prev = dilation;
       int stride = stride_l[li];
@@ -232,7 +234,8 @@ int build(wc_seg* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
   const std::string c = "classifier";
   Act cat5 = b.act(h, w, 1280);
   b.conv_bn(feat, c + ".aspp.convs.0.0", c + ".aspp.convs.0.1", 2048, 256, 1, 1, 1, nullptr, 1, slice_act(cat5, 0, 256));
-  const int rates[3] = {6, 12, 18};
+  const int rmul = net->output_stride == 8 ? 2 : 1;
+  const int rates[3] = {6 * rmul, 12 * rmul, 18 * rmul};   // ASPP dilations (modeling.py:35,38)
   for (int k = 0; k < 3; ++k)
     b.conv_bn(feat, c + ".aspp.convs." + std::to_string(k + 1) + ".0", c + ".aspp.convs." + std::to_string(k + 1) + ".1", 2048,
               256, 3, 1, rates[k], nullptr, 1, slice_act(cat5, 256 * (k + 1), 256));
@@ -397,6 +400,16 @@ int wc_seg_create(wc_seg** out, const int* blocks_per_layer, int num_classes, in
   net->num_classes = num_classes;
   for (int i = 0; i < n_params; ++i) net->params.ptr[names[i]] = ptrs[i];
   *out = net.release();
+  return 0;
+}
+
+int wc_seg_set_output_stride(wc_seg* net, int output_stride) {
+  WC_REQUIRE(net, "null handle");
+  WC_REQUIRE(output_stride == 8 || output_stride == 16, "output_stride must be 8 or 16 (modeling.py:34-39)");
+  if (net->output_stride != output_stride) {
+    net->output_stride = output_stride;
+    net->B = net->H = net->W = 0;   // force a rebuild of the plan on the next call
+  }
   return 0;
 }
 

@@ -66,9 +66,9 @@ def param_spec(backbone="resnet50", num_classes=19):
 class DeepLabV3(nn.Module):
     """DeepLabV3+ (ResNet backbone) with the reference's forward contract: x [B,3,H,W] fp32 -> logits [B,nc,H,W]."""
 
-    def __init__(self, backbone_name, num_classes):
+    def __init__(self, backbone_name, num_classes, output_stride=16):
         super().__init__()
-        self.backbone_name, self.num_classes = backbone_name, num_classes
+        self.backbone_name, self.num_classes, self.output_stride = backbone_name, num_classes, output_stride
         for name, (shape, kind) in param_spec(backbone_name, num_classes).items():
             if kind == "conv":      # kaiming_normal_ (fan_out for the backbone resnet.py:155, fan_in for the head _deeplab.py:56)
                 fan = (shape[0] if name.startswith("backbone") else shape[1]) * shape[2] * shape[3]
@@ -126,6 +126,7 @@ class DeepLabV3(nn.Module):
         layers = (C.c_int * 4)(*_LAYERS[self.backbone_name])
         h = C.c_void_p()
         check(lib().wc_seg_create(C.byref(h), layers, self.num_classes, n, names, ptrs, stream_ptr()))
+        check(lib().wc_seg_set_output_stride(h, self.output_stride))
         self._handle, self._key, self._keep, self._ws = h, key, list(ts.values()), {}
 
     def _workspace(self, B, H, W, with_grad, device):
@@ -178,11 +179,11 @@ class DeepLabV3(nn.Module):
 
 
 def _build(backbone, num_classes, output_stride, pretrained_backbone):
-    if output_stride != 16:
-        raise NotImplementedError("the B200 path implements output_stride=16 (the reference's configuration)")
+    if output_stride not in (8, 16):
+        raise ValueError("output_stride must be 8 or 16 (seg_model/network/modeling.py:34-39)")
     if pretrained_backbone:
         raise RuntimeError("pretrained_backbone=True needs a network download (resnet.py:216-222); load a checkpoint instead")
-    return DeepLabV3(backbone, num_classes)
+    return DeepLabV3(backbone, num_classes, output_stride)
 
 
 def deeplabv3plus_resnet50(num_classes=21, output_stride=8, pretrained_backbone=True):
