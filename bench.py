@@ -592,7 +592,8 @@ def secondary_training(dev, rank, world, peaks, steps=3, warmup=3, batch=64):
             "steps": steps, "warmup": warmup, "ms_per_step": ms_full, "ms_per_step_without_allreduce": ms_nocomm,
             "allreduce_bytes_per_step": int(trainer.used) * 4, "allreduce_alone_ms": ms_ar,
             "allreduce_alone_busbw_gbs": 2.0 * (world - 1) / world * trainer.used * 4 / (ms_ar * 1e-3) / 1e9,
-            "allreduce_hidden_frac": max(0.0, 1.0 - exposed / ms_ar) if ms_ar > 0 else None,
+            "allreduce_exposed_ms": exposed,
+            "allreduce_hidden_frac": min(1.0, max(0.0, 1.0 - exposed / ms_ar)) if ms_ar > 0 else None,
             "buckets": len(trainer._buckets), "step_tflops_per_gpu": trainer.flops_per_step / (ms_full * 1e-3) / 1e12,
             "final_loss": loss, "finite": loss == loss}
 

@@ -55,8 +55,7 @@ def main():
     ok = True
     if rank == 0:
         model1 = Unet(cfg).to(dev); model1.load_state_dict(sd)
-        tr1 = DenoisingTrainer(model1, sched, lr=1e-4)
-        tr1.world = 1                       # single-process reference on the concatenated batch
+        tr1 = DenoisingTrainer(model1, sched, lr=1e-4, data_parallel=False)   # single-process reference on the concatenated batch
         loss1 = run(tr1, 0, Bg)
         dp, d1 = tr.flat_params, tr1.flat_params
         upd = (d1 - torch.cat([v.flatten() for v in []]) if False else None)

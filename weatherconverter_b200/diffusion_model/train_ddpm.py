@@ -82,13 +82,16 @@ class DenoisingTrainer:
     parameter buffer) and the C training plan bound to one (batch, H, W)."""
 
     def __init__(self, model: Unet, scheduler, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, process_group=None,
-                 bucket_bytes=64 << 20, seed=None):
+                 bucket_bytes=64 << 20, seed=None, data_parallel=True):
         if not torch.cuda.is_available():
             raise RuntimeError("wc_b200 training needs a CUDA device (sm_100a); there is no CPU fallback")
         self.model, self.scheduler = model, scheduler
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        # data_parallel=False: a single-process trainer inside an initialised process group (no broadcast, no all-reduce) - e.g.
+        # the one-process reference run of tools/ddp_check.py; constructing a data-parallel trainer is a COLLECTIVE call
+        self.world = (dist.get_world_size(process_group)
+                      if (data_parallel and dist.is_available() and dist.is_initialized()) else 1)
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         self.bucket_bytes = int(bucket_bytes)
         self.step_count = 0
