@@ -3,7 +3,7 @@
 A plain-PyTorch fp32 restatement of the reference's DDPM reverse-sampling loop with
 semantic-gradient guidance.  Every function cites the reference file:line it follows.
 
-Rules (enforced by tests/test_no_oracle_in_product.py):
+Rules (enforced by tests/test_host_logic.py::test_no_oracle_in_product):
   * only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
     ``--impl reference`` legs may import anything from this package;
   * nothing under ``weatherconverter_b200/`` imports it; the product path raises when the
