@@ -55,6 +55,15 @@ bool lean_enabled() {   // WC_IGEMM_LEAN=0: previous epilogue everywhere
   return lean != 0;
 }
 
+bool lean_mask_enabled() {   // WC_IGEMM_LEAN_MASK=1: layers with a ReLU-mask input (segmentor data gradients) use the lean epilogue
+  static int v = -1;          // too.  Default off: measured neutral (C3 igemm 10.96 vs 10.99 ms) - those layers are bound by the mask rows
+  if (v < 0) {
+    const char* e = getenv("WC_IGEMM_LEAN_MASK");
+    v = e ? atoi(e) : 0;
+  }
+  return v != 0;
+}
+
 struct TapDef {
   int map, dy, dx;
   const WeightSrc* w;
@@ -263,7 +272,7 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3, wres_bytes);
   plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, plan.args.row3, plan.args.nstages, wres_bytes) ? 1 : 0;
   plan.args.tma_res = (plan.args.tma_res == 2 && plan.args.stage2) ? 1 : 0;
-  plan.args.lean = (lean_enabled() && plan.args.tma_store && !plan.args.mask && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
+  plan.args.lean = (lean_enabled() && plan.args.tma_store && (!plan.args.mask || lean_mask_enabled()) && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
   { const char* e = getenv("WC_IGEMM_DBG"); plan.args.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("WC_IGEMM_TRACE"); plan.args.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   op->flops = plan.flops;
@@ -332,7 +341,7 @@ int build_conv_transposed_s2(ConvOp* op, DeviceArena* arena, const Act& x, const
       plan.args.nstages = igemm_stages_for(plan.args.BN, 0);
       plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, 0, plan.args.nstages) ? 1 : 0;
       plan.args.tma_res = (plan.args.tma_res == 2 && plan.args.stage2) ? 1 : 0;
-      plan.args.lean = (lean_enabled() && plan.args.tma_store && !plan.args.mask && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
+      plan.args.lean = (lean_enabled() && plan.args.tma_store && (!plan.args.mask || lean_mask_enabled()) && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
       op->flops += plan.flops;
     }
   return 0;

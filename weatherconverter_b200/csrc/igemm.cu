@@ -246,8 +246,9 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
 // chunk by chunk (ectr counts this warp's chunks across tiles): the TMA store of chunk i reads buffer i & 1 while chunk i + 1 is
 // staged in the other one.  With a residual the box of chunk i is loaded by TMA INTO the buffer chunk i will be stored from; each
 // lane reads its row, adds, and writes the bf16 result back in place.
-template <int NC, bool RES>
-__device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t tacc, int n0, int b, int grp, const float* s_bias,
+template <int NC, bool RES, bool MASK>
+__device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t tacc, int n0, int b, int y, int x, bool valid, int grp,
+                                                   const float* s_bias,
                                                    const float* s_prelu, uint32_t tfull_addr, uint32_t tfull_parity,
                                                    const CUtensorMap* cmap, const CUtensorMap* rmap, uint32_t buf0, uint32_t buf1,
                                                    int nbuf, int qx, int qy, int qb0, uint32_t res_bar, uint32_t& res_phase,
@@ -266,6 +267,17 @@ __device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t 
   };
   const int c_first = grp * NC;
   if (RES && c_first < p.BN && n0 + c_first < p.N) request(ectr, n0 + c_first);   // before the accumulator is ready: overlaps the main loop
+  // ReLU-derivative mask rows (segmentor data gradients): per-lane global loads of this pixel's row, one chunk ahead
+  const uint4* mask_row = nullptr;
+  uint4 mk[NV];
+  if (MASK) {
+    const int oy = y * p.sy + p.py, ox = x * p.sx + p.px;
+    mask_row = reinterpret_cast<const uint4*>(p.mask + ((static_cast<size_t>(b) * p.Ho + oy) * p.Wo + ox) * p.ldm);
+    if (valid && c_first < p.BN && n0 + c_first < p.N) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) mk[j] = __ldg(mask_row + ((n0 + c_first) >> 3) + j);
+    }
+  }
   mbar_wait(tfull_addr, tfull_parity);
   tc_fence_after();
   const float* rb = p.rowbias ? p.rowbias + static_cast<size_t>(b < p.B ? b : p.B - 1) * p.ldrb : nullptr;
@@ -285,6 +297,15 @@ __device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t 
                      : "r"(mine + ((static_cast<uint32_t>(j) ^ sw) << 4)) : "memory");
       // the next box goes into the OTHER buffer (last touched, through the generic proxy, one chunk ago and fenced then)
       if (c0 + 2 * NC < p.BN && nb + 2 * NC < p.N) request(ectr + 1, nb + 2 * NC);
+    }
+    uint4 mcur[NV];
+    if (MASK) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) mcur[j] = mk[j];
+      if (valid && c0 + 2 * NC < p.BN && nb + 2 * NC < p.N) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) mk[j] = __ldg(mask_row + ((nb + 2 * NC) >> 3) + j);
+      }
     }
     tmem_wait_ld();
     float v[NC];
@@ -338,6 +359,21 @@ __device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t 
         v[j + 2] = v[j + 2] > 0.f ? v[j + 2] : v[j + 2] * sv.z; v[j + 3] = v[j + 3] > 0.f ? v[j + 3] : v[j + 3] * sv.w;
       }
     }
+    if (MASK) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const uint4 u = mcur[j];
+        const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+        if (!(f0.x > 0.f)) v[8 * j + 0] = 0.f;
+        if (!(f0.y > 0.f)) v[8 * j + 1] = 0.f;
+        if (!(f1.x > 0.f)) v[8 * j + 2] = 0.f;
+        if (!(f1.y > 0.f)) v[8 * j + 3] = 0.f;
+        if (!(f2.x > 0.f)) v[8 * j + 4] = 0.f;
+        if (!(f2.y > 0.f)) v[8 * j + 5] = 0.f;
+        if (!(f3.x > 0.f)) v[8 * j + 6] = 0.f;
+        if (!(f3.y > 0.f)) v[8 * j + 7] = 0.f;
+      }
+    }
     if (!RES) {   // the store that last read this buffer (two chunks ago with two buffers, the previous one otherwise)
       if (lane == 0) {
         if (nbuf == 2) tma_store_wait_read<1>();
@@ -360,7 +396,7 @@ __device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t 
   }
 }
 
-template <bool ROW3, bool TMA_OUT, bool TMA_RES, bool LEAN = false>
+template <bool ROW3, bool TMA_OUT, bool TMA_RES, int LEAN = 0>   // LEAN: 0 generic epilogue, 1 lean, 2 lean with a ReLU-mask input
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -607,10 +643,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       if (warp == 2 && lane == 0) trace(2, 20);
       if (LEAN) {
         if ((p.BN % 32 == 0) && (p.N % 32 == 0))
-          epilogue_tile_lean<32, TMA_RES>(p, tacc, n0, b, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
+          epilogue_tile_lean<32, TMA_RES, LEAN == 2>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
                                           p.stage2 ? 2 : 1, x0 + qx0, y0 + qy0, b0 + qb0, res_bar, res_phase, ectr);
         else
-          epilogue_tile_lean<16, TMA_RES>(p, tacc, n0, b, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
+          epilogue_tile_lean<16, TMA_RES, LEAN == 2>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
                                           p.stage2 ? 2 : 1, x0 + qx0, y0 + qy0, b0 + qb0, res_bar, res_phase, ectr);
       } else if (p.out_mode != kOutQKV && (p.BN % 32 == 0) && (p.N % 32 == 0))
         epilogue_tile<32, TMA_OUT, TMA_RES>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, out_stage, x0 + qx0,
@@ -653,7 +689,7 @@ bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes) {
   return static_cast<uint32_t>(nstages) * stage + static_cast<uint32_t>(wres_bytes > 0 ? wres_bytes : 0) + kOutStageBytes <= kPipeBytes;
 }
 
-template <bool ROW3, bool TMA_OUT, bool TMA_RES, bool LEAN = false>
+template <bool ROW3, bool TMA_OUT, bool TMA_RES, int LEAN = 0>
 static int launch_variant(const IgemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -670,9 +706,12 @@ int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
                 8000 * (plan.args.out_mode != kOutNHWC) + 16000 * (plan.args.tma_store == 0), plan.grid);
   const int variant = plan.args.tma_store ? (plan.args.tma_res ? 2 : 1) : 0;   // epilogue: per-lane stores / TMA store / TMA store + TMA residual
   int e = 0;
-  if (plan.args.lean) {
-    if (plan.args.row3) e = plan.args.tma_res ? launch_variant<true, true, true, true>(plan, stream) : launch_variant<true, true, false, true>(plan, stream);
-    else e = plan.args.tma_res ? launch_variant<false, true, true, true>(plan, stream) : launch_variant<false, true, false, true>(plan, stream);
+  if (plan.args.lean && plan.args.mask) {
+    if (plan.args.row3) e = plan.args.tma_res ? launch_variant<true, true, true, 2>(plan, stream) : launch_variant<true, true, false, 2>(plan, stream);
+    else e = plan.args.tma_res ? launch_variant<false, true, true, 2>(plan, stream) : launch_variant<false, true, false, 2>(plan, stream);
+  } else if (plan.args.lean) {
+    if (plan.args.row3) e = plan.args.tma_res ? launch_variant<true, true, true, 1>(plan, stream) : launch_variant<true, true, false, 1>(plan, stream);
+    else e = plan.args.tma_res ? launch_variant<false, true, true, 1>(plan, stream) : launch_variant<false, true, false, 1>(plan, stream);
   } else if (plan.args.row3) e = variant == 2 ? launch_variant<true, true, true>(plan, stream) : variant == 1 ? launch_variant<true, true, false>(plan, stream) : launch_variant<true, false, false>(plan, stream);
   else e = variant == 2 ? launch_variant<false, true, true>(plan, stream) : variant == 1 ? launch_variant<false, true, false>(plan, stream) : launch_variant<false, false, false>(plan, stream);
   if (e) return e;

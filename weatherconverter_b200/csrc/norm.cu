@@ -12,6 +12,15 @@ namespace {
 
 constexpr int kGroups = 8;
 
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2: ONE MUFU op (tanh.approx, relative error 2^-11 - the result is rounded to bf16,
+// 2^-9) instead of two (ex2 + rcp); the apply pass of a 33 MB tensor otherwise spends 7 us of its ~12 us on the MUFU pipe
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 // Each thread owns one 8-channel vector column (fixed group) and strides over pixels.
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, int ld, int nsplit,
                                 float2* __restrict__ partial) {
@@ -105,7 +114,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float o = fmaf(f[j], ga[j], be[j]);
-      if (silu) o = __fdividef(o, 1.f + __expf(-o));
+      if (silu) o = silu_fast(o);
       f[j] = o;
     }
     uint4 w;
@@ -483,7 +492,7 @@ __global__ void gn_fused_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float o = fmaf(f[j], ga[j], be[j]);
-      if (silu) o = __fdividef(o, 1.f + __expf(-o));
+      if (silu) o = silu_fast(o);
       f[j] = o;
     }
     uint4 w;
@@ -532,15 +541,15 @@ int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int 
   const int nsplit = groupnorm_stats_splits(B, HW);
   const int max_split = (HW + 31) / 32;
   float2* partial = reinterpret_cast<float2*>(workspace);
-  // Single-launch cluster kernel for SMALL tensors only (WC_GN_FUSED_MAX_BYTES, default 4 MiB; 0 disables it): with 8 CTAs per
-  // sample it cannot fill the chip on the 25 - 67 MB tensors of a batch-32 step (measured: GroupNorm 1.55 -> 2.13 ms per C3 step
-  // when used for every map of <= 2048 pixels), but at batch 1 every GroupNorm below the first level is one launch instead of two.
-  // Both paths partition and order the sums identically, so they give bit-identical results (the batch-invariance tests compare
-  // batch 1 - fused - with batch 16 / 32 - two-pass).
+  // Single-launch cluster kernel, for tensors of at most WC_GN_FUSED_MAX_BYTES bytes.  Default 0 = OFF: measured on B200 it loses
+  // in both regimes - batch 32 (all maps of <= 2048 pixels): GroupNorm 1.55 -> 2.13 ms per C3 step (8 CTAs per sample cannot fill
+  // the chip on 25 - 67 MB tensors); batch 1 (reference geometry, tensors <= 4 MiB): 0.94 -> 1.61 ms per step (a cluster launch
+  // plus two cluster barriers cost more than the second small launch they replace).  Both paths partition and order the sums
+  // identically and give bit-identical results.
   static long fused_max = -1;
   if (fused_max < 0) {
     const char* e = getenv("WC_GN_FUSED_MAX_BYTES");
-    fused_max = e ? atol(e) : (4l << 20);
+    fused_max = e ? atol(e) : 0;
   }
   if (HW <= 2048 && 2l * B * HW * C <= fused_max) {
     ProfScope prof(kProfGroupNorm, st, 4.0 * B * static_cast<double>(HW) * C);  // algorithmic bytes: 1 read + 1 write, bf16
