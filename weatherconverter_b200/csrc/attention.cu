@@ -422,6 +422,8 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
 
 int attention_small_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
                             int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse, float scale);
+int attention_small4_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
+                             int heads, int ntok, int hd, int ldo, cudaStream_t st, float* lse, float scale);
 
 // q,k [B,heads,ntok,hd]; vt [B,heads,hd,ntok]; out [B,ntok,ldo] (columns head*hd .. head*hd+hd).
 int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B,
@@ -433,7 +435,18 @@ int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv
     const char* e = getenv("WC_ATTN_SMALL");
     small = e ? atoi(e) : 1;
   }
-  if (small && (hd == 16 || hd == 32)) return attention_small_forward(q, k, vt, out, B, heads, ntok, hd, ldo, st, lse, scale);
+  if (small && (hd == 16 || hd == 32)) {
+    static int four = -1;   // WC_ATTN_SMALL4=0: three softmax groups with a double-buffered S (attention_small.cu, round 1)
+    if (four < 0) {
+      const char* e = getenv("WC_ATTN_SMALL4");
+      four = e ? atoi(e) : 1;
+    }
+    // Measured on B200 (batch 32, N 8192): head_dim 16 2.42 -> 2.24 ms with four groups; head_dim 32 2.35 (three groups, P' in
+    // tensor memory) vs 2.41 (four groups, P' through shared memory) -> head_dim 32 keeps the 3-group kernel.  Four groups per
+    // CTA cover 512 queries: shorter sequences keep the 3-group kernel too.
+    if (four && hd == 16 && ntok >= 2048) return attention_small4_forward(q, k, vt, out, B, heads, ntok, hd, ldo, st, lse, scale);
+    return attention_small_forward(q, k, vt, out, B, heads, ntok, hd, ldo, st, lse, scale);
+  }
   static int tp = -1;   // WC_ATTN_TP=0: P through shared memory (previous design); default: P in tensor memory
   if (tp < 0) {
     const char* e = getenv("WC_ATTN_TP");
