@@ -844,6 +844,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "parity": parity,
             "secondary": secondary,
+            "peak_hbm_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
             "finite": finite,
         }
         print(json.dumps(line), flush=True)
