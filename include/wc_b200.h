@@ -133,6 +133,10 @@ int wc_nhwc_bf16_to_nchw_f32(const wc_bf16* x, float* y, int batch, int C, int h
  * tcgen05.  q,k: [B,heads,ntok,hd] bf16; vt: [B,heads,hd,ntok] bf16; out: [B,ntok,heads*hd] bf16 (ldo). */
 int wc_attention(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, int batch, int heads, int ntok,
                  int hd, int ldo, void* stream);
+/* wc_attention with an explicit softmax scale: scale > 0 replaces 1/sqrt(hd); scale == 0 is wc_attention; scale < 0 says that q
+ * already carries log2(e)/sqrt(hd) (what the UNet plan's QKV projection stores), so that exp2(q.k) is the softmax numerator. */
+int wc_attention_scaled(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, int batch, int heads, int ntok,
+                        int hd, int ldo, float scale, void* stream);
 
 /* ---- image / label edges of the loop: byte-exact replacements of the host-side PIL / numpy / torchvision
  * steps right before and after the path.  *_host pointers are HOST memory (three floats). ------------------------------ */

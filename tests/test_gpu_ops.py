@@ -231,3 +231,31 @@ def test_attention_small_heads_stale_max(hd, N, B, mode):
     lse_ref = (torch.logsumexp(s, dim=-1) * math.log2(math.e)).reshape(B * heads, N).float()
     # l is summed from bf16-rounded P: relative error <= 2^-9 per term -> absolute log2 error of a few 1e-3
     assert (lse - lse_ref).abs().max() < 2e-2 + 1e-5 * lse_ref.abs().max(), float((lse - lse_ref).abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hd,N,B,mode", [(16, 8192, 1, "plain"), (16, 2048, 2, "grow"), (16, 2504, 1, "big"), (16, 1024, 1, "grow"),
+                                          (32, 2048, 1, "plain"), (64, 1024, 1, "plain"), (128, 512, 1, "plain")])
+def test_attention_prescaled_q(hd, N, B, mode):
+    """scale < 0 (csrc/wc_host.h: kAttnScalePrescaled): Q already carries log2(e)/sqrt(hd) - what the UNet plan's QKV projection
+    stores - and every attention kernel runs with a unit log2-domain scale (head_dim 16, N >= 2048: the UNIT variant of
+    attention_small4_kernel without the per-logit multiply).  Reference: softmax over ln(2) * (q' . k) in float64."""
+    from weatherconverter_b200 import ops
+    dev = _dev()
+    heads = 4
+    g = torch.Generator(device="cpu").manual_seed(11 * hd + N)
+    q = torch.randn(B, heads, N, hd, generator=g)
+    k = torch.randn(B, heads, N, hd, generator=g)
+    v = torch.randn(B, heads, N, hd, generator=g)
+    if mode == "grow":
+        k = k * torch.linspace(0.25, 14.0, N)[None, None, :, None]
+    elif mode == "big":
+        q, k = q * 6.0, k * 6.0
+    qp = (q * (math.log2(math.e) / math.sqrt(hd))).to(dev).bfloat16()
+    k, v = k.to(dev), v.to(dev)
+    o = ops.attention(qp, k.bfloat16(), v.transpose(2, 3).contiguous().bfloat16(), scale=-1.0)
+    s = (qp.double() @ _bf(k).double().transpose(-2, -1)) * math.log(2.0)
+    ref = (torch.softmax(s, dim=-1) @ _bf(v).double()).transpose(1, 2).reshape(B, N, heads * hd).float()
+    assert torch.isfinite(o.float()).all()
+    err = _rel(o.float(), ref)
+    assert err < 1e-2, err

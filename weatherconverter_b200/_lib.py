@@ -68,6 +68,7 @@ _SIGS = {
     "wc_resample_u8": (C.c_int, [c_ptr] * 3 + [C.c_int] * 5 + [c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr]),
     "wc_u8_to_tensor": (C.c_int, [c_ptr] + [C.c_int] * 6 + [C.POINTER(C.c_float), C.POINTER(C.c_float), c_ptr, c_ptr]),
     "wc_attention_lse": (C.c_int, [c_ptr] * 5 + [C.c_int] * 5 + [c_ptr]),
+    "wc_attention_scaled": (C.c_int, [c_ptr] * 4 + [C.c_int] * 5 + [C.c_float, c_ptr]),
     "wc_attention_bwd": (C.c_int, [c_ptr] * 8 + [C.c_int] * 4 + [c_ptr]),
     "wc_conv2d_wgrad": (C.c_int, [c_ptr, c_ptr] + [C.c_int] * 10 + [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr]),
     "wc_groupnorm_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),

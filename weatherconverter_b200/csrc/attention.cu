@@ -387,7 +387,7 @@ int launch_attention_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __n
   }
   AttnArgs args;
   args.ntok = ntok; args.heads = heads; args.ldo = ldo; args.out = out; args.lse = lse;
-  args.scale_log2 = 1.4426950408889634f * (scale > 0.f ? scale : 1.f / sqrtf(static_cast<float>(HD)));
+  args.scale_log2 = attn_scale_log2(scale, HD);
   static bool attr_set = false;
   if (!attr_set) {
     WC_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<HD, BKV, NQ, POLY, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -672,7 +672,7 @@ int launch_small_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bf
   SmallArgs args;
   args.ntok = ntok; args.heads = heads; args.ldo = ldo; args.out = out; args.lse = lse;
   {
-    const float sl2 = 1.4426950408889634f * (scale > 0.f ? scale : 1.f / sqrtf(static_cast<float>(HD)));
+    const float sl2 = attn_scale_log2(scale, HD);
     int ex = 0;
     const float mant = frexpf(sl2, &ex);    // sl2 = mant * 2^ex, mant in [0.5, 1)
     args.c = mant * 2.f;

@@ -109,7 +109,7 @@ __device__ __forceinline__ float2 exp2_poly2_scaled(float2 x, float2 c, float lo
   return o;
 }
 
-template <int HD, int POLY>
+template <int HD, int POLY, bool UNIT>   // UNIT: the softmax scale is exactly 1 in the log2 domain (Q prescaled by the QKV projection)
 __global__ void __launch_bounds__(Cfg4<HD>::kThreads, 1)
 attention_small4_kernel(const __grid_constant__ Small4Maps maps, const __grid_constant__ Small4Args p) {
   using Cfg = Cfg4<HD>;
@@ -301,7 +301,7 @@ attention_small4_kernel(const __grid_constant__ Small4Maps maps, const __grid_co
       const uint32_t q_row = q_smem + q * Cfg::kQTile + row * Cfg::kRowBytes;
       const float qs = p.qscale;
 #pragma unroll
-      for (int c = 0; c < Cfg::kRowBytes / 16; ++c) {
+      for (int c = 0; c < (UNIT ? 0 : Cfg::kRowBytes / 16); ++c) {
         uint32_t v[4];
         lds128(q_row + 16 * c, v);
 #pragma unroll
@@ -348,7 +348,7 @@ attention_small4_kernel(const __grid_constant__ Small4Maps maps, const __grid_co
             if (i < POLY) {
               v = exp2_poly2_scaled(xs, cv, lo);
             } else {
-              const float2 y = fmul2(xs, cv);
+              const float2 y = UNIT ? xs : fmul2(xs, cv);
               v.x = ex2_approx(y.x);
               v.y = ex2_approx(y.y);
             }
@@ -483,7 +483,7 @@ attention_small4_kernel(const __grid_constant__ Small4Maps maps, const __grid_co
   }
 }
 
-template <int HD, int POLY>
+template <int HD, int POLY, bool UNIT>
 int launch_small4_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* vt, __nv_bfloat16* out, int B, int heads,
                     int ntok, int ldo, cudaStream_t st, float* lse, float scale) {
   using Cfg = Cfg4<HD>;
@@ -506,7 +506,7 @@ int launch_small4_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_b
   Small4Args args;
   args.ntok = ntok; args.heads = heads; args.ldo = ldo; args.out = out; args.lse = lse;
   {
-    const float sl2 = 1.4426950408889634f * (scale > 0.f ? scale : 1.f / sqrtf(static_cast<float>(HD)));
+    const float sl2 = attn_scale_log2(scale, HD);   // 1 -> c = 1, qscale = 1 (UNIT)
     int ex = 0;
     const float mant = frexpf(sl2, &ex);
     args.c = mant * 2.f;
@@ -514,14 +514,14 @@ int launch_small4_p(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_b
   }
   static bool attr_set = false;
   if (!attr_set) {
-    WC_CHECK_CUDA(cudaFuncSetAttribute(attention_small4_kernel<HD, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(attention_small4_kernel<HD, POLY, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;
   }
   const int nqb = (ntok + 128 * kNQ - 1) / (128 * kNQ);
   dim3 grid(HD == 16 ? BH : nqb, HD == 16 ? nqb : BH);
   ProfScope prof(kProfAttention, st, 4.0 * BH * static_cast<double>(ntok) * ntok * HD);
   prof.note(BH, ntok, HD);
-  launch_k<1>(attention_small4_kernel<HD, POLY>, grid, Cfg::kThreads, Cfg::kSmem, st, maps, args);
+  launch_k<1>(attention_small4_kernel<HD, POLY, UNIT>, grid, Cfg::kThreads, Cfg::kSmem, st, maps, args);
   WC_LAUNCH_CHECK();
   return 0;
 }
@@ -534,10 +534,21 @@ int launch_small4(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfl
     const char* e = getenv("WC_ATTN_SMALL4_POLY");
     poly = e ? atoi(e) : 8;   // measured best on B200 (batch 32, N 8192): 8: 2.245 ms, 12: 2.262, 16: 2.427 (head_dim 16)
   }
+  // UNIT kernels exist for head_dim 16 only (the shape this kernel is dispatched for)
+  const bool unit = (HD == 16) && attn_scale_log2(scale, HD) == 1.f;
+  if constexpr (HD == 16) {
+    if (unit) {
+      switch (poly) {
+        case 8: return launch_small4_p<HD, 8, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+        case 16: return launch_small4_p<HD, 16, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+        default: return launch_small4_p<HD, 12, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+      }
+    }
+  }
   switch (poly) {   // how many of every 32 exponentials run on the FMA pipe
-    case 8: return launch_small4_p<HD, 8>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
-    case 16: return launch_small4_p<HD, 16>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
-    default: return launch_small4_p<HD, 12>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 8: return launch_small4_p<HD, 8, false>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    case 16: return launch_small4_p<HD, 16, false>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
+    default: return launch_small4_p<HD, 12, false>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
   }
 }
 

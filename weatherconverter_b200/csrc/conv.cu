@@ -190,7 +190,7 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
   } else if (out.mode == kOutNCHWf32) {
     a.out_f32 = out.out_f32; a.n_store = out.n_store;
   } else {
-    a.q = out.q; a.k = out.k; a.vt = out.vt; a.v = out.v; a.heads = out.heads; a.hd = out.hd; a.C = out.heads * out.hd;
+    a.q = out.q; a.k = out.k; a.vt = out.vt; a.v = out.v; a.heads = out.heads; a.hd = out.hd; a.C = out.heads * out.hd; a.q_scale = out.q_scale;
     WC_REQUIRE(N == 3 * a.C, "QKV epilogue needs N == 3*C");
     WC_REQUIRE((H * W) % 8 == 0, "token count must be a multiple of 8");
   }
@@ -314,6 +314,33 @@ int build_conv_stem7s2(ConvOp* op, DeviceArena* arena, const __nv_bfloat16* xp, 
   plan.args.tma_res = 0;
   plan.args.lean = (lean_enabled() && plan.args.tma_store && !plan.args.mask && !plan.args.res) ? 1 : 0;
   plan.flops = 2.0 * 147.0 * N * static_cast<double>(B) * Ho * Wo;   // algorithmic (the reference's 7x7x3 taps), not the padded K
+  op->flops = plan.flops;
+  return 0;
+}
+
+// 1 x KW horizontal convolution ('same' size, stride 1): one tap per kernel column.  Used by the SRGAN final layer (srgan.cu), whose
+// 9x9 depthwise + 64 -> 3 pointwise pair is run as N = (kernel row, output) columns of a horizontal convolution on the tensor
+// core, followed by a vertical shift-add of the 27 fp32 planes (seg_kernels.cu: srgan_final_combine).
+int build_conv_hrow(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w, int N, const Epilogue& ep, const OutSpec& out,
+                    cudaStream_t st) {
+  WC_REQUIRE(w.KH == 1 && (w.KW & 1) == 1 && w.KW <= kMaxTaps, "build_conv_hrow: 1 x odd kernel with at most kMaxTaps columns");
+  WC_REQUIRE(x.C == in_channels_of(w), "input channels do not match the weight");
+  WC_REQUIRE(x.ld % 8 == 0, "input pixel stride must be a multiple of 8 elements");
+  op->plans.clear();
+  op->plans.emplace_back();
+  IgemmPlan& plan = op->plans.back();
+  int tb, th, tw;
+  igemm_pick_tile(x.B, x.H, x.W, &tb, &th, &tw);
+  if (int e = igemm_make_amap(&plan.maps.a[0], x, tb, th, tw)) return e;
+  for (int i = 1; i < kMaxMaps; ++i) plan.maps.a[i] = plan.maps.a[0];
+  std::vector<TapDef> taps;
+  for (int kx = 0; kx < w.KW; ++kx) taps.push_back({0, 0, kx - w.KW / 2, &w, 0, kx, x.C});
+  if (int e = finish_plan(&plan, arena, taps, x.B, x.H, x.W, tb, th, tw, N, ep, out, 1, 1, 0, 0, st)) return e;
+  plan.args.row3 = 0;
+  plan.args.nstages = igemm_stages_for(plan.args.BN, 0);
+  plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, 0, plan.args.nstages) ? 1 : 0;
+  plan.args.tma_res = (plan.args.tma_res == 2 && plan.args.stage2) ? 1 : 0;
+  plan.args.lean = (lean_enabled() && plan.args.tma_store && !plan.args.mask && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
   op->flops = plan.flops;
   return 0;
 }

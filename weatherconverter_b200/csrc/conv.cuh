@@ -58,6 +58,10 @@ struct OutSpec {
   int n_store = 0;
   __nv_bfloat16 *q = nullptr, *k = nullptr, *vt = nullptr, *v = nullptr;
   int heads = 0, hd = 0;
+  // kOutQKV: Q := q_scale * (x W_q + b_q), rounded to bf16 once.  With q_scale = log2(e) / sqrt(hd) the attention kernels run with a
+  // unit softmax scale in the log2 domain (attention_forward(.., scale = kAttnScalePrescaled)): same rounding error as storing Q
+  // unscaled, one multiply per logit less in the exponential loop.
+  float q_scale = 1.f;
   int up = 1, py = 0, px = 0;  // build_conv only: write pixel (y,x) to (y*up+py, x*up+px) of an up-times larger grid
 };
 
@@ -83,6 +87,10 @@ int build_conv_stem7s2(ConvOp* op, DeviceArena* arena, const __nv_bfloat16* xp, 
                        const float* scale, int N, const Epilogue& ep, const OutSpec& out, cudaStream_t st);
 int stem_prepare(const float* x_nchw, __nv_bfloat16* xp, int B, int H, int W, cudaStream_t st);
 int stem_weights(const float* w /*[N][3][7][7]*/, float* wprime /*[N][64][7]*/, int N, cudaStream_t st);
+
+// 1 x KW horizontal convolution (w.KH == 1, KW odd), 'same' size: see conv.cu.
+int build_conv_hrow(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w, int N, const Epilogue& ep, const OutSpec& out,
+                    cudaStream_t st);
 
 // Transposed convolution with stride 2 (ConvTranspose2d(k, 2, pad), output exactly 2x) or, equivalently, the
 // data gradient of a stride-2 convolution: out[2j+q] = sum_{k = (q+pad) mod 2 ...} in[j + (q+pad-k)/2] * W[k].

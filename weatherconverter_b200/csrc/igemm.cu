@@ -201,6 +201,10 @@ __device__ __forceinline__ void epilogue_tile(const IgemmArgs& p, uint32_t tacc,
         if (nb + j < p.n_store) op[static_cast<size_t>(nb + j) * plane] = v[j];
     } else {  // kOutQKV, NC == 16, hd % 16 == 0: a chunk never straddles a head or the q/k/v boundary
       const int which = nb / p.C, c = nb % p.C, head = c / p.hd, d = c % p.hd;
+      if (which == 0 && p.q_scale != 1.f) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) v[j] *= p.q_scale;
+      }
       const int ntok = p.H * p.W;
       const size_t tok = static_cast<size_t>(y) * p.W + x;
       const size_t bh = static_cast<size_t>(b) * p.heads + head;

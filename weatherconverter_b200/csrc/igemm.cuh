@@ -61,6 +61,7 @@ struct IgemmArgs {
   __nv_bfloat16 *q, *k, *vt;  // kOutQKV: Q,K [B,heads,ntok,hd]; V^T [B,heads,hd,ntok]
   __nv_bfloat16* v;           // kOutQKV, optional: V [B,heads,ntok,hd] as well (the attention backward reads it)
   int heads, hd, C;
+  float q_scale;               // kOutQKV: the Q columns are multiplied by this before the bf16 rounding (1: off); see OutSpec::q_scale
   // kOutNHWC through TMA (tma_store == 1; unit-stride outputs only): every epilogue warp stages its 32 rows x NC channels in
   // shared memory and one lane stores the box (NC, qw, qh, qb) = its TMEM lane quadrant of the tile with IgemmMaps::c
   int tma_store, qw, qh, qb;

@@ -848,6 +848,68 @@ srgan_final_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
   }
 }
 
+// ---- SRGAN final layer on the tensor core (round 2).  out[y][x][o] = sum_ty sum_tx sum_c in[y+ty-4][x+tx-4][c] pw[o][c] dw[c][ty][tx]
+// is split into  T[y'][x][(ty, o)] = sum_tx sum_c in[y'][x+tx-4][c] Wq[(ty, o)][c][tx]  - a 1x9 horizontal convolution with
+// N = 27 (padded to 32) output columns, run by the implicit-GEMM kernel into 27 fp32 planes - and the vertical shift-add
+// out[y][x][o] = sum_ty T[y+ty-4][x][(ty, o)] + bias, (tanh + 1)/2, done here.  36 tcgen05.mma (128x32x16) per 128 pixels replace
+// 5376 FMAs per pixel on the CUDA cores.
+__global__ void srgan_final_compose_kernel(const float* __restrict__ dw, const float* __restrict__ dwb, const float* __restrict__ pw,
+                                           const float* __restrict__ pwb, float* __restrict__ wq /*[32][64][1][9]*/,
+                                           float* __restrict__ bias3) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 32 * 64 * 9) {
+    const int tx = i % 9, c = (i / 9) % 64, n = i / (9 * 64);
+    float v = 0.f;
+    if (n < 27) {
+      const int ty = n / 3, o = n % 3;
+      v = pw[o * 64 + c] * dw[(c * 9 + ty) * 9 + tx];
+    }
+    wq[i] = v;
+  }
+  if (i < 3) {
+    float b = pwb ? pwb[i] : 0.f;
+    if (dwb)
+      for (int c = 0; c < 64; ++c) b = fmaf(pw[i * 64 + c], dwb[c], b);
+    bias3[i] = b;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+srgan_final_combine_kernel(const float* __restrict__ t /*[B][27][H][W]*/, const float* __restrict__ bias3, float* __restrict__ y /*[B][3][H][W]*/,
+                           int H, int W4) {
+  pdl_prologue();
+  const int x4 = blockIdx.x * blockDim.x + threadIdx.x;   // group of four pixels of one row
+  const int yy = blockIdx.y, b = blockIdx.z;
+  if (x4 >= W4) return;
+  const size_t plane4 = static_cast<size_t>(H) * W4;
+  const float4* tp = reinterpret_cast<const float4*>(t) + static_cast<size_t>(b) * 27 * plane4 + x4;
+  float4 acc[3];
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    const float bo = bias3[o];
+    acc[o] = make_float4(bo, bo, bo, bo);
+  }
+#pragma unroll
+  for (int ty = 0; ty < 9; ++ty) {
+    const int r = yy + ty - 4;
+    if (r < 0 || r >= H) continue;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const float4 v = __ldg(tp + static_cast<size_t>(ty * 3 + o) * plane4 + static_cast<size_t>(r) * W4);
+      acc[o].x += v.x; acc[o].y += v.y; acc[o].z += v.z; acc[o].w += v.w;
+    }
+  }
+  float4* yp = reinterpret_cast<float4*>(y) + static_cast<size_t>(b) * 3 * plane4 + static_cast<size_t>(yy) * W4 + x4;
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    float4 v;
+    v.x = (tanhf(acc[o].x) + 1.f) * 0.5f; v.y = (tanhf(acc[o].y) + 1.f) * 0.5f;
+    v.z = (tanhf(acc[o].z) + 1.f) * 0.5f; v.w = (tanhf(acc[o].w) + 1.f) * 0.5f;
+    yp[static_cast<size_t>(o) * plane4] = v;
+  }
+}
+
 __global__ void gather_stride_kernel(const float* src, float* dst, int n, int mul, int off) {
   pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -874,6 +936,19 @@ int srgan_final(const __nv_bfloat16* x, const float* dw, const float* dwb, const
   ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * H * W * (128.0 + 12.0));
   if (half) launch_k(srgan_final_kernel<true>, std::min(tiles, num_sms()), 512, smem, st, x, dw, dwb, pw, pwb, y, B, H, W, ldx);
   else launch_k(srgan_final_kernel<false>, std::min(tiles, num_sms()), 512, smem, st, x, dw, dwb, pw, pwb, y, B, H, W, ldx);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int srgan_final_compose(const float* dw, const float* dwb, const float* pw, const float* pwb, float* wq, float* bias3, cudaStream_t st) {
+  launch_k(srgan_final_compose_kernel, (32 * 64 * 9 + 255) / 256, 256, 0, st, dw, dwb, pw, pwb, wq, bias3);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+int srgan_final_combine(const float* t, const float* bias3, float* y, int B, int H, int W, cudaStream_t st) {
+  WC_REQUIRE(W % 4 == 0, "srgan_final_combine: width must be a multiple of 4");
+  const int W4 = W / 4;
+  ProfScope prof(kProfBoundaryConv, st, static_cast<double>(B) * H * W * (27.0 * 4 + 12.0));
+  launch_k(srgan_final_combine_kernel, dim3((W4 + 255) / 256, H, B), 256, 0, st, t, bias3, y, H, W4);
   WC_LAUNCH_CHECK();
   return 0;
 }

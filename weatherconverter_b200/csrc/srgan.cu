@@ -20,6 +20,8 @@ int srgan_initial(const float* x, const float* dw, const float* dwb, const float
 int srgan_final(const __nv_bfloat16* x, const float* dw, const float* dwb, const float* pw, const float* pwb, float* y, int B,
                 int H, int W, int ldx, cudaStream_t st);
 int gather_stride(const float* src, float* dst, int n, int mul, int off, cudaStream_t st);
+int srgan_final_compose(const float* dw, const float* dwb, const float* pw, const float* pwb, float* wq, float* bias3, cudaStream_t st);
+int srgan_final_combine(const float* t, const float* bias3, float* y, int B, int H, int W, cudaStream_t st);
 }  // namespace wc
 
 struct wc_srgan {
@@ -149,6 +151,15 @@ int build(wc_srgan* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
     cur = up; h *= 2; w *= 2;
   }
   // ---- final: depthwise 9x9 + pointwise 64->3 + (tanh + 1)/2, NCHW fp32 out
+  // WC_SRGAN_FINAL_TC (default 1): on the tensor core - a 1x9 horizontal convolution with N = (kernel row, output) = 27 columns
+  // into fp32 planes (igemm), then the vertical shift-add + bias + tanh (seg_kernels.cu: srgan_final_combine); 0: CUDA-core kernel
+  static int final_tc = -1;
+  if (final_tc < 0) {
+    const char* e = getenv("WC_SRGAN_FINAL_TC");
+    final_tc = e ? atoi(e) : 1;
+  }
+  const bool tc = final_tc && NCH == 64 && w % 4 == 0;
+  float* tplanes = tc ? static_cast<float*>(bump.take(static_cast<size_t>(B) * 27 * h * w * sizeof(float))) : nullptr;
   if (!dry) {
     const float *dw = P("final_conv.depthwise.weight"), *dwb = Popt("final_conv.depthwise.bias");
     const float *pw = P("final_conv.pointwise.weight"), *pwb = Popt("final_conv.pointwise.bias");
@@ -156,8 +167,25 @@ int build(wc_srgan* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
     wc_srgan* n = net;
     const Act last = cur;
     const int hh = h, ww = w;
-    push([=](cudaStream_t s) { return srgan_final(last.ptr, dw, dwb, pw, pwb, n->y_out, B, hh, ww, last.ld, s); });
-    net->flops += 2.0 * B * hh * ww * (81.0 * NCH + 3.0 * NCH);
+    const double fl = 2.0 * B * hh * ww * (81.0 * NCH + 3.0 * NCH);   // algorithmic: the reference's separable form
+    if (tc) {
+      float* wq = fa(32 * 64 * 9);
+      float* bias3 = fa(4);
+      if (!wq || !bias3) return 1;
+      if (int e = srgan_final_compose(dw, dwb, pw, pwb, wq, bias3, st)) return e;
+      WeightSrc ws_; ws_.w = wq; ws_.d0 = 32; ws_.d1 = NCH; ws_.KH = 1; ws_.KW = 9;
+      Epilogue ep;
+      OutSpec os; os.mode = kOutNCHWf32; os.out_f32 = tplanes; os.n_store = 27;
+      auto op = std::make_shared<ConvOp>();
+      if (int e = build_conv_hrow(op.get(), arena, last, ws_, 32, ep, os, st)) return e;
+      op->flops = fl;
+      for (auto& pl : op->plans) pl.flops = fl / op->plans.size();
+      net->ops.push_back([op](cudaStream_t s) { return op->run(s); });
+      push([=](cudaStream_t s) { return srgan_final_combine(tplanes, bias3, n->y_out, B, hh, ww, s); });
+    } else {
+      push([=](cudaStream_t s) { return srgan_final(last.ptr, dw, dwb, pw, pwb, n->y_out, B, hh, ww, last.ld, s); });
+    }
+    net->flops += fl;
   }
   if (dry) net->ws_needed = bump.used() + 4096;
   else if (bump.overflow()) return fail("SRGAN workspace too small");

@@ -247,6 +247,11 @@ int wc_attention(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16*
 }
 
 
+int wc_attention_scaled(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, int batch, int heads, int ntok,
+                        int hd, int ldo, float scale, void* stream) {
+  return attention_forward(BF(q), BF(k), BF(vt), BF(out), batch, heads, ntok, hd, ldo, S(stream), nullptr, scale);
+}
+
 int wc_attention_lse(const wc_bf16* q, const wc_bf16* k, const wc_bf16* vt, wc_bf16* out, float* lse, int batch, int heads,
                      int ntok, int hd, int ldo, void* stream) {
   return attention_forward(BF(q), BF(k), BF(vt), BF(out), batch, heads, ntok, hd, ldo, S(stream), lse);

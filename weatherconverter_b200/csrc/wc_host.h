@@ -9,6 +9,15 @@
 
 namespace wc {
 
+// Softmax scale of the attention kernels in the log2 domain.  scale > 0: explicit softmax scale; 0: 1/sqrt(head_dim);
+// kAttnScalePrescaled (< 0): Q already carries log2(e) * scale (OutSpec::q_scale in the QKV projection) -> exactly 1.
+constexpr float kAttnScalePrescaled = -1.f;
+inline float attn_scale_log2(float scale, int hd) {
+  if (scale < 0.f) return 1.f;
+  return 1.4426950408889634f * (scale > 0.f ? scale : 1.f / sqrtf(static_cast<float>(hd)));
+}
+
+
 // ---- error plumbing: every C-ABI entry returns 0 on success, non-zero otherwise; text via wc_last_error()
 void set_error(const std::string& msg);
 int fail(const std::string& msg);  // sets error, returns 1

@@ -88,14 +88,17 @@ def conv_out(x, weight, bias=None, tanh_out=False):
     return y
 
 
-def attention(q, k, vt):
-    """q,k [B,heads,N,hd] bf16; vt [B,heads,hd,N] bf16 -> [B,N,heads*hd] bf16."""
+def attention(q, k, vt, scale=0.0):
+    """q,k [B,heads,N,hd] bf16; vt [B,heads,hd,N] bf16 -> [B,N,heads*hd] bf16.  scale > 0: explicit softmax scale; 0: 1/sqrt(hd);
+    < 0: q already carries log2(e)/sqrt(hd) (the UNet plan's QKV projection), the kernels run with a unit log2-domain scale."""
     require_cuda(q, k, vt)
     B, h, N, hd = q.shape
     out = torch.empty(B, N, h * hd, device=q.device, dtype=torch.bfloat16)
     q, k, vt = q.contiguous(), k.contiguous(), vt.contiguous()
-    check(lib().wc_attention(ptr(q), ptr(k), ptr(vt), ptr(out), B, h, N, hd,
-                             h * hd, stream_ptr()))
+    if scale == 0.0:
+        check(lib().wc_attention(ptr(q), ptr(k), ptr(vt), ptr(out), B, h, N, hd, h * hd, stream_ptr()))
+    else:
+        check(lib().wc_attention_scaled(ptr(q), ptr(k), ptr(vt), ptr(out), B, h, N, hd, h * hd, float(scale), stream_ptr()))
     return out
 
 
