@@ -125,6 +125,17 @@ def test_loss_head():
     got = ops.to_nchw_f32(dlo)
     assert _rel(got[:, :19], lo.grad) < 5e-3
     assert float(got[:, 19:].abs().max()) == 0.0
+    # fused path (no full-resolution d-logit tensor): same pred / loss / low-resolution gradient from one kernel
+    pred2 = torch.empty_like(pred); loss2 = torch.empty_like(loss)
+    dlo2 = torch.full_like(dlo, float("nan"))
+    check(lib().wc_seg_loss_head(ptr(lo_d), ptr(lab), ptr(nv), ptr(pred2), None, ptr(loss2), None, ptr(dlo2),
+                                 B, h, w, H, W, stream_ptr()))
+    assert torch.equal(pred2, pred)
+    assert (loss2 - loss).abs().max() < 1e-5
+    got2 = ops.to_nchw_f32(dlo2)
+    assert _rel(got2[:, :19], lo.grad) < 5e-3
+    assert _rel(got2[:, :19], got[:, :19]) < 4e-3          # both are bf16 roundings of the same fp32 sums (different summation order)
+    assert float(got2[:, 19:].abs().max()) == 0.0
 
 
 def test_conv1_dgrad():

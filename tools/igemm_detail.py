@@ -38,7 +38,7 @@ for key, g in sorted(groups.items(), key=lambda kv: -kv[1][1])[:60]:
     M, N, K, BN, taps = key
     t = max(1, taps % 100)
     fl_ = taps // 1000
-    key = key + (('lean ' if fl_ & 1 else '') + ('mask ' if fl_ & 2 else '') + ('res ' if fl_ & 4 else '') + ('qkv/f32 ' if fl_ & 8 else '') + ('no-tma-store' if fl_ & 16 else ''),)
+    key = key + (('lean ' if fl_ & 1 else '') + ('deep ' if fl_ & 32 else '') + ('mask ' if fl_ & 2 else '') + ('res ' if fl_ & 4 else '') + ('qkv/f32 ' if fl_ & 8 else '') + ('no-tma-store' if fl_ & 16 else ''),)
     fl = max(g[2] / g[0] * 1e9 / 1370e12, 2.0 * (M * K / t + N * K + M * N) / 6553e9) * 1e6 * g[0]
     fl_tot += fl
     print(f"{g[1]:9.1f} {100*g[1]/tot:5.1f}% {g[0]:3d} {g[2]/g[1]*1e3:6.0f} {fl:9.1f} {g[1]/fl:7.2f}  {key}")

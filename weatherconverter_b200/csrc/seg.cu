@@ -27,6 +27,8 @@ int bilinear_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* mask, __nv_bfloat
                  int Wo, int C, int ldy, int ldm, int ldx, cudaStream_t st);
 int seg_loss_grad(const float* logits_lo, const long long* labels, int* n_valid, long long* pred, float* dlogit_hi,
                   float* loss, float* logits_hi, int B, int h, int w, int H, int W, int nc, int ignore, cudaStream_t st);
+int seg_loss_head_fused(const float* logits_lo, const long long* labels, int* n_valid, long long* pred, float* loss,
+                        __nv_bfloat16* dlo, int B, int h, int w, int H, int W, int nc, int cp, int ldo, int ignore, cudaStream_t st);
 int logits_bilinear_bwd(const float* dhi, __nv_bfloat16* dlo, int B, int h, int w, int H, int W, int nc, int cp, int ldo,
                         cudaStream_t st);
 int conv1_dgrad(const __nv_bfloat16* dz, const float* w, const float* scale, float* dx, int B, int H, int W, int Cout,
@@ -275,10 +277,26 @@ int build(wc_seg* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
   // ---------------- loss head: bilinear to the input size, argmax, softmax-CE gradient (inference.py:135-141)
   float* dlogit_hi = static_cast<float*>(b.bump.take(static_cast<size_t>(B) * H * W * NC * sizeof(float)));
   int* n_valid = static_cast<int*>(b.bump.take(B * sizeof(int)));
+  // WC_SEG_LOSS_FUSED (default 1): with the input gradient requested, pred / loss / low-resolution d-logits come from ONE kernel and the
+  // 19-plane full-resolution d-logit tensor is never written (seg_kernels.cu: seg_loss_head_fused_kernel)
+  static int loss_fused = -1;
+  if (loss_fused < 0) {
+    const char* e = getenv("WC_SEG_LOSS_FUSED");
+    loss_fused = e ? atoi(e) : 1;
+  }
+  Act dlo{};
+  if (net->with_grad) dlo = b.act(H4, W4, NCP);
   {
     wc_seg* n = net;
+    const bool with_grad = net->with_grad;
+    const int fused = loss_fused;
     b.push([=](cudaStream_t s) {
-      return seg_loss_grad(logits_lo, n->labels, n_valid, n->pred, dlogit_hi, n->loss, n->logits_hi, B, H4, W4, H, W, NC, 255, s);
+      if (with_grad && fused && !n->logits_hi) {
+        const int e = seg_loss_head_fused(logits_lo, n->labels, n_valid, n->pred, n->loss, dlo.ptr, B, H4, W4, H, W, NC, NCP, NCP, 255, s);
+        if (e != -1) return e;
+      }
+      if (int e = seg_loss_grad(logits_lo, n->labels, n_valid, n->pred, dlogit_hi, n->loss, n->logits_hi, B, H4, W4, H, W, NC, 255, s)) return e;
+      return with_grad ? logits_bilinear_bwd(dlogit_hi, dlo.ptr, B, H4, W4, H, W, NC, NCP, NCP, s) : 0;
     });
   }
   if (!net->with_grad) {
@@ -288,8 +306,6 @@ int build(wc_seg* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
   }
   // =================================================== backward (data gradients only)
   b.in_bwd = true;
-  Act dlo = b.act(H4, W4, NCP);
-  b.push([=](cudaStream_t s) { return logits_bilinear_bwd(dlogit_hi, dlo.ptr, B, H4, W4, H, W, NC, NCP, NCP, s); });
   Act dlo19 = dlo; dlo19.C = NC;
   Act dy = b.act(H4, W4, 256);
   b.dgrad(dlo19, c + ".classifier.3", "", 256, NC, 1, 1, 1, nullptr, &y, dy, nullptr, true);

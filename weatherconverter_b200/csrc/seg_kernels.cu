@@ -417,6 +417,131 @@ __global__ void logits_bilinear_bwd_kernel(const float* __restrict__ dhi, __nv_b
   }
 }
 
+// Fused loss head (round 2): seg_loss_grad_kernel + logits_bilinear_bwd_kernel without the full-resolution fp32 d-logit tensor
+// (19 planes x H x W x 4 B = 319 MB per 32 images at 256x512, written once and read once).  One block owns a tile of kLhTY x kLhTX
+// LOW-resolution pixels: phase A evaluates softmax-CE for every full-resolution pixel whose bilinear footprint touches the tile
+// (the up-sampled logits are recomputed from the low-res planes; pixels in the halo are evaluated by up to four blocks) and keeps
+// d loss / d logit_hi in shared memory; the pixels the block OWNS also give pred and the loss.  Phase B applies the adjoint of the
+// bilinear up-sampling from shared memory.  Needs integer up-sampling factors (H = fy h, W = fx w); otherwise the two-pass path runs.
+constexpr int kLhTY = 4, kLhTX = 8, kLhThreads = 256;
+template <int NC>
+__global__ void __launch_bounds__(kLhThreads)
+seg_loss_head_fused_kernel(const float* __restrict__ logits_lo, const long long* __restrict__ labels, const int* __restrict__ n_valid,
+                           long long* __restrict__ pred, float* __restrict__ loss, __nv_bfloat16* __restrict__ dlo, int h, int w,
+                           int H, int W, int fy, int fx, int RWmax, int CP, int ldo, int ignore) {
+  pdl_prologue();
+  extern __shared__ float lh_s[];   // [region pixel][NC]
+  __shared__ float lh_loss[kLhThreads / 32];
+  const int b = blockIdx.z, ty0 = blockIdx.y * kLhTY, tx0 = blockIdx.x * kLhTX;
+  const float sy = static_cast<float>(h) / H, sx = static_cast<float>(w) / W;
+  // full-resolution pixel o feeds low-resolution rows floor(src), floor(src) + 1 with src = (o + 0.5) / f - 0.5, i.e. row i is fed by
+  // o in [f i - f/2 - 0.5, f i + 3f/2 - 0.5): the bounds below are that range rounded outwards
+  const int ry0 = max(0, fy * ty0 - (fy + 1) / 2), ry1 = min(H - 1, fy * (ty0 + kLhTY - 1) + (3 * fy) / 2);
+  const int rx0 = max(0, fx * tx0 - (fx + 1) / 2), rx1 = min(W - 1, fx * (tx0 + kLhTX - 1) + (3 * fx) / 2);
+  const int RH = ry1 - ry0 + 1, RW = rx1 - rx0 + 1;
+  (void)RWmax;
+  const size_t plane = static_cast<size_t>(h) * w, plane_hi = static_cast<size_t>(H) * W;
+  const float* lb = logits_lo + static_cast<size_t>(b) * NC * plane;
+  const float invn = 1.f / static_cast<float>(max(n_valid[b], 1));
+  float lsum = 0.f;
+  // ---- phase A
+  for (int idx = threadIdx.x; idx < RH * RW; idx += kLhThreads) {
+    const int oy = ry0 + idx / RW, ox = rx0 + idx % RW;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(oy, sy, h, y0, y1, ly);
+    bilinear_src(ox, sx, w, x0, x1, lx);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    float v[NC];
+    float mx = -INFINITY;
+    int am = 0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float* pl = lb + c * plane;
+      v[c] = w00 * __ldg(pl + y0 * w + x0) + w01 * __ldg(pl + y0 * w + x1) + w10 * __ldg(pl + y1 * w + x0) + w11 * __ldg(pl + y1 * w + x1);
+      if (v[c] > mx) { mx = v[c]; am = c; }
+    }
+    const size_t hi = static_cast<size_t>(b) * plane_hi + static_cast<size_t>(oy) * W + ox;
+    const long long lab = labels[hi];
+    const bool owned = (oy / fy >= ty0) && (oy / fy < ty0 + kLhTY) && (ox / fx >= tx0) && (ox / fx < tx0 + kLhTX);
+    if (owned && pred) pred[hi] = am;
+    float* d = lh_s + static_cast<size_t>(idx) * NC;
+    if (lab == ignore) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) d[c] = 0.f;
+    } else {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) { v[c] = __expf(v[c] - mx); s += v[c]; }
+      const float inv = 1.f / s;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) d[c] = (v[c] * inv - (c == lab ? 1.f : 0.f)) * invn;
+      if (owned) lsum -= __logf(v[lab < NC && lab >= 0 ? lab : 0] * inv) * invn;
+    }
+  }
+  if (loss) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if ((threadIdx.x & 31) == 0) lh_loss[threadIdx.x >> 5] = lsum;
+  }
+  __syncthreads();
+  if (loss && threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLhThreads / 32; ++i) t += lh_loss[i];
+    if (t != 0.f) atomicAdd(loss + b, t);
+  }
+  // ---- phase B: thread = (low-res pixel of the tile, class residue mod 8)
+  const int p = threadIdx.x >> 3, k = threadIdx.x & 7;
+  const int iy = ty0 + p / kLhTX, ix = tx0 + p % kLhTX;
+  if (iy >= h || ix >= w) return;
+  float acc[3] = {0.f, 0.f, 0.f};
+  // the (at most 2f) rows / columns that feed this pixel and their weights, once per thread
+  constexpr int kMaxTap = 16;
+  float wys[kMaxTap], wxs[kMaxTap];
+  int nyt = 0, nxt = 0, oy_first = 0, ox_first = 0;
+  {
+    const int lo = max(ry0, fy * iy - (fy + 1) / 2), hi = min(ry1, fy * iy + (3 * fy) / 2);
+    oy_first = lo;
+    for (int oy = lo; oy <= hi && nyt < kMaxTap; ++oy) {
+      int y0, y1; float ly;
+      bilinear_src(oy, sy, h, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      wys[nyt++] = wy;
+    }
+  }
+  {
+    const int lo = max(rx0, fx * ix - (fx + 1) / 2), hi = min(rx1, fx * ix + (3 * fx) / 2);
+    ox_first = lo;
+    for (int ox = lo; ox <= hi && nxt < kMaxTap; ++ox) {
+      int x0, x1; float lx;
+      bilinear_src(ox, sx, w, x0, x1, lx);
+      float wx = 0.f;
+      if (x0 == ix) wx += 1.f - lx;
+      if (x1 == ix) wx += lx;
+      wxs[nxt++] = wx;
+    }
+  }
+#pragma unroll 1
+  for (int jy = 0; jy < nyt; ++jy) {
+    const float wy = wys[jy];
+    if (wy == 0.f) continue;
+    const float* drow = lh_s + (static_cast<size_t>(oy_first + jy - ry0) * RW + (ox_first - rx0)) * NC + k;
+#pragma unroll 4
+    for (int jx = 0; jx < nxt; ++jx) {
+      const float ww = wy * wxs[jx];
+      const float* d = drow + jx * NC;
+      acc[0] += ww * d[0];
+      acc[1] += ww * d[8];
+      if (k + 16 < NC) acc[2] += ww * d[16];
+    }
+  }
+  __nv_bfloat16* o = dlo + ((static_cast<size_t>(b) * h + iy) * w + ix) * ldo;
+  for (int c = k, j = 0; c < CP; c += 8, ++j) o[c] = __float2bfloat16_rn(c < NC ? acc[j] : 0.f);
+}
+
 // ---- data gradient of conv1 (7x7, stride 2, pad 3, 3 input channels) to the NCHW fp32 image:
 // dX[b,c,y,x] = sum_{ky,kx: parity ok} sum_o dZ[b,(y+3-ky)/2,(x+3-kx)/2,o] * W[o,c,ky,kx] * scale[o]
 // blockIdx.y = parity class (y&1, x&1): every thread of a block uses the same tap subset, so the weight reads are
@@ -646,6 +771,32 @@ int seg_loss_grad(const float* logits_lo, const long long* labels, int* n_valid,
   launch_k(count_valid_kernel, dim3(std::min(64, (H * W + 255) / 256), B), 256, 0, st, labels, H * W, ignore, n_valid);
   WC_LAUNCH_CHECK();
   launch_k(seg_loss_grad_kernel<19>, grid_for(static_cast<size_t>(B) * H * W, 128), 128, 0, st, logits_lo, labels, n_valid, pred, dlogit_hi, loss, logits_hi, B, h, w, H, W, ignore);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
+// Fused loss head: pred, loss and the low-resolution d-logits in one pass (see seg_loss_head_fused_kernel).  Returns -1 (nothing
+// launched) when the geometry is outside what the fused kernel covers; the caller then runs the two-pass path.
+int seg_loss_head_fused(const float* logits_lo, const long long* labels, int* n_valid, long long* pred, float* loss,
+                        __nv_bfloat16* dlo, int B, int h, int w, int H, int W, int nc, int cp, int ldo, int ignore, cudaStream_t st) {
+  WC_REQUIRE(nc == 19, "loss head is compiled for 19 classes (Cityscapes trainIds)");
+  if (H % h != 0 || W % w != 0 || cp > 32) return -1;
+  const int fy = H / h, fx = W / w;
+  if (fy > 8 || fx > 8) return -1;   // per-thread tap arrays hold 2f <= 16 rows / columns
+  const int RH = fy * (kLhTY - 1) + (3 * fy) / 2 + (fy + 1) / 2 + 1, RW = fx * (kLhTX - 1) + (3 * fx) / 2 + (fx + 1) / 2 + 1;
+  const size_t smem = static_cast<size_t>(RH) * RW * 19 * sizeof(float) + 64;
+  if (smem > 200 * 1024) return -1;
+  static size_t attr = 0;
+  if (smem > attr) {
+    WC_CHECK_CUDA(cudaFuncSetAttribute(seg_loss_head_fused_kernel<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  ProfScope prof(kProfOther, st, 0);
+  WC_CHECK_CUDA(cudaMemsetAsync(n_valid, 0, B * sizeof(int), st));
+  if (loss) WC_CHECK_CUDA(cudaMemsetAsync(loss, 0, B * sizeof(float), st));
+  launch_k(count_valid_kernel, dim3(std::min(64, (H * W + 255) / 256), B), 256, 0, st, labels, H * W, ignore, n_valid);
+  WC_LAUNCH_CHECK();
+  launch_k(seg_loss_head_fused_kernel<19>, dim3((w + kLhTX - 1) / kLhTX, (h + kLhTY - 1) / kLhTY, B), kLhThreads, smem, st, logits_lo, labels,
+           n_valid, pred, loss, dlo, h, w, H, W, fy, fx, RW, cp, ldo, ignore);
   WC_LAUNCH_CHECK();
   return 0;
 }

@@ -43,6 +43,8 @@ int bilinear_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* mask, __nv_bfloat
                  int Wo, int C, int ldy, int ldm, int ldx, cudaStream_t st);
 int seg_loss_grad(const float* logits_lo, const long long* labels, int* n_valid, long long* pred, float* dlogit_hi,
                   float* loss, float* logits_hi, int B, int h, int w, int H, int W, int nc, int ignore, cudaStream_t st);
+int seg_loss_head_fused(const float* logits_lo, const long long* labels, int* n_valid, long long* pred, float* loss,
+                        __nv_bfloat16* dlo, int B, int h, int w, int H, int W, int nc, int cp, int ldo, int ignore, cudaStream_t st);
 int logits_bilinear_bwd(const float* dhi, __nv_bfloat16* dlo, int B, int h, int w, int H, int W, int nc, int cp, int ldo,
                         cudaStream_t st);
 int conv1_dgrad(const __nv_bfloat16* dz, const float* w, const float* scale, float* dx, int B, int H, int W, int Cout,
@@ -217,6 +219,13 @@ int wc_bilinear_bwd(const wc_bf16* dy, const wc_bf16* mask, wc_bf16* dx, int bat
 }
 int wc_seg_loss_head(const float* logits_lo, const int64_t* labels, int* n_valid_ws, int64_t* pred, float* dlogit_hi,
                      float* loss, float* logits_hi, wc_bf16* dlogit_lo, int batch, int h, int w, int H, int W, void* stream) {
+  if (!dlogit_hi) {   // fused path: no full-resolution d-logit tensor (and no up-sampled logits)
+    WC_REQUIRE(dlogit_lo && !logits_hi, "wc_seg_loss_head without dlogit_hi needs dlogit_lo and no logits_hi");
+    const int e = seg_loss_head_fused(logits_lo, reinterpret_cast<const long long*>(labels), n_valid_ws, reinterpret_cast<long long*>(pred), loss,
+                                      BF(dlogit_lo), batch, h, w, H, W, 19, 32, 32, 255, S(stream));
+    if (e == -1) return fail("wc_seg_loss_head: the fused path needs integer up-sampling factors; pass dlogit_hi for the two-pass path");
+    return e;
+  }
   if (int e = seg_loss_grad(logits_lo, reinterpret_cast<const long long*>(labels), n_valid_ws,
                             reinterpret_cast<long long*>(pred), dlogit_hi, loss, logits_hi, batch, h, w, H, W, 19, 255, S(stream)))
     return e;
