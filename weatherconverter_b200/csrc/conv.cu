@@ -193,6 +193,33 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
     a.q = out.q; a.k = out.k; a.vt = out.vt; a.v = out.v; a.heads = out.heads; a.hd = out.hd; a.C = out.heads * out.hd; a.q_scale = out.q_scale;
     WC_REQUIRE(N == 3 * a.C, "QKV epilogue needs N == 3*C");
     WC_REQUIRE((H * W) % 8 == 0, "token count must be a multiple of 8");
+    // Lean epilogue with bulk-tensor stores (igemm.cu: the kOutQKV branch of epilogue_tile_lean) when a TMEM lane quadrant is 32
+    // consecutive tokens of one image and a 32-channel chunk stays inside q / k / v and inside whole heads.  WC_IGEMM_QKV_TMA=0: the
+    // per-lane scatter stores of round 1.
+    static int qkv_tma = -1;
+    if (qkv_tma < 0) {
+      const char* e = getenv("WC_IGEMM_QKV_TMA");
+      qkv_tma = e ? atoi(e) : 1;
+    }
+    const int qw = tw < 32 ? tw : 32, qh = th < 32 / qw ? th : 32 / qw, qb = 32 / (qw * qh);
+    const bool tokens_contiguous = qb == 1 && ((qh == 1 && W % qw == 0) || qw == W);
+    if (qkv_tma && lean_enabled() && !out.v && tokens_contiguous && a.C % 32 == 0 && a.BN % 32 == 0 && (out.hd == 16 || out.hd % 32 == 0)) {
+      const int hd = out.hd, heads = out.heads, ntok = H * W;
+      const uint32_t inner = hd == 16 ? 16u : 32u;
+      uint64_t dqk[4] = {static_cast<uint64_t>(hd), static_cast<uint64_t>(ntok), static_cast<uint64_t>(heads), static_cast<uint64_t>(B)};
+      uint64_t sqk[4] = {1, static_cast<uint64_t>(hd), static_cast<uint64_t>(ntok) * hd, static_cast<uint64_t>(heads) * ntok * hd};
+      uint32_t bqk[4] = {inner, 32, 1, 1};
+      if (int e = encode_tmap_bf16(&plan->maps.qkv[0], out.q, 4, dqk, sqk, bqk, inner * 2)) return e;
+      if (int e = encode_tmap_bf16(&plan->maps.qkv[1], out.k, 4, dqk, sqk, bqk, inner * 2)) return e;
+      uint64_t dv[4] = {static_cast<uint64_t>(ntok), static_cast<uint64_t>(hd), static_cast<uint64_t>(heads), static_cast<uint64_t>(B)};
+      uint64_t sv[4] = {1, static_cast<uint64_t>(ntok), static_cast<uint64_t>(ntok) * hd, static_cast<uint64_t>(heads) * ntok * hd};
+      uint32_t bv[4] = {32, inner, 1, 1};
+      if (int e = encode_tmap_bf16(&plan->maps.qkv[2], out.vt, 4, dv, sv, bv, 0)) return e;
+      plan->maps.c = plan->maps.qkv[0];
+      plan->maps.r = plan->maps.qkv[0];
+      a.tma_store = 1;
+      a.qw = qw; a.qh = qh; a.qb = qb;
+    }
   }
   const long tiles = m_tiles * ((N + a.BN - 1) / a.BN);
   plan->grid = static_cast<int>(std::min<long>(tiles, num_sms()));

@@ -256,7 +256,7 @@ __device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t 
                                                    const float* s_prelu, uint32_t tfull_addr, uint32_t tfull_parity,
                                                    const CUtensorMap* cmap, const CUtensorMap* rmap, uint32_t buf0, uint32_t buf1,
                                                    int nbuf, int qx, int qy, int qb0, uint32_t res_bar, uint32_t& res_phase,
-                                                   uint32_t& ectr) {
+                                                   uint32_t& ectr, const CUtensorMap* qkv_maps = nullptr) {
   constexpr int NV = NC / 8;
   const int lane = threadIdx.x & 31;
   const uint32_t sw = NC == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
@@ -384,6 +384,64 @@ __device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t 
         else tma_store_wait_read<0>();
       }
       __syncwarp();
+    }
+    if (NC == 32 && !RES && !MASK && p.out_mode == kOutQKV) {
+      // ---- QKV projection: the quadrant's 32 pixels are 32 consecutive tokens of image qb0 (host-checked); a 32-channel chunk lies
+      // inside q, k or v and covers two heads of 16, one head of 32 or part of a wider head.  Q / K [B,heads,N,hd]: rows of the
+      // staging block are tokens (two 1 KiB blocks of 32-byte rows for head_dim 16, else one block of 64-byte rows, as for NHWC);
+      // V^T [B,heads,hd,N]: rows of the staging block are channels, 32 tokens = 64 bytes each, written two bytes at a time
+      // (conflict-free: the 32 lanes of one store fill one row).
+      const int which = nb / p.C, c = nb - which * p.C;
+      const int tok0 = qy * p.W + qx;
+      const uint32_t blk = buf_of(ectr);
+      if (which == 0 && p.q_scale != 1.f) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) v[j] *= p.q_scale;
+      }
+      if (which < 2) {
+        if (p.hd == 16) {
+          const uint32_t s32 = (lane >> 2) & 1;   // SWIZZLE_32B: 16-byte chunk index ^ bit 7 of the address (row / 4)
+#pragma unroll
+          for (int j = 0; j < NV; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(blk + static_cast<uint32_t>(j >> 1) * 1024u + lane * 32u + ((static_cast<uint32_t>(j & 1) ^ s32) << 4)),
+                         "r"(pack_bf16(v[8 * j + 0], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
+                         "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7])) : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < NV; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(mine + ((static_cast<uint32_t>(j) ^ sw) << 4)),
+                         "r"(pack_bf16(v[8 * j + 0], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
+                         "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7])) : "memory");
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) {
+          const __nv_bfloat16 hv = __float2bfloat16_rn(v[j]);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(blk + static_cast<uint32_t>(j) * 64u + lane * 2u), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const CUtensorMap* m = qkv_maps + which;
+        if (p.hd == 16) {
+          const int head = c >> 4;
+          if (which < 2) {
+            tma_store_4d(m, blk, 0, tok0, head, qb0);
+            tma_store_4d(m, blk + 1024u, 0, tok0, head + 1, qb0);
+          } else {
+            tma_store_4d(m, blk, tok0, 0, head, qb0);
+            tma_store_4d(m, blk + 1024u, tok0, 0, head + 1, qb0);
+          }
+        } else {
+          const int head = c / p.hd, d0 = c - head * p.hd;
+          if (which < 2) tma_store_4d(m, blk, d0, tok0, head, qb0);
+          else tma_store_4d(m, blk, tok0, d0, head, qb0);
+        }
+        tma_store_commit();
+      }
+      ++ectr;
+      continue;
     }
 #pragma unroll
     for (int j = 0; j < NV; ++j)
@@ -648,7 +706,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       if (LEAN) {
         if ((p.BN % 32 == 0) && (p.N % 32 == 0))
           epilogue_tile_lean<32, TMA_RES, LEAN == 2>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
-                                          p.stage2 ? 2 : 1, x0 + qx0, y0 + qy0, b0 + qb0, res_bar, res_phase, ectr);
+                                          p.stage2 ? 2 : 1, x0 + qx0, y0 + qy0, b0 + qb0, res_bar, res_phase, ectr, maps.qkv);
         else
           epilogue_tile_lean<16, TMA_RES, LEAN == 2>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
                                           p.stage2 ? 2 : 1, x0 + qx0, y0 + qy0, b0 + qb0, res_bar, res_phase, ectr);

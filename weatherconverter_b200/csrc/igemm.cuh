@@ -82,6 +82,7 @@ struct IgemmMaps {
   CUtensorMap b;
   CUtensorMap c;   // output (tma_store)
   CUtensorMap r;   // residual (tma_res)
+  CUtensorMap qkv[3];   // kOutQKV through the lean epilogue: Q, K as (hd, N, heads, B), V^T as (N, hd, heads, B)
 };
 
 struct IgemmPlan {
