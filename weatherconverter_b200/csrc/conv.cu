@@ -189,6 +189,22 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
     }
   } else if (out.mode == kOutNCHWf32) {
     a.out_f32 = out.out_f32; a.n_store = out.n_store;
+    // lean epilogue with bulk-tensor stores of [16 planes][32 pixels] fp32 boxes (igemm.cu) when a TMEM lane quadrant is 32 consecutive
+    // pixels of one image row; the map addresses the fp32 planes as bf16 pairs.  WC_IGEMM_F32_TMA=0: per-lane stores.
+    static int f32_tma = -1;
+    if (f32_tma < 0) {
+      const char* e = getenv("WC_IGEMM_F32_TMA");
+      f32_tma = e ? atoi(e) : 1;
+    }
+    if (f32_tma && lean_enabled() && sy == 1 && sx == 1 && tw >= 32 && W % 32 == 0 && (W * 2) % 8 == 0 && !ep.res && !ep.mask) {
+      uint64_t dims[4] = {static_cast<uint64_t>(2 * W), static_cast<uint64_t>(H), static_cast<uint64_t>(out.n_store), static_cast<uint64_t>(B)};
+      uint64_t strides[4] = {1, static_cast<uint64_t>(2 * W), static_cast<uint64_t>(2 * W) * H, static_cast<uint64_t>(2 * W) * H * out.n_store};
+      uint32_t box[4] = {64, 1, 16, 1};
+      if (int e = encode_tmap_bf16(&plan->maps.c, out.out_f32, 4, dims, strides, box, 0)) return e;
+      plan->maps.r = plan->maps.c;
+      a.tma_store = 1;
+      a.qw = 32; a.qh = 1; a.qb = 1;
+    }
   } else {
     a.q = out.q; a.k = out.k; a.vt = out.vt; a.v = out.v; a.heads = out.heads; a.hd = out.hd; a.C = out.heads * out.hd; a.q_scale = out.q_scale;
     WC_REQUIRE(N == 3 * a.C, "QKV epilogue needs N == 3*C");
@@ -278,6 +294,7 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   }
   if (int e = finish_plan(&plan, arena, taps, B, H, W, tb, th, tw, N, ep, out, out.up, out.up, out.py, out.px, st)) return e;
   plan.args.row3 = (want_row3 && plan.args.BN <= 128) ? row3_mode() : 0;
+  plan.args.row_nky = plan.args.row_nkx = 3;
   int wres_bytes = 0;
   {
     // resident weights: one N tile, the packed matrix fits next to a useful ring, and every CTA processes several tiles
@@ -363,9 +380,36 @@ int build_conv_hrow(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSr
   std::vector<TapDef> taps;
   for (int kx = 0; kx < w.KW; ++kx) taps.push_back({0, 0, kx - w.KW / 2, &w, 0, kx, x.C});
   if (int e = finish_plan(&plan, arena, taps, x.B, x.H, x.W, tb, th, tw, N, ep, out, 1, 1, 0, 0, st)) return e;
+  // Row-segment mode with all KW taps in one stage (WC_HROW_SEG=0: one stage per tap): one box of 128 + KW - 1 pixels per tile instead
+  // of KW boxes of 128, one barrier hand-over per tile instead of KW
+  static int hseg = -1;
+  if (hseg < 0) {
+    const char* e = getenv("WC_HROW_SEG");
+    hseg = e ? atoi(e) : 1;
+  }
   plan.args.row3 = 0;
-  plan.args.nstages = igemm_stages_for(plan.args.BN, 0);
-  plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, 0, plan.args.nstages) ? 1 : 0;
+  plan.args.row_nky = 1; plan.args.row_nkx = w.KW;
+  if (hseg && row3_enabled() && tw == 128 && th == 1 && tb == 1 && plan.args.BN <= 128 && igemm_stages_for(plan.args.BN, 1, 0, w.KW) >= 2) {
+    if (int e = igemm_make_rowseg_map(&plan.maps.a[2], x, w.KW)) return e;
+    plan.args.row3 = row3_mode();
+  }
+  // the packed weights of all taps (KW x BN x 64 bf16) are the same for every tile: keep them resident (one load per CTA) when this
+  // is a single N tile - the ring then carries activations only
+  int wres_bytes = 0;
+  {
+    static int hres = -1;
+    if (hres < 0) {
+      const char* e = getenv("WC_HROW_WRES");
+      hres = e ? atoi(e) : 1;
+    }
+    const long wb = static_cast<long>(plan.args.BN) * plan.args.total_kb * kIgemmBK * 2;
+    if (hres && plan.args.row3 && plan.args.BN >= N && wb <= kIgemmWresMaxBytes) {
+      plan.args.wres = 1;
+      wres_bytes = static_cast<int>(wb);
+    }
+  }
+  plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3, wres_bytes, w.KW);
+  plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, plan.args.row3, plan.args.nstages, wres_bytes, w.KW) ? 1 : 0;
   plan.args.tma_res = (plan.args.tma_res == 2 && plan.args.stage2) ? 1 : 0;
   plan.args.lean = (lean_enabled() && plan.args.tma_store && !plan.args.mask && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
   op->flops = plan.flops;

@@ -25,7 +25,6 @@ constexpr uint32_t kTmemCols = 512;
 // Row-segment mode (3x3, stride 1, dilation 1, tiles of 128 pixels of ONE image row): per (channel block, ky) one TMA
 // box of 130 pixels [x0-1, x0+129) is loaded once and the three kx taps read it through UMMA descriptors whose start is
 // shifted by kx*128 bytes (base_offset = kx keeps the 128-byte swizzle phase right) -> A traffic / 3.
-constexpr uint32_t kRowSegPixels = 130;
 constexpr uint32_t kRowABytes = 18432;                       // 130*128 = 16640, padded to a multiple of 1024
 
 template <int NC>
@@ -385,6 +384,22 @@ __device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t 
       }
       __syncwarp();
     }
+    if (NC == 16 && !RES && !MASK && p.out_mode == kOutNCHWf32) {
+      // ---- fp32 planes [B, n_store, H, W] through a bulk-tensor store: the staging block is [16 planes][32 pixels] fp32 (2 KiB), the
+      // tensor map sees the planes as bf16 pairs (a pure byte mover); planes beyond n_store are clipped by the TMA
+      const uint32_t blk = buf_of(ectr);
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(blk + static_cast<uint32_t>(j) * 128u + lane * 4u), "r"(__float_as_uint(v[j])) : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(cmap, blk, 2 * qx, qy, nb, qb0);
+        tma_store_commit();
+      }
+      ++ectr;
+      continue;
+    }
     if (NC == 32 && !RES && !MASK && p.out_mode == kOutQKV) {
       // ---- QKV projection: the quadrant's 32 pixels are 32 consecutive tokens of image qb0 (host-checked); a 32-channel chunk lies
       // inside q, k or v and covers two heads of 16, one head of 32 or part of a wider head.  Q / K [B,heads,N,hd]: rows of the
@@ -467,7 +482,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   constexpr uint32_t kAOff = ROW3 ? kRowABytes : kABytes;   // offset of the B tile(s) inside a stage
   const int kStages = p.nstages;
   const uint32_t kBTile = static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
-  const uint32_t kStageSz = kAOff + (p.wres ? 0u : (ROW3 ? 3u : 1u) * kBTile);
+  const uint32_t kStageSz = kAOff + (p.wres ? 0u : (ROW3 ? static_cast<uint32_t>(p.row_nkx) : 1u) * kBTile);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t wres_base = smem_base + static_cast<uint32_t>(kStages) * kStageSz;   // resident weights sit right behind the ring
   const uint32_t bar_base = smem_base + kPipeBytes + kOutStageBytes;   // [ring | output staging | barriers | bias / PReLU]
@@ -568,26 +583,29 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         int kb_global = 0;
         int t_first = 0;
         if (ROW3) {
-          // taps 0..8 are the 3x3 window (ky-major) over map 0, all with nkb = p.taps[0].nkb channel blocks
+          // taps 0 .. nky*nkx-1 are the window (ky-major) over map 0, all with nkb = p.taps[0].nkb channel blocks; one box of
+          // 128 + nkx - 1 pixels of an image row serves the nkx horizontal taps (3x3: nky = nkx = 3; 1x9: nky = 1, nkx = 9)
           const int nkb = p.taps[0].nkb;
+          const int nky = p.row_nky, nkx = p.row_nkx;
           const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
-          for (int ky = 0; ky < 3; ++ky)
+          const uint32_t a_bytes = static_cast<uint32_t>(128 + nkx - 1) * 128u;
+          for (int ky = 0; ky < nky; ++ky)
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               if (elect_one_sync()) {
                 trace(0, 1);
                 const uint32_t sa = smem_base + stage * kStageSz;
-                mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0u : kRowSegPixels * 128u) + (((p.dbg & 4) || p.wres) ? 0u : 3u * b_bytes));
-                if (!(p.dbg & 8)) tma_load_4d(sa, &maps.a[2], full_bar(stage), kb * kIgemmBK, x0 - 1, y0 + ky - 1, b0);
-                for (int kx = 0; kx < 3 && !(p.dbg & 4) && !p.wres; ++kx)
-                  tma_load_2d(sa + kAOff + kx * b_bytes, &maps.b, full_bar(stage), ((ky * 3 + kx) * nkb + kb) * kIgemmBK, n0);
+                mbar_arrive_expect_tx(full_bar(stage), ((p.dbg & 8) ? 0u : a_bytes) + (((p.dbg & 4) || p.wres) ? 0u : static_cast<uint32_t>(nkx) * b_bytes));
+                if (!(p.dbg & 8)) tma_load_4d(sa, &maps.a[2], full_bar(stage), kb * kIgemmBK, x0 - nkx / 2, y0 + ky - nky / 2, b0);
+                for (int kx = 0; kx < nkx && !(p.dbg & 4) && !p.wres; ++kx)
+                  tma_load_2d(sa + kAOff + kx * b_bytes, &maps.b, full_bar(stage), ((ky * nkx + kx) * nkb + kb) * kIgemmBK, n0);
                 trace(0, 2);
               }
               __syncwarp();
               if (++stage == kStages) { stage = 0; phase ^= 1u; }
             }
-          t_first = 9;
-          kb_global = 9 * nkb;
+          t_first = nky * nkx;
+          kb_global = nky * nkx * nkb;
         }
         for (int t = t_first; t < p.ntaps; ++t) {
           const IgemmTap tap = p.taps[t];
@@ -628,7 +646,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(a) * 256u;
         int ks_first = 0;
         if (ROW3) {
-          const int nseg = 3 * p.taps[0].nkb;
+          const int nkx = p.row_nkx;
+          const int nseg = p.row_nky * p.taps[0].nkb;
           for (int sg = 0; sg < nseg; ++sg) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
@@ -637,10 +656,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
               // stage sg = (ky, kb): its three B tiles are k-blocks (ky*3 + kx) * nkb + kb of the packed weights
               const int nkb3 = p.taps[0].nkb, ky3 = sg / nkb3, kb3 = sg - ky3 * nkb3;
               const uint32_t a_lo = a_lo0 + stage * stage16;
-              const uint32_t b_lo = p.wres ? w_lo0 + static_cast<uint32_t>(ky3 * 3 * nkb3 + kb3) * bt16 : b_lo0 + stage * stage16;
+              const uint32_t b_lo = p.wres ? w_lo0 + static_cast<uint32_t>(ky3 * nkx * nkb3 + kb3) * bt16 : b_lo0 + stage * stage16;
               const uint32_t bkx16 = p.wres ? static_cast<uint32_t>(nkb3) * bt16 : bt16;
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll 3
+              for (int kx = 0; kx < nkx; ++kx) {
                 // window of 128 pixels starting kx pixels (kx*128 B = 8 descriptor units) into the 130-pixel segment; the
                 // UMMA swizzle is a function of the absolute shared-memory address, so the shifted start needs no fix-up
 #pragma unroll
@@ -655,7 +674,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          ks_first = 9 * p.taps[0].nkb;
+          ks_first = p.row_nky * nkx * p.taps[0].nkb;
         }
         for (int ks = ks_first; ks < p.total_kb; ++ks) {
           mbar_wait(full_bar(stage), phase);
@@ -704,13 +723,14 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       const uint32_t tacc = tmem_base + static_cast<uint32_t>(a) * 256u + (static_cast<uint32_t>(quad * 32) << 16);
       if (warp == 2 && lane == 0) trace(2, 20);
       if (LEAN) {
-        if ((p.BN % 32 == 0) && (p.N % 32 == 0))
+        if ((p.BN % 32 == 0) && (p.N % 32 == 0) && p.out_mode != kOutNCHWf32)
           epilogue_tile_lean<32, TMA_RES, LEAN == 2>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
                                           p.stage2 ? 2 : 1, x0 + qx0, y0 + qy0, b0 + qb0, res_bar, res_phase, ectr, maps.qkv);
         else
           epilogue_tile_lean<16, TMA_RES, LEAN == 2>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
                                           p.stage2 ? 2 : 1, x0 + qx0, y0 + qy0, b0 + qb0, res_bar, res_phase, ectr);
-      } else if (p.out_mode != kOutQKV && (p.BN % 32 == 0) && (p.N % 32 == 0))
+      } else if (p.out_mode != kOutQKV && (p.BN % 32 == 0) && (p.N % 32 == 0) && !(p.out_mode == kOutNCHWf32 && p.BN == 32))
+        // (fp32 planes with a single 32-column N tile: 16-column chunks keep BOTH epilogue groups busy)
         epilogue_tile<32, TMA_OUT, TMA_RES>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, out_stage, x0 + qx0,
                           y0 + qy0, b0 + qb0, &maps.r, res_stage, res_bar, res_phase);
       else
@@ -734,20 +754,20 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
 
 // wres_bytes > 0: resident weights (that many bytes behind the ring), stages carry activations only; 16 KiB are then always
 // left for the second staging buffer of the lean epilogue
-int igemm_stages_for(int BN, int row3, int wres_bytes) {
+int igemm_stages_for(int BN, int row3, int wres_bytes, int row_nkx) {
   if (wres_bytes > 0) {
     const uint32_t stage = row3 ? kRowABytes : kABytes;
     int n = static_cast<int>((kPipeBytes - kOutStageBytes - static_cast<uint32_t>(wres_bytes)) / stage);
     return n > kMaxStages ? kMaxStages : n;
   }
-  const uint32_t stage = (row3 ? kRowABytes : kABytes) + (row3 ? 3u : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2;
+  const uint32_t stage = (row3 ? kRowABytes : kABytes) + (row3 ? static_cast<uint32_t>(row_nkx) : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2;
   // stages must stay 1024-byte aligned: BN is a multiple of 16 -> BN*128 is a multiple of 2048
   int n = static_cast<int>(kPipeBytes / stage);
   return n > kMaxStages ? kMaxStages : n;
 }
 
-bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes) {
-  const uint32_t stage = (row3 ? kRowABytes : kABytes) + (wres_bytes > 0 ? 0u : (row3 ? 3u : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2);
+bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes, int row_nkx) {
+  const uint32_t stage = (row3 ? kRowABytes : kABytes) + (wres_bytes > 0 ? 0u : (row3 ? static_cast<uint32_t>(row_nkx) : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2);
   return static_cast<uint32_t>(nstages) * stage + static_cast<uint32_t>(wres_bytes > 0 ? wres_bytes : 0) + kOutStageBytes <= kPipeBytes;
 }
 
@@ -831,12 +851,13 @@ int igemm_make_amap(CUtensorMap* out, const Act& act, int tb, int th, int tw, in
   return encode_tmap_bf16(out, base, 4, dims, strides, box, 128);
 }
 
-int igemm_make_rowseg_map(CUtensorMap* out, const Act& act) {
+int igemm_make_rowseg_map(CUtensorMap* out, const Act& act, int nkx) {
+  WC_REQUIRE(nkx >= 1 && (128u + nkx - 1) * 128u <= kRowABytes, "row segment does not fit its stage slot");
   uint64_t dims[4] = {static_cast<uint64_t>(act.C), static_cast<uint64_t>(act.W), static_cast<uint64_t>(act.H),
                       static_cast<uint64_t>(act.B)};
   uint64_t strides[4] = {1, static_cast<uint64_t>(act.ld), static_cast<uint64_t>(act.ld) * act.W,
                          static_cast<uint64_t>(act.ld) * act.W * act.H};
-  uint32_t box[4] = {static_cast<uint32_t>(kIgemmBK), kRowSegPixels, 1, 1};
+  uint32_t box[4] = {static_cast<uint32_t>(kIgemmBK), static_cast<uint32_t>(128 + nkx - 1), 1, 1};
   return encode_tmap_bf16(out, act.ptr, 4, dims, strides, box, 128);
 }
 

@@ -61,6 +61,7 @@ struct IgemmArgs {
   __nv_bfloat16 *q, *k, *vt;  // kOutQKV: Q,K [B,heads,ntok,hd]; V^T [B,heads,hd,ntok]
   __nv_bfloat16* v;           // kOutQKV, optional: V [B,heads,ntok,hd] as well (the attention backward reads it)
   int heads, hd, C;
+  int row_nky, row_nkx;        // row-segment mode: the window is row_nky x row_nkx taps (3 x 3, or 1 x 9 for build_conv_hrow)
   float q_scale;               // kOutQKV: the Q columns are multiplied by this before the bf16 rounding (1: off); see OutSpec::q_scale
   // kOutNHWC through TMA (tma_store == 1; unit-stride outputs only): every epilogue warp stages its 32 rows x NC channels in
   // shared memory and one lane stores the box (NC, qw, qh, qb) = its TMEM lane quadrant of the tile with IgemmMaps::c
@@ -93,9 +94,9 @@ struct IgemmPlan {
 };
 
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
-int igemm_stages_for(int BN, int row3, int wres_bytes = 0);
+int igemm_stages_for(int BN, int row3, int wres_bytes = 0, int row_nkx = 3);
 // true if 16 KiB stay free behind `nstages` stages of the TMA ring (room for the residual staging of the TMA epilogue)
-bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes = 0);
+bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes = 0, int row_nkx = 3);
 
 // Choose the M-tile shape for a (B,H,W) grid: widest power-of-two span of x, then y, then b.
 void igemm_pick_tile(int B, int H, int W, int* tb, int* th, int* tw);
@@ -106,7 +107,7 @@ int igemm_pick_bn(int N, long m_tiles);
 int igemm_make_amap(CUtensorMap* out, const Act& act, int tb, int th, int tw, int y0 = 0, int ys = 1, int x0 = 0,
                     int xs = 1, int Hv = -1, int Wv = -1);
 // Row-segment A map (box 64 ch x 130 pixels of one image row) for the row3 mode.
-int igemm_make_rowseg_map(CUtensorMap* out, const Act& act);
+int igemm_make_rowseg_map(CUtensorMap* out, const Act& act, int nkx = 3);
 int igemm_make_bmap(CUtensorMap* out, const __nv_bfloat16* wpacked, int n_rows, int ktotal, int BN);
 // Output map for the TMA-store epilogue: channels [0, N) of an NHWC view, box (nc, qw, qh, qb), swizzle = nc*2 bytes.
 int igemm_make_cmap(CUtensorMap* out, const Act& act, int N, int nc, int qw, int qh, int qb, int sy = 1, int sx = 1, int py = 0,
