@@ -444,7 +444,12 @@ int attention_forward(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv
     // Measured on B200 (batch 32, N 8192): head_dim 16 2.42 -> 2.24 ms with four groups; head_dim 32 2.35 (three groups, P' in
     // tensor memory) vs 2.41 (four groups, P' through shared memory) -> head_dim 32 keeps the 3-group kernel.  Four groups per
     // CTA cover 512 queries: shorter sequences keep the 3-group kernel too.
-    if (four && hd == 16 && ntok >= 2048) return attention_small4_forward(q, k, vt, out, B, heads, ntok, hd, ldo, st, lse, scale);
+    static int four32 = -1;   // WC_ATTN_SMALL4_HD32: head_dim 32 through the four-group kernel as well (row sums on the tensor core there too)
+    if (four32 < 0) {
+      const char* e = getenv("WC_ATTN_SMALL4_HD32");
+      four32 = e ? atoi(e) : 1;
+    }
+    if (four && (hd == 16 || (hd == 32 && four32)) && ntok >= 2048) return attention_small4_forward(q, k, vt, out, B, heads, ntok, hd, ldo, st, lse, scale);
     return attention_small_forward(q, k, vt, out, B, heads, ntok, hd, ldo, st, lse, scale);
   }
   static int tp = -1;   // WC_ATTN_TP=0: P through shared memory (previous design); default: P in tensor memory

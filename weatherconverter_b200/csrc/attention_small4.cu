@@ -54,7 +54,7 @@ static_assert(128 * kRegsService + 512 * kRegsSoftmax <= 640 * 96, "register poo
 
 template <int HD>
 struct Cfg4 {
-  static constexpr bool kLT = (HD == 16);                       // row sums on the tensor core
+  static constexpr bool kLT = true;                             // row sums on the tensor core: 4 x (64 + hd + 16) <= 512 columns for hd 16 and 32
   static constexpr int kRowBytes = HD * 2;
   static constexpr int kSwz = HD * 2;
   static constexpr int kKSteps = HD / 16;
@@ -534,9 +534,8 @@ int launch_small4(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfl
     const char* e = getenv("WC_ATTN_SMALL4_POLY");
     poly = e ? atoi(e) : 8;   // measured best on B200 (batch 32, N 8192): 8: 2.245 ms, 12: 2.262, 16: 2.427 (head_dim 16)
   }
-  // UNIT kernels exist for head_dim 16 only (the shape this kernel is dispatched for)
-  const bool unit = (HD == 16) && attn_scale_log2(scale, HD) == 1.f;
-  if constexpr (HD == 16) {
+  const bool unit = attn_scale_log2(scale, HD) == 1.f;
+  {
     if (unit) {
       switch (poly) {
         case 8: return launch_small4_p<HD, 8, true>(q, k, vt, out, B, heads, ntok, ldo, st, lse, scale);
