@@ -98,6 +98,8 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
   const int ktotal = total_kb * kIgemmBK;
   const long m_tiles = static_cast<long>((W + tw - 1) / tw) * ((H + th - 1) / th) * ((B + tb - 1) / tb);
   a.BN = igemm_pick_bn(N, m_tiles);
+  if (out.bn_max > 0 && a.BN > out.bn_max) a.BN = out.bn_max;
+  if (out.phases == 4) a.BN = (a.BN + 31) / 32 * 32;   // phase blocks are stored in 32-channel chunks
   if (out.mode == kOutQKV) {
     WC_REQUIRE(out.hd % 16 == 0, "head_dim must be a multiple of 16");
   }
@@ -153,7 +155,24 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
   a.out_mode = out.mode;
   a.sy = sy; a.sx = sx; a.py = py; a.px = px;
   a.Ho = H * sy; a.Wo = W * sx;
-  if (out.mode == kOutNHWC) {
+  if (out.mode == kOutNHWC && out.phases == 4) {
+    // four phase blocks of N/4 channels, one strided output map per phase; lean epilogue only (igemm.cu)
+    const int pn = N / 4;
+    WC_REQUIRE(sy == 2 && sx == 2 && N % 128 == 0 && a.BN % 32 == 0 && lean_enabled(), "phase-block output needs up == 2, N % 128 == 0 and the lean epilogue");
+    WC_REQUIRE(out.out.ptr && out.out.B == B && out.out.H == a.Ho && out.out.W == a.Wo && out.out.ld % 8 == 0 && !ep.res && !ep.mask, "phase-block output grid mismatch");
+    a.out = out.out.ptr; a.ldc = out.out.ld;
+    a.qw = tw < 32 ? tw : 32;
+    a.qh = th < 32 / a.qw ? th : 32 / a.qw;
+    a.qb = 32 / (a.qw * a.qh);
+    WC_REQUIRE(a.qb <= tb, "phase-block output: tile too small");
+    for (int q = 0; q < 4; ++q) {
+      CUtensorMap* m = q == 0 ? &plan->maps.c : &plan->maps.qkv[q - 1];
+      if (int e = igemm_make_cmap(m, out.out, pn, 32, a.qw, a.qh, a.qb, 2, 2, q / 2, q % 2)) return e;
+    }
+    plan->maps.r = plan->maps.c;
+    a.tma_store = 1;
+    a.phase_n = pn;
+  } else if (out.mode == kOutNHWC) {
     WC_REQUIRE(out.out.ptr && out.out.B == B && out.out.H == a.Ho && out.out.W == a.Wo, "output grid mismatch");
     WC_REQUIRE(out.out.ld % 8 == 0, "output pixel stride must be a multiple of 8");
     a.out = out.out.ptr; a.ldc = out.out.ld;
@@ -272,7 +291,7 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
     }
     for (int i = nmaps; i < kMaxMaps; ++i) plan.maps.a[i] = plan.maps.a[0];
     // Row-segment mode: 3x3 / dilation 1 on maps at least 128 pixels wide with narrow N (the L2->SM bound layers)
-    if (g.K == 3 && g.dil == 1 && tw == 128 && th == 1 && tb == 1 && N <= 128 && row3_enabled()) {
+    if (g.K == 3 && g.dil == 1 && tw == 128 && th == 1 && tb == 1 && (N <= 128 || (out.bn_max > 0 && out.bn_max <= 128)) && row3_enabled()) {
       if (int e = igemm_make_rowseg_map(&plan.maps.a[2], x)) return e;
       want_row3 = true;
     }

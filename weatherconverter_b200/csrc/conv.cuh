@@ -63,6 +63,10 @@ struct OutSpec {
   // unscaled, one multiply per logit less in the exponential loop.
   float q_scale = 1.f;
   int up = 1, py = 0, px = 0;  // build_conv only: write pixel (y,x) to (y*up+py, x*up+px) of an up-times larger grid
+  // build_conv only, with up == 2: the N output columns are FOUR PHASE BLOCKS of N/4 channels; block q goes to (y*2 + q/2, x*2 + q%2)
+  // (PixelShuffle with phase-major weight rows: one launch instead of four, the activation tile is read once)
+  int phases = 0;
+  int bn_max = 0;              // > 0: cap on the N tile (lets a 3x3 layer with N > 128 keep the row-segment mode)
 };
 
 // One logical layer = one or more igemm launches (4 for stride-2 transposed / dgrad convs).

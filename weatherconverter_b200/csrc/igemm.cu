@@ -466,7 +466,12 @@ __device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t 
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_4d(cmap, buf_of(ectr), nb, qx, qy, qb0);
+      if (p.phase_n > 0) {   // phase-block output (PixelShuffle): block nb / phase_n has its own strided map
+        const int ph = nb / p.phase_n;
+        tma_store_4d(ph == 0 ? cmap : qkv_maps + (ph - 1), buf_of(ectr), nb - ph * p.phase_n, qx, qy, qb0);
+      } else {
+        tma_store_4d(cmap, buf_of(ectr), nb, qx, qy, qb0);
+      }
       tma_store_commit();
     }
     ++ectr;

@@ -1061,6 +1061,16 @@ srgan_final_combine_kernel(const float* __restrict__ t /*[B][27][H][W]*/, const 
   }
 }
 
+// PixelShuffle(r = 2) as phase-major output rows: dst row q*cb + c = src row c*4 + q (rows of `len` floats); with rep_src = 1 the
+// source has only cb rows and is replicated to every phase (per-channel PReLU slopes).
+__global__ void phase_major_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int cb, int len, int rep_src) {
+  pdl_prologue();
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(4) * cb * len) return;
+  const int e = static_cast<int>(i % len), n = static_cast<int>(i / len), q = n / cb, c = n % cb;
+  dst[i] = src[static_cast<size_t>(rep_src ? c : c * 4 + q) * len + e];
+}
+
 __global__ void gather_stride_kernel(const float* src, float* dst, int n, int mul, int off) {
   pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1167,6 +1177,12 @@ int srgan_initial(const float* x, const float* dw, const float* dwb, const float
   return 0;
 }
 
+int phase_major_rows(const float* src, float* dst, int cb, int len, int rep_src, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(4) * cb * len;
+  launch_k(phase_major_rows_kernel, static_cast<int>((total + 255) / 256), 256, 0, st, src, dst, cb, len, rep_src);
+  WC_LAUNCH_CHECK();
+  return 0;
+}
 int gather_stride(const float* src, float* dst, int n, int mul, int off, cudaStream_t st) {
   launch_k(gather_stride_kernel, (n + 255) / 256, 256, 0, st, src, dst, n, mul, off);
   WC_LAUNCH_CHECK();

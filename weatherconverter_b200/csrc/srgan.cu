@@ -20,6 +20,7 @@ int srgan_initial(const float* x, const float* dw, const float* dwb, const float
 int srgan_final(const __nv_bfloat16* x, const float* dw, const float* dwb, const float* pw, const float* pwb, float* y, int B,
                 int H, int W, int ldx, cudaStream_t st);
 int gather_stride(const float* src, float* dst, int n, int mul, int off, cudaStream_t st);
+int phase_major_rows(const float* src, float* dst, int cb, int len, int rep_src, cudaStream_t st);
 int srgan_final_compose(const float* dw, const float* dwb, const float* pw, const float* pwb, float* wq, float* bias3, cudaStream_t st);
 int srgan_final_combine(const float* t, const float* bias3, float* y, int B, int H, int W, cudaStream_t st);
 }  // namespace wc
@@ -132,6 +133,32 @@ int build(wc_srgan* net, bool dry, void* ws, size_t ws_bytes, cudaStream_t st) {
       Composed c = compose(p + ".conv", NCH, NCH * 4, 3, "");
       const float* slope = P(p + ".act.weight");
       if (err) return err;
+      static int merged = -1;   // WC_SRGAN_UP_MERGED=0: one launch per PixelShuffle phase (round 1)
+      if (merged < 0) {
+        const char* e = getenv("WC_SRGAN_UP_MERGED");
+        merged = e ? atoi(e) : 1;
+      }
+      if (merged && NCH % 32 == 0) {
+        // ONE launch for the four phases: weight rows, bias and PReLU slopes re-ordered phase-major (row q*64 + c = conv channel 4c + q),
+        // N tile 128 so that the row-segment mode applies; every 32-channel chunk is stored through the strided map of its phase
+        float* wpm = fa(static_cast<size_t>(NCH) * 4 * NCH * 9);
+        float* bpm = fa(NCH * 4);
+        float* spm = fa(NCH * 4);
+        if (!wpm || !bpm || !spm) return 1;
+        if (int e = phase_major_rows(c.w, wpm, NCH, NCH * 9, 0, st)) return e;
+        if (int e = phase_major_rows(c.bias, bpm, NCH, 1, 0, st)) return e;
+        if (int e = phase_major_rows(slope, spm, NCH, 1, 1, st)) return e;
+        WeightSrc ws_; ws_.w = wpm; ws_.d0 = NCH * 4; ws_.d1 = NCH; ws_.KH = ws_.KW = 3;
+        ConvGeom g; g.K = 3; g.pad = 1;
+        Epilogue ep; ep.bias = bpm; ep.prelu = spm;
+        OutSpec os; os.mode = kOutNHWC; os.out = up; os.up = 2; os.phases = 4; os.bn_max = 128;
+        auto op = std::make_shared<ConvOp>();
+        if (int e = build_conv(op.get(), arena, cur, ws_, g, NCH * 4, nullptr, nullptr, ep, os, st)) return e;
+        op->flops = 2.0 * cur.pixels() * (9.0 * NCH + static_cast<double>(NCH) * NCH * 4);
+        for (auto& pl : op->plans) pl.flops = op->flops / op->plans.size();
+        net->flops += op->flops;
+        net->ops.push_back([op](cudaStream_t s) { return op->run(s); });
+      } else
       for (int q = 0; q < 4; ++q) {   // PixelShuffle: out[c, 2y+i, 2x+j] = conv[4c + 2i + j, y, x]
         float* bq = fa(NCH);
         if (!bq) return 1;
