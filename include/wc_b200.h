@@ -121,7 +121,9 @@ int wc_bilinear_bwd(const wc_bf16* dy, const wc_bf16* mask, wc_bf16* dx, int bat
                     void* stream);
 /* Loss head (network/utils.py:17 + inference.py:135-141): low-res logits nchw_f32 [B,19,h,w] -> full-res argmax,
  * per-image CE(ignore 255) and d loss / d logits, full-res (f32 class planes [B,19,H,W]) and pulled back to low-res
- * (nhwc_bf16 [B,h,w,32], optional).  n_valid_ws: int[B] scratch. */
+ * (nhwc_bf16 [B,h,w,32], optional).  n_valid_ws: int[B] scratch.  dlogit_hi == NULL (then logits_hi must be NULL and
+ * dlogit_lo given, H and W integer multiples of h and w): pred, loss and dlogit_lo come from one fused kernel and the
+ * full-resolution d-logit tensor is never materialised. */
 int wc_seg_loss_head(const float* logits_lo, const int64_t* labels, int* n_valid_ws, int64_t* pred, float* dlogit_hi,
                      float* loss, float* logits_hi, wc_bf16* dlogit_lo, int batch, int h, int w, int H, int W, void* stream);
 /* Data gradient of the 7x7/2 stem convolution (64 output channels) to the nchw_f32 image (resnet.py:142). */

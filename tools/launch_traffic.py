@@ -2,7 +2,7 @@
 last N launches (one step), write a compact per-launch CSV, a per-kernel summary (time share, DRAM bytes) and the JSON that
 bench.py reads for `roofline.traffic` (DRAM bytes per igemm launch).
 
-usage: python tools/launch_traffic.py <ncu_log.csv> <launches_per_step> <out_prefix> <workload>
+usage: python tools/launch_traffic.py <ncu_log.csv> <launches_per_step> <out_prefix> <workload> [round]
 """
 import collections
 import csv
@@ -16,7 +16,7 @@ def clean(name):
     return (m.group(1) + (m.group(2) or "")) if m else name
 
 
-def main(path, per_step, prefix, workload):
+def main(path, per_step, prefix, workload, rnd=2):
     rows = list(csv.reader(open(path)))
     hi = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr = rows[hi]
@@ -53,9 +53,9 @@ def main(path, per_step, prefix, workload):
     c = sum(a[0] for a in ig); rd = sum(a[2] for a in ig); wr = sum(a[3] for a in ig); ms = sum(a[1] for a in ig)
     json.dump({"workload": workload, "kernel": "igemm_kernel", "launches_per_step": c, "dram_bytes_read_per_step": rd,
                "dram_bytes_write_per_step": wr, "dram_bytes_per_launch": (rd + wr) / c, "share_of_step_under_ncu": ms / tot,
-               "source": prefix + ".csv"}, open(f"profiles/r1_dram_traffic_{workload}.json", "w"), indent=1)
+               "source": prefix + ".csv"}, open(f"profiles/r{rnd}_dram_traffic_{workload}.json", "w"), indent=1)
     print("\n".join(lines[:12]))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]), sys.argv[3], sys.argv[4])
+    main(sys.argv[1], int(sys.argv[2]), sys.argv[3], sys.argv[4], int(sys.argv[5]) if len(sys.argv) > 5 else 2)
