@@ -64,6 +64,33 @@ bool lean_mask_enabled() {   // WC_IGEMM_LEAN_MASK=1: layers with a ReLU-mask in
   return v != 0;
 }
 
+// Residual stream epilogue (igemm.cu, LEAN == 3) for layers with a residual input and a short main loop: K <= 768, plain mode, no
+// ReLU mask, no PReLU / GELU, full N tiles that are multiples of 64.  WC_IGEMM_RES_DEEP = load buffers per warp (2..4, default 3; 0: off).
+void apply_res_deep(IgemmPlan* plan, int N, bool res_candidate) {
+  static int deep = -1;
+  if (deep < 0) {
+    const char* e = getenv("WC_IGEMM_RES_DEEP");
+    deep = e ? atoi(e) : 3;
+    if (deep > 4) deep = 4;
+  }
+  IgemmArgs& a = plan->args;
+  a.res_deep = 0;
+  if (deep < 2 || !lean_enabled() || !a.tma_store || !res_candidate || a.row3 || a.mask || a.wres || a.prelu || a.act == 3 || a.phase_n ||
+      a.total_kb > 12 || a.BN % 64 != 0 || N % a.BN != 0 || a.out_mode != kOutNHWC)
+    return;
+  for (int nl = deep; nl >= 2; --nl) {
+    const int ns = igemm_res_deep_stages(a.BN, nl);
+    if (ns >= 2 && ns >= (a.total_kb < 3 ? a.total_kb + 1 : 3)) {
+      a.res_deep = nl;
+      a.nstages = ns;
+      a.tma_res = 1;
+      a.stage2 = 1;
+      a.lean = 3;
+      return;
+    }
+  }
+}
+
 struct TapDef {
   int map, dy, dx;
   const WeightSrc* w;
@@ -334,8 +361,10 @@ int build_conv(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSrc& w,
   }
   plan.args.nstages = igemm_stages_for(plan.args.BN, plan.args.row3, wres_bytes);
   plan.args.stage2 = igemm_res_staging_fits(plan.args.BN, plan.args.row3, plan.args.nstages, wres_bytes) ? 1 : 0;
+  const bool res_candidate = plan.args.tma_res == 2;
   plan.args.tma_res = (plan.args.tma_res == 2 && plan.args.stage2) ? 1 : 0;
   plan.args.lean = (lean_enabled() && plan.args.tma_store && (!plan.args.mask || lean_mask_enabled()) && (!plan.args.res || plan.args.tma_res)) ? 1 : 0;
+  apply_res_deep(&plan, N, res_candidate);
   { const char* e = getenv("WC_IGEMM_DBG"); plan.args.dbg = e ? atoi(e) : 0; }
   { const char* e = getenv("WC_IGEMM_TRACE"); plan.args.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
   op->flops = plan.flops;

@@ -14,13 +14,15 @@ constexpr uint32_t kPipeBytes = 212992;  // shared-memory budget of the TMA ring
 constexpr int kMaxStages = 8;
 // bias / PReLU vectors up to this many channels are staged in shared memory (wider layers: L1-cached broadcast loads); the two
 // limits are what is left of the 227 KiB after the ring, the output staging, the barriers and the alignment slack
-constexpr int kBiasMaxN = 256, kPreluMaxN = 192;
+constexpr int kBiasMaxN = 256, kPreluMaxN = 128;
 constexpr uint32_t kVecBytes = (kBiasMaxN + kPreluMaxN) * 4;
 // Output staging of the TMA-store epilogue: 2 KiB per epilogue warp (32 rows x 32 channels bf16, 64-byte swizzle).  The
 // row-per-lane global stores it replaces touch 32 different 128-byte lines per request (16 bytes each) and keep the L1TEX
 // tag stage busy (profiles/r1_ncu_igemm_1x1_64_256.txt); a TMA store reads shared memory directly.
 constexpr uint32_t kOutStageBytes = 8 * 2048;
-constexpr uint32_t kSmemBytes = kPipeBytes + kOutStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kVecBytes;   // + 1 KiB static
+constexpr uint32_t kBarBytes = 512;   // 64 mbarriers: ring (2 x 8), accumulators (4), TMEM slot, residual boxes (8), resident weights,
+                                      // and 8 x 4 for the residual stream epilogue (index 32 + 4 * epilogue warp + slot)
+constexpr uint32_t kSmemBytes = kPipeBytes + kOutStageBytes + 1024 /*align*/ + kBarBytes + kVecBytes;   // = 227 KiB
 constexpr uint32_t kTmemCols = 512;
 // Row-segment mode (3x3, stride 1, dilation 1, tiles of 128 pixels of ONE image row): per (channel block, ky) one TMA
 // box of 130 pixels [x0-1, x0+129) is loaded once and the three kx taps read it through UMMA descriptors whose start is
@@ -478,7 +480,22 @@ __device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t 
   }
 }
 
-template <bool ROW3, bool TMA_OUT, bool TMA_RES, int LEAN = 0>   // LEAN: 0 generic epilogue, 1 lean, 2 lean with a ReLU-mask input
+// Residual STREAM epilogue (LEAN == 3) for memory-bound layers with a residual input (1x1 convolutions with K <= 768).  The lean
+// epilogue keeps ONE residual box (2 KiB) in flight per epilogue warp: tools/micro/tma_store_rate.cu shows that this pattern moves
+// one box per DRAM round trip (~2000 clk) and warp, 2.3 TB/s each way - the bytes in flight bound those layers.  Here the residual
+// boxes of a warp form a stream that runs NL - 1 boxes ahead of the accumulators and across tile boundaries: NL load buffers (one
+// mbarrier each) separate from two store buffers; after chunk i has been staged for its store, the box of chunk i + NL is requested
+// into the load buffer chunk i has just released (its rows were read into registers before the math; every lane fences generic ->
+// async before the elected lane issues the load).  The stream's cursor - tile, chunk and the DECODED coordinates of that tile, which
+// are recomputed only when the cursor moves to a new tile - is warp-uniform state.  Host guarantees N % BN == 0 and BN % 64 == 0.
+struct ResStream {
+  int tile, k;             // next box to request: tile index, chunk number of this warp within the tile
+  int n0, qx, qy, qb;      // decoded origin of that tile's quadrant box
+  uint32_t issued, done;   // boxes requested / chunks processed so far
+};
+
+template <bool ROW3, bool TMA_OUT, bool TMA_RES, int LEAN = 0>   // LEAN: 0 generic epilogue, 1 lean, 2 lean with a ReLU-mask input,
+                                                                  // 3 lean with the residual stream
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -503,7 +520,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (role dispatch below)
   const int lane = threadIdx.x & 31;
   // bias / PReLU vectors -> shared memory (read once per CTA instead of once per tile from L2)
-  float* s_vec = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+  float* s_vec = reinterpret_cast<float*>(smem_raw + (bar_base + kBarBytes - smem_u32(smem_raw)));
   const bool bias_in_smem = p.bias && p.N <= kBiasMaxN, prelu_in_smem = p.prelu && p.N <= kPreluMaxN;
   const float* s_bias = bias_in_smem ? s_vec : nullptr;
   const float* s_prelu = prelu_in_smem ? s_vec + kBiasMaxN : nullptr;
@@ -528,6 +545,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         mbar_init(tempty_bar(a), 256);
       }
       for (int w = 0; w < 8; ++w) mbar_init(bar_base + 8u * (2 * kMaxStages + 5 + w), 1);   // residual boxes (tma_res)
+      if (LEAN == 3)
+        for (int i = 0; i < 32; ++i) mbar_init(bar_base + 8u * (32 + i), 1);                // residual stream (LEAN == 3)
       mbar_init(wfull_bar, 1);
       fence_barrier_init();
     }
@@ -716,8 +735,41 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     uint32_t ectr = 0;     // lean epilogue: this warp's running chunk count (selects the staging buffer)
     const int q_pix = quad * 32;
     const int qx0 = q_pix % p.tw, qy0 = (q_pix / p.tw) % p.th, qb0 = q_pix / (p.tw * p.th);
+    // residual stream (LEAN == 3): [2 store blocks | res_deep load blocks] of 16 KiB end where the output staging ends; every warp
+    // owns the 2 KiB slice (warp - 2) of each block
+    const int nl = p.res_deep;
+    const uint32_t deep_base = smem_base + kPipeBytes + kOutStageBytes - static_cast<uint32_t>(2 + nl) * kOutStageBytes + static_cast<uint32_t>(warp - 2) * 2048u;
+    const uint32_t lbuf0 = deep_base + 2 * kOutStageBytes;
+    const uint32_t lbar0 = bar_base + 8u * (32 + 4 * (warp - 2));
+    const int ncw = p.BN / 64;   // chunks of this warp per tile (LEAN == 3: BN % 64 == 0, N % BN == 0)
+    ResStream rs{static_cast<int>(blockIdx.x), 0, 0, 0, 0, 0, 0u, 0u};
+    auto rs_decode = [&]() {
+      if (rs.tile < total_tiles) {
+        int n0, b0, y0, x0;
+        decode(rs.tile, n0, b0, y0, x0);
+        rs.n0 = n0; rs.qx = x0 + qx0; rs.qy = y0 + qy0; rs.qb = b0 + qb0;
+      }
+    };
+    auto rs_request = [&]() {
+      if (rs.tile >= total_tiles) return;
+      const uint32_t slot = rs.issued % static_cast<uint32_t>(nl);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(lbar0 + 8u * slot, 32 * 2 * 32);
+        tma_load_4d(lbuf0 + slot * kOutStageBytes, &maps.r, lbar0 + 8u * slot, rs.n0 + grp * 32 + rs.k * 64, rs.qx, rs.qy, rs.qb);
+      }
+      ++rs.issued;
+      if (++rs.k == ncw) {
+        rs.k = 0;
+        rs.tile += gridDim.x;
+        rs_decode();
+      }
+    };
     const int bb = row / (p.th * p.tw), rem = row % (p.th * p.tw), yy = rem / p.tw, xx = rem % p.tw;
     int it = 0;
+    if (LEAN == 3) {
+      rs_decode();
+      for (int i = 0; i < nl; ++i) rs_request();
+    }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int a = it & 1;
       const uint32_t aphase = (it >> 1) & 1u;
@@ -727,7 +779,85 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       const bool valid = (b < p.B) && (y < p.H) && (x < p.W);
       const uint32_t tacc = tmem_base + static_cast<uint32_t>(a) * 256u + (static_cast<uint32_t>(quad * 32) << 16);
       if (warp == 2 && lane == 0) trace(2, 20);
-      if (LEAN) {
+      if (LEAN == 3) {
+        // ---- residual stream: chunks grp*32 + k*64 of this tile; residual rows come from the load ring, results go out through two
+        // alternating store buffers
+        constexpr int NC = 32, NV = 4;
+        const uint32_t sw = (lane >> 1) & 3;
+        const uint32_t row_off = static_cast<uint32_t>(lane) * (NC * 2);
+        mbar_wait(tfull_bar(a), aphase);
+        tc_fence_after();
+        const float* rb = p.rowbias ? p.rowbias + static_cast<size_t>(b < p.B ? b : p.B - 1) * p.ldrb : nullptr;
+        for (int k = 0; k < ncw; ++k) {
+          const int c0 = grp * NC + k * 2 * NC, nb = n0 + c0;
+          uint32_t r[NC];
+          tmem_ld_n<NC>(tacc + c0, r);
+          const uint32_t slot = rs.done % static_cast<uint32_t>(nl);
+          mbar_wait(lbar0 + 8u * slot, (rs.done / static_cast<uint32_t>(nl)) & 1u);
+          uint4 rr[NV];
+          {
+            const uint32_t src = lbuf0 + slot * kOutStageBytes + row_off;
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[j].x), "=r"(rr[j].y), "=r"(rr[j].z), "=r"(rr[j].w)
+                           : "r"(src + ((static_cast<uint32_t>(j) ^ sw) << 4)) : "memory");
+          }
+          tmem_wait_ld();
+          float v[NC];
+#pragma unroll
+          for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(r[j]);
+          if (s_bias) {
+#pragma unroll
+            for (int j = 0; j < NC; j += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(s_bias + nb + j);
+              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+            }
+          } else if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < NC; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+            }
+          }
+          if (rb) {
+#pragma unroll
+            for (int j = 0; j < NC; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + nb + j));
+              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < NV; ++j) {
+            const float2 f0 = unpack_bf16(rr[j].x), f1 = unpack_bf16(rr[j].y), f2 = unpack_bf16(rr[j].z), f3 = unpack_bf16(rr[j].w);
+            v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
+            v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+          }
+          if (lane == 0) tma_store_wait_read<1>();   // the store that read this store buffer two chunks ago is done with it
+          __syncwarp();
+          const uint32_t dst = deep_base + (rs.done & 1u) * kOutStageBytes;
+#pragma unroll
+          for (int j = 0; j < NV; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + row_off + ((static_cast<uint32_t>(j) ^ sw) << 4)),
+                         "r"(pack_bf16(v[8 * j + 0], v[8 * j + 1])), "r"(pack_bf16(v[8 * j + 2], v[8 * j + 3])),
+                         "r"(pack_bf16(v[8 * j + 4], v[8 * j + 5])), "r"(pack_bf16(v[8 * j + 6], v[8 * j + 7])) : "memory");
+          fence_proxy_async_smem();   // orders this lane's st.shared AND its earlier ld.shared of the load buffer before the async proxy
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&maps.c, dst, nb, x0 + qx0, y0 + qy0, b0 + qb0);
+            tma_store_commit();
+          }
+          ++rs.done;
+          rs_request();   // box of chunk done - 1 + nl into the load buffer just released
+        }
+      } else if (LEAN) {
         if ((p.BN % 32 == 0) && (p.N % 32 == 0) && p.out_mode != kOutNCHWf32)
           epilogue_tile_lean<32, TMA_RES, LEAN == 2>(p, tacc, n0, b, y, x, valid, grp, s_bias, s_prelu, tfull_bar(a), aphase, &maps.c, &maps.r, out_stage, res_stage,
                                           p.stage2 ? 2 : 1, x0 + qx0, y0 + qy0, b0 + qb0, res_bar, res_phase, ectr, maps.qkv);
@@ -771,6 +901,13 @@ int igemm_stages_for(int BN, int row3, int wres_bytes, int row_nkx) {
   return n > kMaxStages ? kMaxStages : n;
 }
 
+int igemm_res_deep_stages(int BN, int nl) {
+  const uint32_t stage = kABytes + static_cast<uint32_t>(BN) * kIgemmBK * 2;
+  const uint32_t cap = kPipeBytes + kOutStageBytes - static_cast<uint32_t>(2 + nl) * kOutStageBytes;
+  int n = static_cast<int>(cap / stage);
+  return n > kMaxStages ? kMaxStages : n;
+}
+
 bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes, int row_nkx) {
   const uint32_t stage = (row3 ? kRowABytes : kABytes) + (wres_bytes > 0 ? 0u : (row3 ? static_cast<uint32_t>(row_nkx) : 1u) * static_cast<uint32_t>(BN) * kIgemmBK * 2);
   return static_cast<uint32_t>(nstages) * stage + static_cast<uint32_t>(wres_bytes > 0 ? wres_bytes : 0) + kOutStageBytes <= kPipeBytes;
@@ -789,11 +926,13 @@ static int launch_variant(const IgemmPlan& plan, cudaStream_t stream) {
 
 int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
   ProfScope prof(kProfIgemm, stream, plan.flops);
-  prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.total_kb * kIgemmBK, plan.args.BN, plan.args.ntaps + 100 * plan.args.row3 + 1000 * plan.args.lean + 2000 * (plan.args.mask != nullptr) + 4000 * (plan.args.res != nullptr) +
+  prof.note(plan.args.B * plan.args.H * plan.args.W, plan.args.N, plan.args.total_kb * kIgemmBK, plan.args.BN, plan.args.ntaps + 100 * plan.args.row3 + 1000 * (plan.args.lean != 0) + 32000 * (plan.args.lean == 3) + 2000 * (plan.args.mask != nullptr) + 4000 * (plan.args.res != nullptr) +
                 8000 * (plan.args.out_mode != kOutNHWC) + 16000 * (plan.args.tma_store == 0), plan.grid);
   const int variant = plan.args.tma_store ? (plan.args.tma_res ? 2 : 1) : 0;   // epilogue: per-lane stores / TMA store / TMA store + TMA residual
   int e = 0;
-  if (plan.args.lean && plan.args.mask) {
+  if (plan.args.lean == 3) {
+    e = launch_variant<false, true, true, 3>(plan, stream);
+  } else if (plan.args.lean && plan.args.mask) {
     if (plan.args.row3) e = plan.args.tma_res ? launch_variant<true, true, true, 2>(plan, stream) : launch_variant<true, true, false, 2>(plan, stream);
     else e = plan.args.tma_res ? launch_variant<false, true, true, 2>(plan, stream) : launch_variant<false, true, false, 2>(plan, stream);
   } else if (plan.args.lean) {

@@ -63,6 +63,7 @@ struct IgemmArgs {
   int heads, hd, C;
   int row_nky, row_nkx;        // row-segment mode: the window is row_nky x row_nkx taps (3 x 3, or 1 x 9 for build_conv_hrow)
   int phase_n;                 // > 0: kOutNHWC through the lean epilogue with four phase blocks of phase_n channels (maps c, qkv[0..2])
+  int res_deep;                // LEAN == 3: load buffers per epilogue warp of the residual stream (igemm.cu)
   float q_scale;               // kOutQKV: the Q columns are multiplied by this before the bf16 rounding (1: off); see OutSpec::q_scale
   // kOutNHWC through TMA (tma_store == 1; unit-stride outputs only): every epilogue warp stages its 32 rows x NC channels in
   // shared memory and one lane stores the box (NC, qw, qh, qb) = its TMEM lane quadrant of the tile with IgemmMaps::c
@@ -98,6 +99,8 @@ int igemm_launch(const IgemmPlan& plan, cudaStream_t stream);
 int igemm_stages_for(int BN, int row3, int wres_bytes = 0, int row_nkx = 3);
 // true if 16 KiB stay free behind `nstages` stages of the TMA ring (room for the residual staging of the TMA epilogue)
 bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes = 0, int row_nkx = 3);
+// ring depth left (plain mode) when the residual stream epilogue takes 2 store + nl load blocks of 16 KiB from the tail of the ring
+int igemm_res_deep_stages(int BN, int nl);
 
 // Choose the M-tile shape for a (B,H,W) grid: widest power-of-two span of x, then y, then b.
 void igemm_pick_tile(int B, int H, int W, int* tb, int* th, int* tw);
