@@ -73,17 +73,36 @@ void apply_res_deep(IgemmPlan* plan, int N, bool res_candidate) {
     deep = e ? atoi(e) : 3;
     if (deep > 4) deep = 4;
   }
+  static int deep_mask = -1;   // WC_IGEMM_STREAM_MASK=0: layers with a ReLU-mask input keep the generic epilogue
+  if (deep_mask < 0) {
+    const char* e = getenv("WC_IGEMM_STREAM_MASK");
+    deep_mask = e ? atoi(e) : 1;
+  }
   IgemmArgs& a = plan->args;
   a.res_deep = 0;
-  if (deep < 2 || !lean_enabled() || !a.tma_store || !res_candidate || a.row3 || a.mask || a.wres || a.prelu || a.act == 3 || a.phase_n ||
+  const bool mask_candidate = a.stream_mask == 2;
+  a.stream_mask = 0;
+  a.stream_res = 0;
+  if (deep < 2 || !lean_enabled() || !a.tma_store || a.row3 || a.wres || a.prelu || a.act == 3 || a.phase_n ||
       a.total_kb > 12 || a.BN % 64 != 0 || N % a.BN != 0 || a.out_mode != kOutNHWC)
     return;
+  if (a.res && !res_candidate) return;             // a residual that cannot go through TMA
+  if (a.mask && !(mask_candidate && deep_mask)) return;
+  const int nbox = (a.res ? 1 : 0) + (a.mask ? 1 : 0);
+  if (nbox == 0) return;
   for (int nl = deep; nl >= 2; --nl) {
-    const int ns = igemm_res_deep_stages(a.BN, nl);
-    if (ns >= 2 && ns >= (a.total_kb < 3 ? a.total_kb + 1 : 3)) {
+    const int ns = igemm_res_deep_stages(a.BN, nl * nbox);
+    static int min_stages = -1;   // WC_IGEMM_STREAM_MIN_STAGES (default 2): these layers are epilogue-bound, a short ring suffices
+    if (min_stages < 0) {
+      const char* e = getenv("WC_IGEMM_STREAM_MIN_STAGES");
+      min_stages = e ? atoi(e) : 2;
+    }
+    if (ns >= 2 && ns >= (a.total_kb < min_stages ? a.total_kb + 1 : min_stages)) {
       a.res_deep = nl;
+      a.stream_res = a.res ? 1 : 0;
+      a.stream_mask = a.mask ? 1 : 0;
       a.nstages = ns;
-      a.tma_res = 1;
+      a.tma_res = a.res ? 1 : 0;
       a.stage2 = 1;
       a.lean = 3;
       return;
@@ -230,6 +249,10 @@ int finish_plan(IgemmPlan* plan, DeviceArena* arena, const std::vector<TapDef>& 
         if (tma_res && ep.res && ep.res->ld % 8 == 0) {
           if (int e = igemm_make_cmap(&plan->maps.r, *ep.res, N, nc, a.qw, a.qh, a.qb, sy, sx, py, px)) return e;
           a.tma_res = 2;   // candidate: confirmed by the caller once the ring depth is known
+        }
+        if (ep.mask && ep.mask->ld % 8 == 0) {
+          if (int e = igemm_make_cmap(&plan->maps.m, *ep.mask, N, nc, a.qw, a.qh, a.qb, sy, sx, py, px)) return e;
+          a.stream_mask = 2;   // candidate for the stream epilogue
         }
       }
     }

@@ -738,7 +738,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     // residual stream (LEAN == 3): [2 store blocks | res_deep load blocks] of 16 KiB end where the output staging ends; every warp
     // owns the 2 KiB slice (warp - 2) of each block
     const int nl = p.res_deep;
-    const uint32_t deep_base = smem_base + kPipeBytes + kOutStageBytes - static_cast<uint32_t>(2 + nl) * kOutStageBytes + static_cast<uint32_t>(warp - 2) * 2048u;
+    const int nbox = p.stream_res + p.stream_mask;   // boxes per slot: residual rows, then ReLU-mask rows
+    const uint32_t deep_base = smem_base + kPipeBytes + kOutStageBytes - static_cast<uint32_t>(2 + nl * nbox) * kOutStageBytes + static_cast<uint32_t>(warp - 2) * 2048u;
     const uint32_t lbuf0 = deep_base + 2 * kOutStageBytes;
     const uint32_t lbar0 = bar_base + 8u * (32 + 4 * (warp - 2));
     const int ncw = p.BN / 64;   // chunks of this warp per tile (LEAN == 3: BN % 64 == 0, N % BN == 0)
@@ -754,8 +755,13 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
       if (rs.tile >= total_tiles) return;
       const uint32_t slot = rs.issued % static_cast<uint32_t>(nl);
       if (lane == 0) {
-        mbar_arrive_expect_tx(lbar0 + 8u * slot, 32 * 2 * 32);
-        tma_load_4d(lbuf0 + slot * kOutStageBytes, &maps.r, lbar0 + 8u * slot, rs.n0 + grp * 32 + rs.k * 64, rs.qx, rs.qy, rs.qb);
+        mbar_arrive_expect_tx(lbar0 + 8u * slot, static_cast<uint32_t>(nbox) * 32 * 2 * 32);
+        uint32_t dstb = lbuf0 + slot * static_cast<uint32_t>(nbox) * kOutStageBytes;
+        if (p.stream_res) {
+          tma_load_4d(dstb, &maps.r, lbar0 + 8u * slot, rs.n0 + grp * 32 + rs.k * 64, rs.qx, rs.qy, rs.qb);
+          dstb += kOutStageBytes;
+        }
+        if (p.stream_mask) tma_load_4d(dstb, &maps.m, lbar0 + 8u * slot, rs.n0 + grp * 32 + rs.k * 64, rs.qx, rs.qy, rs.qb);
       }
       ++rs.issued;
       if (++rs.k == ncw) {
@@ -794,13 +800,22 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           tmem_ld_n<NC>(tacc + c0, r);
           const uint32_t slot = rs.done % static_cast<uint32_t>(nl);
           mbar_wait(lbar0 + 8u * slot, (rs.done / static_cast<uint32_t>(nl)) & 1u);
-          uint4 rr[NV];
+          uint4 rr[NV], mm[NV];
           {
-            const uint32_t src = lbuf0 + slot * kOutStageBytes + row_off;
+            uint32_t src = lbuf0 + slot * static_cast<uint32_t>(nbox) * kOutStageBytes + row_off;
+            if (p.stream_res) {
 #pragma unroll
-            for (int j = 0; j < NV; ++j)
-              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[j].x), "=r"(rr[j].y), "=r"(rr[j].z), "=r"(rr[j].w)
-                           : "r"(src + ((static_cast<uint32_t>(j) ^ sw) << 4)) : "memory");
+              for (int j = 0; j < NV; ++j)
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rr[j].x), "=r"(rr[j].y), "=r"(rr[j].z), "=r"(rr[j].w)
+                             : "r"(src + ((static_cast<uint32_t>(j) ^ sw) << 4)) : "memory");
+              src += kOutStageBytes;
+            }
+            if (p.stream_mask) {
+#pragma unroll
+              for (int j = 0; j < NV; ++j)
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(mm[j].x), "=r"(mm[j].y), "=r"(mm[j].z), "=r"(mm[j].w)
+                             : "r"(src + ((static_cast<uint32_t>(j) ^ sw) << 4)) : "memory");
+            }
           }
           tmem_wait_ld();
           float v[NC];
@@ -826,11 +841,13 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
               v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
             }
           }
+          if (p.stream_res) {
 #pragma unroll
-          for (int j = 0; j < NV; ++j) {
-            const float2 f0 = unpack_bf16(rr[j].x), f1 = unpack_bf16(rr[j].y), f2 = unpack_bf16(rr[j].z), f3 = unpack_bf16(rr[j].w);
-            v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
-            v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
+            for (int j = 0; j < NV; ++j) {
+              const float2 f0 = unpack_bf16(rr[j].x), f1 = unpack_bf16(rr[j].y), f2 = unpack_bf16(rr[j].z), f3 = unpack_bf16(rr[j].w);
+              v[8 * j + 0] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
+              v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
+            }
           }
           if (p.relu) {
 #pragma unroll
@@ -839,6 +856,20 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           if (p.act == 2) {
 #pragma unroll
             for (int j = 0; j < NC; ++j) v[j] = __fdividef(v[j], 1.f + __expf(-v[j]));
+          }
+          if (p.stream_mask) {   // ReLU derivative of the forward activation (segmentor data gradients)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+              const float2 f0 = unpack_bf16(mm[j].x), f1 = unpack_bf16(mm[j].y), f2 = unpack_bf16(mm[j].z), f3 = unpack_bf16(mm[j].w);
+              if (!(f0.x > 0.f)) v[8 * j + 0] = 0.f;
+              if (!(f0.y > 0.f)) v[8 * j + 1] = 0.f;
+              if (!(f1.x > 0.f)) v[8 * j + 2] = 0.f;
+              if (!(f1.y > 0.f)) v[8 * j + 3] = 0.f;
+              if (!(f2.x > 0.f)) v[8 * j + 4] = 0.f;
+              if (!(f2.y > 0.f)) v[8 * j + 5] = 0.f;
+              if (!(f3.x > 0.f)) v[8 * j + 6] = 0.f;
+              if (!(f3.y > 0.f)) v[8 * j + 7] = 0.f;
+            }
           }
           if (lane == 0) tma_store_wait_read<1>();   // the store that read this store buffer two chunks ago is done with it
           __syncwarp();

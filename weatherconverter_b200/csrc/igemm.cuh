@@ -63,7 +63,8 @@ struct IgemmArgs {
   int heads, hd, C;
   int row_nky, row_nkx;        // row-segment mode: the window is row_nky x row_nkx taps (3 x 3, or 1 x 9 for build_conv_hrow)
   int phase_n;                 // > 0: kOutNHWC through the lean epilogue with four phase blocks of phase_n channels (maps c, qkv[0..2])
-  int res_deep;                // LEAN == 3: load buffers per epilogue warp of the residual stream (igemm.cu)
+  int res_deep;                // LEAN == 3: load slots per epilogue warp of the residual / mask stream (igemm.cu)
+  int stream_res, stream_mask; // LEAN == 3: which boxes a slot carries (residual rows, ReLU-mask rows)
   float q_scale;               // kOutQKV: the Q columns are multiplied by this before the bf16 rounding (1: off); see OutSpec::q_scale
   // kOutNHWC through TMA (tma_store == 1; unit-stride outputs only): every epilogue warp stages its 32 rows x NC channels in
   // shared memory and one lane stores the box (NC, qw, qh, qb) = its TMEM lane quadrant of the tile with IgemmMaps::c
@@ -85,6 +86,7 @@ struct IgemmMaps {
   CUtensorMap b;
   CUtensorMap c;   // output (tma_store)
   CUtensorMap r;   // residual (tma_res)
+  CUtensorMap m;   // ReLU-mask rows through the stream epilogue (same box as c / r)
   CUtensorMap qkv[3];   // kOutQKV through the lean epilogue: Q, K as (hd, N, heads, B), V^T as (N, hd, heads, B)
 };
 
