@@ -69,25 +69,41 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int
   }
 }
 
+// Combine the per-slab partial sums of sample b into mean / rstd per group.  Warp g owns group g: lane i takes slab i (<= 32 slabs),
+// the sums are added in double precision in a FIXED butterfly order (deterministic, independent of the batch) instead of one thread
+// per group looping over up to 32 slabs of dependent FP64 adds.  (Measured neutral on the C3 step: 1.50 vs 1.51 ms for the class.)
+__device__ __forceinline__ void combine_partials(const float2* __restrict__ partial, int b, int nsplit_stats, int HW, int C, float eps,
+                                                 float* s_mean, float* s_rstd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g = warp; g < kGroups; g += (blockDim.x >> 5)) {
+    double s = 0.0, ss = 0.0;
+    for (int i = lane; i < nsplit_stats; i += 32) {
+      const float2 t = partial[(static_cast<size_t>(b) * nsplit_stats + i) * kGroups + g];
+      s += t.x; ss += t.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+      const double n = static_cast<double>(HW) * (C / kGroups);
+      const double mean = s / n;
+      double var = ss / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = static_cast<float>(mean);
+      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+  }
+}
+
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int HW, int C,
                                 int ld, int ldy, int nsplit_stats, int nsplit, const float2* __restrict__ partial,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu) {
   pdl_prologue();
   __shared__ float s_mean[kGroups], s_rstd[kGroups];
   const int b = blockIdx.y, split = blockIdx.x;
-  if (threadIdx.x < kGroups) {
-    double s = 0.0, ss = 0.0;
-    for (int i = 0; i < nsplit_stats; ++i) {
-      const float2 t = partial[(static_cast<size_t>(b) * nsplit_stats + i) * kGroups + threadIdx.x];
-      s += t.x; ss += t.y;
-    }
-    const double n = static_cast<double>(HW) * (C / kGroups);
-    const double mean = s / n;
-    double var = ss / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = static_cast<float>(mean);
-    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  }
+  combine_partials(partial, b, nsplit_stats, HW, C, eps, s_mean, s_rstd);
   __syncthreads();
   const int vpp = C / 8, cpg = C / kGroups;
   const int rows = blockDim.x / vpp;
@@ -149,19 +165,7 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
 
 __device__ __forceinline__ void group_stats(const float2* partial, int b, int nsplit_stats, int HW, int C, float eps,
                                             float* s_mean, float* s_rstd) {
-  if (threadIdx.x < kGroups) {
-    double s = 0.0, ss = 0.0;
-    for (int i = 0; i < nsplit_stats; ++i) {
-      const float2 t = partial[(static_cast<size_t>(b) * nsplit_stats + i) * kGroups + threadIdx.x];
-      s += t.x; ss += t.y;
-    }
-    const double n = static_cast<double>(HW) * (C / kGroups);
-    const double mean = s / n;
-    double var = ss / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = static_cast<float>(mean);
-    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  }
+  combine_partials(partial, b, nsplit_stats, HW, C, eps, s_mean, s_rstd);   // the same order as the forward pass: identical statistics
   __syncthreads();
 }
 
