@@ -574,7 +574,13 @@ int groupnorm_silu(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int 
   ProfScope prof(kProfGroupNorm, st, 6.0 * B * static_cast<double>(HW) * C);  // algorithmic bytes: 2 reads + 1 write, bf16
   launch_k(gn_stats_kernel, dim3(nsplit, B), threads, threads * sizeof(float2), st, x, HW, C, ld, nsplit, partial);
   WC_LAUNCH_CHECK();
-  int asplit = (8 * num_sms() + B - 1) / B;
+  static int per_sm = -1;   // WC_GN_APPLY_BLOCKS_PER_SM: blocks of the apply pass per SM (the result does not depend on it)
+  if (per_sm < 0) {
+    const char* e = getenv("WC_GN_APPLY_BLOCKS_PER_SM");
+    per_sm = e ? atoi(e) : 8;
+    if (per_sm < 1) per_sm = 1;
+  }
+  int asplit = (per_sm * num_sms() + B - 1) / B;
   if (asplit > max_split) asplit = max_split;
   if (asplit < 1) asplit = 1;
   launch_k(gn_apply_kernel, dim3(asplit, B), threads, 0, st, x, y, HW, C, ld, ldy, nsplit, asplit, partial, gamma, beta, eps,
