@@ -180,9 +180,9 @@ def test_launch_traffic_tool_parses_an_ncu_log(tmp_path, monkeypatch):
     log.write_text("==PROF== Connected\n" + "\n".join(rows) + "\n")
     (tmp_path / "profiles").mkdir()
     monkeypatch.chdir(tmp_path)
-    launch_traffic.main(str(log), 3, str(tmp_path / "profiles" / "x"), "zz")
+    launch_traffic.main(str(log), 3, str(tmp_path / "profiles" / "x"), "zz", 7)    # round number -> profiles/r7_dram_traffic_zz.json
     import json
-    meta = json.load(open(tmp_path / "profiles" / "r1_dram_traffic_zz.json"))
+    meta = json.load(open(tmp_path / "profiles" / "r7_dram_traffic_zz.json"))
     assert meta["launches_per_step"] == 2
     assert meta["dram_bytes_per_launch"] == pytest.approx((10e6 + 30e6 + 0.5e6 + 1.5e6) / 2)
     summary = (tmp_path / "profiles" / "x_summary.txt").read_text()
