@@ -491,7 +491,9 @@ __device__ __forceinline__ void epilogue_tile_lean(const IgemmArgs& p, uint32_t 
 struct ResStream {
   int tile, k;             // next box to request: tile index, chunk number of this warp within the tile
   int n0, qx, qy, qb;      // decoded origin of that tile's quadrant box
-  uint32_t issued, done;   // boxes requested / chunks processed so far
+  uint32_t req_slot;       // slot of the next request (counters instead of issued % nl: no integer division in the chain)
+  uint32_t slot, phase;    // slot and mbarrier parity of the next chunk to process
+  uint32_t sbuf;           // store buffer (0 / 1) of the next chunk
 };
 
 template <bool ROW3, bool TMA_OUT, bool TMA_RES, int LEAN = 0>   // LEAN: 0 generic epilogue, 1 lean, 2 lean with a ReLU-mask input,
@@ -743,7 +745,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     const uint32_t lbuf0 = deep_base + 2 * kOutStageBytes;
     const uint32_t lbar0 = bar_base + 8u * (32 + 4 * (warp - 2));
     const int ncw = p.BN / 64;   // chunks of this warp per tile (LEAN == 3: BN % 64 == 0, N % BN == 0)
-    ResStream rs{static_cast<int>(blockIdx.x), 0, 0, 0, 0, 0, 0u, 0u};
+    ResStream rs{static_cast<int>(blockIdx.x), 0, 0, 0, 0, 0, 0u, 0u, 0u, 0u};
     auto rs_decode = [&]() {
       if (rs.tile < total_tiles) {
         int n0, b0, y0, x0;
@@ -753,7 +755,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
     };
     auto rs_request = [&]() {
       if (rs.tile >= total_tiles) return;
-      const uint32_t slot = rs.issued % static_cast<uint32_t>(nl);
+      const uint32_t slot = rs.req_slot;
       if (lane == 0) {
         mbar_arrive_expect_tx(lbar0 + 8u * slot, static_cast<uint32_t>(nbox) * 32 * 2 * 32);
         uint32_t dstb = lbuf0 + slot * static_cast<uint32_t>(nbox) * kOutStageBytes;
@@ -763,7 +765,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         }
         if (p.stream_mask) tma_load_4d(dstb, &maps.m, lbar0 + 8u * slot, rs.n0 + grp * 32 + rs.k * 64, rs.qx, rs.qy, rs.qb);
       }
-      ++rs.issued;
+      if (++rs.req_slot == static_cast<uint32_t>(nl)) rs.req_slot = 0;
       if (++rs.k == ncw) {
         rs.k = 0;
         rs.tile += gridDim.x;
@@ -798,8 +800,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           const int c0 = grp * NC + k * 2 * NC, nb = n0 + c0;
           uint32_t r[NC];
           tmem_ld_n<NC>(tacc + c0, r);
-          const uint32_t slot = rs.done % static_cast<uint32_t>(nl);
-          mbar_wait(lbar0 + 8u * slot, (rs.done / static_cast<uint32_t>(nl)) & 1u);
+          const uint32_t slot = rs.slot;
+          mbar_wait(lbar0 + 8u * slot, rs.phase);
           uint4 rr[NV], mm[NV];
           {
             uint32_t src = lbuf0 + slot * static_cast<uint32_t>(nbox) * kOutStageBytes + row_off;
@@ -873,7 +875,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           }
           if (lane == 0) tma_store_wait_read<1>();   // the store that read this store buffer two chunks ago is done with it
           __syncwarp();
-          const uint32_t dst = deep_base + (rs.done & 1u) * kOutStageBytes;
+          const uint32_t dst = deep_base + rs.sbuf * kOutStageBytes;
 #pragma unroll
           for (int j = 0; j < NV; ++j)
             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + row_off + ((static_cast<uint32_t>(j) ^ sw) << 4)),
@@ -885,8 +887,9 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             tma_store_4d(&maps.c, dst, nb, x0 + qx0, y0 + qy0, b0 + qb0);
             tma_store_commit();
           }
-          ++rs.done;
-          rs_request();   // box of chunk done - 1 + nl into the load buffer just released
+          rs.sbuf ^= 1u;
+          if (++rs.slot == static_cast<uint32_t>(nl)) { rs.slot = 0; rs.phase ^= 1u; }
+          rs_request();   // box of the chunk nl ahead, into the slot just released
         }
       } else if (LEAN) {
         if ((p.BN % 32 == 0) && (p.N % 32 == 0) && p.out_mode != kOutNCHWf32)
