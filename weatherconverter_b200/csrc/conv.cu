@@ -460,7 +460,8 @@ int build_conv_hrow(ConvOp* op, DeviceArena* arena, const Act& x, const WeightSr
   }
   plan.args.row3 = 0;
   plan.args.row_nky = 1; plan.args.row_nkx = w.KW;
-  if (hseg && row3_enabled() && tw == 128 && th == 1 && tb == 1 && plan.args.BN <= 128 && igemm_stages_for(plan.args.BN, 1, 0, w.KW) >= 2) {
+  // (the kernel is instantiated for 3 x 3 and 1 x 9 windows: other widths keep one stage per tap)
+  if (hseg && w.KW == 9 && row3_enabled() && tw == 128 && th == 1 && tb == 1 && plan.args.BN <= 128 && igemm_stages_for(plan.args.BN, 1, 0, w.KW) >= 2) {
     if (int e = igemm_make_rowseg_map(&plan.maps.a[2], x, w.KW)) return e;
     plan.args.row3 = row3_mode();
   }

@@ -496,17 +496,21 @@ struct ResStream {
   uint32_t sbuf;           // store buffer (0 / 1) of the next chunk
 };
 
-template <bool ROW3, bool TMA_OUT, bool TMA_RES, int LEAN = 0>   // LEAN: 0 generic epilogue, 1 lean, 2 lean with a ReLU-mask input,
+// ROWK: 0 plain taps; 3: row-segment mode for a 3 x 3 window; 9: for a 1 x 9 window (compile-time so that the tap loops of the producer and
+// of the MMA issuer unroll - with run-time tap counts the 3 x 3 layers lost 8 %)
+template <int ROWK, bool TMA_OUT, bool TMA_RES, int LEAN = 0>   // LEAN: 0 generic epilogue, 1 lean, 2 lean with a ReLU-mask input,
                                                                   // 3 lean with the residual stream
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ IgemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   // Pipeline depth is chosen per launch: narrow N tiles have small stages, so more of them fit and more bytes are in
   // flight per SM (these layers are TMA-latency bound, not tensor bound).
+  constexpr bool ROW3 = ROWK != 0;
+  constexpr int kNky = ROWK == 3 ? 3 : 1, kNkx = ROWK == 0 ? 1 : ROWK;
   constexpr uint32_t kAOff = ROW3 ? kRowABytes : kABytes;   // offset of the B tile(s) inside a stage
   const int kStages = p.nstages;
   const uint32_t kBTile = static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
-  const uint32_t kStageSz = kAOff + (p.wres ? 0u : (ROW3 ? static_cast<uint32_t>(p.row_nkx) : 1u) * kBTile);
+  const uint32_t kStageSz = kAOff + (p.wres ? 0u : static_cast<uint32_t>(kNkx) * kBTile);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t wres_base = smem_base + static_cast<uint32_t>(kStages) * kStageSz;   // resident weights sit right behind the ring
   const uint32_t bar_base = smem_base + kPipeBytes + kOutStageBytes;   // [ring | output staging | barriers | bias / PReLU]
@@ -612,7 +616,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
           // taps 0 .. nky*nkx-1 are the window (ky-major) over map 0, all with nkb = p.taps[0].nkb channel blocks; one box of
           // 128 + nkx - 1 pixels of an image row serves the nkx horizontal taps (3x3: nky = nkx = 3; 1x9: nky = 1, nkx = 9)
           const int nkb = p.taps[0].nkb;
-          const int nky = p.row_nky, nkx = p.row_nkx;
+          constexpr int nky = kNky, nkx = kNkx;
           const uint32_t b_bytes = static_cast<uint32_t>(p.BN) * kIgemmBK * 2;
           const uint32_t a_bytes = static_cast<uint32_t>(128 + nkx - 1) * 128u;
           for (int ky = 0; ky < nky; ++ky)
@@ -672,8 +676,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
         const uint32_t d_tmem = tmem_u + static_cast<uint32_t>(a) * 256u;
         int ks_first = 0;
         if (ROW3) {
-          const int nkx = p.row_nkx;
-          const int nseg = p.row_nky * p.taps[0].nkb;
+          constexpr int nkx = kNkx;
+          const int nseg = kNky * p.taps[0].nkb;
           for (int sg = 0; sg < nseg; ++sg) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
@@ -684,7 +688,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
               const uint32_t a_lo = a_lo0 + stage * stage16;
               const uint32_t b_lo = p.wres ? w_lo0 + static_cast<uint32_t>(ky3 * nkx * nkb3 + kb3) * bt16 : b_lo0 + stage * stage16;
               const uint32_t bkx16 = p.wres ? static_cast<uint32_t>(nkb3) * bt16 : bt16;
-#pragma unroll 3
+#pragma unroll
               for (int kx = 0; kx < nkx; ++kx) {
                 // window of 128 pixels starting kx pixels (kx*128 B = 8 descriptor units) into the 130-pixel segment; the
                 // UMMA swizzle is a function of the absolute shared-memory address, so the shifted start needs no fix-up
@@ -700,7 +704,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          ks_first = p.row_nky * nkx * p.taps[0].nkb;
+          ks_first = kNky * nkx * p.taps[0].nkb;
         }
         for (int ks = ks_first; ks < p.total_kb; ++ks) {
           mbar_wait(full_bar(stage), phase);
@@ -947,7 +951,7 @@ bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes, int r
   return static_cast<uint32_t>(nstages) * stage + static_cast<uint32_t>(wres_bytes > 0 ? wres_bytes : 0) + kOutStageBytes <= kPipeBytes;
 }
 
-template <bool ROW3, bool TMA_OUT, bool TMA_RES, int LEAN = 0>
+template <int ROW3, bool TMA_OUT, bool TMA_RES, int LEAN = 0>
 static int launch_variant(const IgemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -964,16 +968,18 @@ int igemm_launch(const IgemmPlan& plan, cudaStream_t stream) {
                 8000 * (plan.args.out_mode != kOutNHWC) + 16000 * (plan.args.tma_store == 0), plan.grid);
   const int variant = plan.args.tma_store ? (plan.args.tma_res ? 2 : 1) : 0;   // epilogue: per-lane stores / TMA store / TMA store + TMA residual
   int e = 0;
-  if (plan.args.lean == 3) {
-    e = launch_variant<false, true, true, 3>(plan, stream);
+  if (plan.args.row3 && plan.args.row_nkx == 9) {   // 1 x 9 row-segment mode (build_conv_hrow): fp32 planes, lean or generic epilogue
+    e = plan.args.lean ? launch_variant<9, true, false, 1>(plan, stream) : launch_variant<9, false, false>(plan, stream);
+  } else if (plan.args.lean == 3) {
+    e = launch_variant<0, true, true, 3>(plan, stream);
   } else if (plan.args.lean && plan.args.mask) {
-    if (plan.args.row3) e = plan.args.tma_res ? launch_variant<true, true, true, 2>(plan, stream) : launch_variant<true, true, false, 2>(plan, stream);
-    else e = plan.args.tma_res ? launch_variant<false, true, true, 2>(plan, stream) : launch_variant<false, true, false, 2>(plan, stream);
+    if (plan.args.row3) e = plan.args.tma_res ? launch_variant<3, true, true, 2>(plan, stream) : launch_variant<3, true, false, 2>(plan, stream);
+    else e = plan.args.tma_res ? launch_variant<0, true, true, 2>(plan, stream) : launch_variant<0, true, false, 2>(plan, stream);
   } else if (plan.args.lean) {
-    if (plan.args.row3) e = plan.args.tma_res ? launch_variant<true, true, true, 1>(plan, stream) : launch_variant<true, true, false, 1>(plan, stream);
-    else e = plan.args.tma_res ? launch_variant<false, true, true, 1>(plan, stream) : launch_variant<false, true, false, 1>(plan, stream);
-  } else if (plan.args.row3) e = variant == 2 ? launch_variant<true, true, true>(plan, stream) : variant == 1 ? launch_variant<true, true, false>(plan, stream) : launch_variant<true, false, false>(plan, stream);
-  else e = variant == 2 ? launch_variant<false, true, true>(plan, stream) : variant == 1 ? launch_variant<false, true, false>(plan, stream) : launch_variant<false, false, false>(plan, stream);
+    if (plan.args.row3) e = plan.args.tma_res ? launch_variant<3, true, true, 1>(plan, stream) : launch_variant<3, true, false, 1>(plan, stream);
+    else e = plan.args.tma_res ? launch_variant<0, true, true, 1>(plan, stream) : launch_variant<0, true, false, 1>(plan, stream);
+  } else if (plan.args.row3) e = variant == 2 ? launch_variant<3, true, true>(plan, stream) : variant == 1 ? launch_variant<3, true, false>(plan, stream) : launch_variant<3, false, false>(plan, stream);
+  else e = variant == 2 ? launch_variant<0, true, true>(plan, stream) : variant == 1 ? launch_variant<0, true, false>(plan, stream) : launch_variant<0, false, false>(plan, stream);
   if (e) return e;
   WC_LAUNCH_CHECK();
   return 0;
