@@ -24,10 +24,11 @@ constexpr uint32_t kBarBytes = 512;   // 64 mbarriers: ring (2 x 8), accumulator
                                       // and 8 x 4 for the residual stream epilogue (index 32 + 4 * epilogue warp + slot)
 constexpr uint32_t kSmemBytes = kPipeBytes + kOutStageBytes + 1024 /*align*/ + kBarBytes + kVecBytes;   // = 227 KiB
 constexpr uint32_t kTmemCols = 512;
-// Row-segment mode (3x3, stride 1, dilation 1, tiles of 128 pixels of ONE image row): per (channel block, ky) one TMA
-// box of 130 pixels [x0-1, x0+129) is loaded once and the three kx taps read it through UMMA descriptors whose start is
-// shifted by kx*128 bytes (base_offset = kx keeps the 128-byte swizzle phase right) -> A traffic / 3.
-constexpr uint32_t kRowABytes = 18432;                       // 130*128 = 16640, padded to a multiple of 1024
+// Row-segment mode (stride 1, dilation 1, tiles of 128 pixels of ONE image row; ROWK = 3: 3 x 3 window, ROWK = 9: 1 x 9 window): per
+// (channel block, kernel row) one TMA box of 128 + nkx - 1 pixels [x0 - nkx/2, ..) is loaded once and the nkx horizontal taps read it
+// through UMMA descriptors whose start is shifted by kx*128 bytes (the 128-byte swizzle is a function of the absolute shared-memory
+// address, so the shifted start needs no fix-up) -> A traffic / nkx.
+constexpr uint32_t kRowABytes = 18432;                       // (128 + 9 - 1) * 128 = 17408, padded to a multiple of 1024
 
 template <int NC>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[NC]) {
@@ -690,7 +691,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps maps, const __grid_constant__ Ige
               const uint32_t bkx16 = p.wres ? static_cast<uint32_t>(nkb3) * bt16 : bt16;
 #pragma unroll
               for (int kx = 0; kx < nkx; ++kx) {
-                // window of 128 pixels starting kx pixels (kx*128 B = 8 descriptor units) into the 130-pixel segment; the
+                // window of 128 pixels starting kx pixels (kx*128 B = 8 descriptor units) into the row segment; the
                 // UMMA swizzle is a function of the absolute shared-memory address, so the shifted start needs no fix-up
 #pragma unroll
                 for (int k = 0; k < kIgemmBK / 16; ++k)
@@ -951,14 +952,14 @@ bool igemm_res_staging_fits(int BN, int row3, int nstages, int wres_bytes, int r
   return static_cast<uint32_t>(nstages) * stage + static_cast<uint32_t>(wres_bytes > 0 ? wres_bytes : 0) + kOutStageBytes <= kPipeBytes;
 }
 
-template <int ROW3, bool TMA_OUT, bool TMA_RES, int LEAN = 0>
+template <int ROWK, bool TMA_OUT, bool TMA_RES, int LEAN = 0>
 static int launch_variant(const IgemmPlan& plan, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<ROW3, TMA_OUT, TMA_RES, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    WC_CHECK_CUDA(cudaFuncSetAttribute(igemm_kernel<ROWK, TMA_OUT, TMA_RES, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  launch_k<1>(igemm_kernel<ROW3, TMA_OUT, TMA_RES, LEAN>, plan.grid, kThreads, kSmemBytes, stream, plan.maps, plan.args);
+  launch_k<1>(igemm_kernel<ROWK, TMA_OUT, TMA_RES, LEAN>, plan.grid, kThreads, kSmemBytes, stream, plan.maps, plan.args);
   return 0;
 }
 

@@ -112,7 +112,7 @@ int igemm_pick_bn(int N, long m_tiles);
 // stride-2 convolutions): element (b, y, x, c) of the view = act(b, y*ys + y0, x*xs + x0, c), view dims Hv x Wv.
 int igemm_make_amap(CUtensorMap* out, const Act& act, int tb, int th, int tw, int y0 = 0, int ys = 1, int x0 = 0,
                     int xs = 1, int Hv = -1, int Wv = -1);
-// Row-segment A map (box 64 ch x 130 pixels of one image row) for the row3 mode.
+// Row-segment A map (box 64 ch x (128 + nkx - 1) pixels of one image row) for the row-segment mode (nkx = 3 or 9).
 int igemm_make_rowseg_map(CUtensorMap* out, const Act& act, int nkx = 3);
 int igemm_make_bmap(CUtensorMap* out, const __nv_bfloat16* wpacked, int n_rows, int ktotal, int BN);
 // Output map for the TMA-store epilogue: channels [0, N) of an NHWC view, box (nc, qw, qh, qb), swizzle = nc*2 bytes.
