@@ -83,8 +83,13 @@ void apply_res_deep(IgemmPlan* plan, int N, bool res_candidate) {
   const bool mask_candidate = a.stream_mask == 2;
   a.stream_mask = 0;
   a.stream_res = 0;
+  static int max_kb = -1;   // WC_IGEMM_STREAM_MAX_KB: longest main loop (in 64-channel blocks) that still takes the stream epilogue
+  if (max_kb < 0) {
+    const char* e = getenv("WC_IGEMM_STREAM_MAX_KB");
+    max_kb = e ? atoi(e) : 12;
+  }
   if (deep < 2 || !lean_enabled() || !a.tma_store || a.row3 || a.wres || a.prelu || a.act == 3 || a.phase_n ||
-      a.total_kb > 12 || a.BN % 64 != 0 || N % a.BN != 0 || a.out_mode != kOutNHWC)
+      a.total_kb > max_kb || a.BN % 64 != 0 || N % a.BN != 0 || a.out_mode != kOutNHWC)
     return;
   if (a.res && !res_candidate) return;             // a residual that cannot go through TMA
   if (a.mask && !(mask_candidate && deep_mask)) return;
